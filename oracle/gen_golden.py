@@ -1,0 +1,198 @@
+"""Generate tests/golden/*.npz by EXECUTING the reference's own numpy / pure-python code.
+
+Run in the build container only (needs /root/reference, read-only):
+    python oracle/gen_golden.py
+The fixtures are committed; tests and the GPU box never touch /root/reference.
+
+What is executed unmodified from the reference:
+* baselines/ppo2/runner.py  Runner.run  (rollout bookkeeping, GAE :53-65, sf01 :69-74)
+* baselines/common/segment_tree.py  SumSegmentTree / MinSegmentTree
+* baselines/deepq/replay_buffer.py  PrioritizedReplayBuffer (loaded by file path because
+  deepq/__init__.py imports TensorFlow)
+`gym` is absent from the image, so an empty module is stubbed into sys.modules before
+importing.
+"""
+import importlib.util
+import os
+import random
+import sys
+import types
+
+import numpy as np
+
+REF = "/root/reference"
+OUT = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden")
+
+
+def _import_reference():
+    sys.modules.setdefault("gym", types.ModuleType("gym"))
+    sys.path.insert(0, REF)
+    from baselines.ppo2.runner import Runner                     # noqa
+    from baselines.common.segment_tree import SumSegmentTree, MinSegmentTree  # noqa
+    spec = importlib.util.spec_from_file_location(
+        "ref_replay_buffer", os.path.join(REF, "baselines/deepq/replay_buffer.py"))
+    rb = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(rb)
+    return Runner, SumSegmentTree, MinSegmentTree, rb
+
+
+class _Space:
+    def __init__(self, shape, dtype):
+        self.shape = shape
+        self.dtype = np.dtype(dtype)
+
+
+class FakeEnv:
+    """Replays pre-drawn rewards / dones; obs encode (t, env) so sf01 ordering is visible."""
+
+    def __init__(self, rew, done, ob_shape=(2,)):
+        self.rew, self.done = rew, done
+        self.num_envs = rew.shape[1]
+        self.observation_space = _Space(ob_shape, np.float32)
+        self.t = 0
+
+    def _obs(self):
+        o = np.zeros((self.num_envs,) + self.observation_space.shape, np.float32)
+        o[:, 0] = self.t
+        o[:, 1] = np.arange(self.num_envs)
+        return o
+
+    def reset(self):
+        return self._obs()
+
+    def step(self, actions):
+        r, d = self.rew[self.t], self.done[self.t]
+        self.t += 1
+        return self._obs(), r, d, [{} for _ in range(self.num_envs)]
+
+
+class FakeModel:
+    initial_state = None
+
+    def __init__(self, val):
+        self.val = val
+        self.t = 0
+
+    def step(self, obs, S=None, M=None):
+        n = obs.shape[0]
+        v = self.val[self.t]
+        self.t += 1
+        return np.full(n, self.t, np.int64), v, None, (v * 0.5).astype(np.float32)
+
+    def value(self, obs, S=None, M=None):
+        return self.val[self.t]
+
+
+def gen_gae(Runner, name, T, N, seed, p_done, nrollouts=1):
+    rng = np.random.RandomState(seed)
+    REW = rng.randn(T * nrollouts, N).astype(np.float32)
+    VAL = rng.randn(T * nrollouts + 1, N).astype(np.float32)
+    DONE = rng.rand(T * nrollouts, N) < p_done
+    env, model = FakeEnv(REW, DONE), FakeModel(VAL)
+    runner = Runner(env=env, model=model, nsteps=T, gamma=0.99, lam=0.95)
+    out = {}
+    for k in range(nrollouts):
+        first_dones = np.asarray(runner.dones, dtype=np.bool_).copy()
+        # model.value() is asked for VAL[(k+1)*T]; FakeModel.t points there after T steps
+        obs, returns, masks, actions, values, neglogpacs, states, epinfos = runner.run()
+        model.t = (k + 1) * T  # value() did not advance t; next rollout's first step reads VAL[(k+1)T]
+        out[f"obs{k}"], out[f"returns{k}"], out[f"masks{k}"] = obs, returns, masks
+        out[f"actions{k}"], out[f"values{k}"], out[f"neglogpacs{k}"] = actions, values, neglogpacs
+        out[f"first_dones{k}"] = first_dones
+        out[f"last_dones{k}"] = np.asarray(runner.dones, dtype=np.bool_).copy()
+    np.savez_compressed(os.path.join(OUT, name), REW=REW, VAL=VAL, DONE=DONE, T=T, N=N,
+                        gamma=0.99, lam=0.95, nrollouts=nrollouts, **out)
+    return out
+
+
+def gen_segment_tree(Sum, Min):
+    rng = np.random.RandomState(7)
+    cap = 64
+    s, m = Sum(cap), Min(cap)
+    ops = []          # (kind, a, b, result)
+    for step in range(600):
+        kind = rng.randint(0, 4)
+        if kind == 0 or step < 40:
+            i, v = int(rng.randint(0, cap)), float(rng.rand() * 3 + 1e-3)
+            s[i] = v
+            m[i] = v
+            ops.append((0, i, v, 0.0))
+        elif kind == 1:
+            a = int(rng.randint(0, cap - 1))
+            b = int(rng.randint(a + 1, cap + 1))
+            ops.append((1, a, b, float(s.sum(a, b))))
+            ops.append((2, a, b, float(m.min(a, b))))
+        elif kind == 2:
+            a = int(rng.randint(0, cap - 2))
+            b = -int(rng.randint(1, cap - a - 1))           # negative `end` wraps (segment_tree.py:71-72)
+            ops.append((1, a, b, float(s.sum(a, b))))
+        else:
+            p = float(rng.rand() * s.sum())
+            ops.append((3, 0, p, float(s.find_prefixsum_idx(p))))
+    arr = np.array(ops, dtype=np.float64)
+    np.savez_compressed(os.path.join(OUT, "segment_tree_trace.npz"), ops=arr, capacity=cap,
+                        final_sum=np.array(s._value, np.float64), final_min=np.array(m._value, np.float64))
+
+
+def gen_per(rb):
+    """PrioritizedReplayBuffer trace: adds (with ring wrap), samples with python's `random`
+    seeded so the uniforms can be regenerated, priority updates, more samples."""
+    size, alpha, batch = 100, 0.6, 16            # capacity rounds to 128; ring wraps at 100
+    buf = rb.PrioritizedReplayBuffer(size, alpha)
+    rng = np.random.RandomState(11)
+    trace = {}
+    nadd1 = 70
+    for i in range(nadd1):
+        buf.add(np.full((2,), i, np.float32), np.array(i % 3), float(i), np.full((2,), i + 1, np.float32), float(i % 7 == 0))
+    rounds = []
+    uni_all, idx_all, w_all, prio_all, beta_all, nstored = [], [], [], [], [], []
+    added = nadd1
+    for r in range(6):
+        beta = 0.4 + 0.1 * r
+        random.seed(1000 + r)
+        uniforms = [random.random() for _ in range(batch)]
+        random.seed(1000 + r)
+        out = buf.sample(batch, beta)
+        weights, idxes = out[5], out[6]
+        prios = (np.abs(rng.randn(batch)) + 1e-6) * (3.0 if r == 2 else 1.0)
+        buf.update_priorities(idxes, prios)
+        uni_all.append(uniforms); idx_all.append(idxes); w_all.append(weights)
+        prio_all.append(prios); beta_all.append(beta); nstored.append(len(buf))
+        nadd = 25
+        for i in range(nadd):                   # keeps adding -> wraps the ring on later rounds
+            buf.add(np.zeros(2, np.float32), np.array(0), 0.0, np.zeros(2, np.float32), 0.0)
+        added += nadd
+        rounds.append(nadd)
+    np.savez_compressed(os.path.join(OUT, "per_trace.npz"), size=size, alpha=alpha, batch=batch, nadd1=nadd1,
+                        adds_after_round=np.array(rounds), uniforms=np.array(uni_all, np.float64),
+                        idxes=np.array(idx_all, np.int64), weights=np.array(w_all, np.float64),
+                        priorities=np.array(prio_all, np.float64), betas=np.array(beta_all, np.float64),
+                        nstored=np.array(nstored), final_sum=np.array(buf._it_sum._value, np.float64),
+                        final_min=np.array(buf._it_min._value, np.float64), max_priority=buf._max_priority)
+
+    # the p_total quirk (replay_buffer.py:109): sum(0, len-1) drops the last stored element
+    b2 = rb.PrioritizedReplayBuffer(4, 1.0)
+    for i in range(4):
+        b2.add(np.zeros(1), np.array(0), 0.0, np.zeros(1), 0.0)
+    np.savez_compressed(os.path.join(OUT, "per_ptotal_quirk.npz"),
+                        p_total_used=b2._it_sum.sum(0, len(b2._storage) - 1), full_sum=b2._it_sum.sum())
+
+
+def main():
+    os.makedirs(OUT, exist_ok=True)
+    Runner, Sum, Min, rb = _import_reference()
+    small = gen_gae(Runner, "gae_small.npz", T=8, N=3, seed=1234, p_done=0.25)
+    # SURVEY.md section 8c vector (regenerated here; assert it reproduces)
+    adv0 = (small["returns0"] - small["values0"])[:8]
+    ref_adv0 = np.array([-1.2307085, 1.5043753, 1.2574286, -2.3858485, 0.8286112, -1.1049898, 1.3270301, 0.9890473], np.float32)
+    assert np.allclose(adv0, ref_adv0, atol=2e-6), (adv0, ref_adv0)
+    gen_gae(Runner, "gae_medium.npz", T=128, N=64, seed=5, p_done=0.02)
+    gen_gae(Runner, "gae_two_rollouts.npz", T=16, N=5, seed=9, p_done=0.2, nrollouts=2)
+    gen_gae(Runner, "gae_alldone.npz", T=6, N=4, seed=3, p_done=1.1)
+    gen_segment_tree(Sum, Min)
+    gen_per(rb)
+    print("golden fixtures written to", OUT)
+
+
+if __name__ == "__main__":
+    main()
