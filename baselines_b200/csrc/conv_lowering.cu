@@ -1,0 +1,225 @@
+// Lowering of NHWC convolutions (tf.nn.conv2d, a2c/utils.py:56 of the reference) onto the tcgen05 GEMM:
+//   im2col  : patches -> cols[B*OH*OW, rf*rf*C] fp16, K ordered (ky, kx, c) = HWIO weight flatten order
+//             - uint8 source: the uint8->fp16 cast of models.py:19 is fused into this first load (the /255
+//               is folded into the fp16 copy of the c1 weights), and the minibatch gather of
+//               ppo2/ppo2.py:165 is fused too (src_idx picks samples straight out of the rollout buffer)
+//   col2im  : dcols -> dx (gather form: every input element sums the taps that touched it), fused with
+//             the activation derivative of the layer below
+//   colsum  : bias gradients
+// All HBM-bound: 16-byte vector accesses, consecutive lanes on consecutive 16 B chunks.
+#include "common.cuh"
+
+namespace b200rl {
+
+struct ConvGeom {
+  int H, W, C, rf, stride, OH, OW, pad_t, pad_l;   // pad_* = 0 for VALID
+};
+
+// one thread = one 16 B output chunk (8 fp16) of cols
+template <typename SrcT>
+__global__ void __launch_bounds__(256)
+im2col_kernel(const SrcT* __restrict__ x, const long long* __restrict__ src_idx, __half* __restrict__ cols,
+              long long B, ConvGeom g) {
+  const int seg = g.rf * g.C;                 // contiguous elements per (pixel, ky)
+  const int chunks_per_seg = seg / 8;
+  const long long K = (long long)g.rf * seg;
+  const long long total = B * g.OH * g.OW * g.rf * chunks_per_seg;
+  for (long long id = (long long)blockIdx.x * blockDim.x + threadIdx.x; id < total;
+       id += (long long)gridDim.x * blockDim.x) {
+    const int j = (int)(id % chunks_per_seg);
+    long long t = id / chunks_per_seg;
+    const int ky = (int)(t % g.rf);
+    t /= g.rf;                                 // t = output pixel row of cols
+    const int ox = (int)(t % g.OW);
+    long long t2 = t / g.OW;
+    const int oy = (int)(t2 % g.OH);
+    const long long b = t2 / g.OH;
+    const long long sb = src_idx ? src_idx[b] : b;
+    const int y = oy * g.stride + ky - g.pad_t;
+    const int e0 = j * 8;                      // first element of this chunk inside the segment
+    const int x_first = ox * g.stride - g.pad_l;
+    __half out[8];
+    const bool row_ok = (y >= 0 && y < g.H);
+    const int kx0 = e0 / g.C, kx1 = (e0 + 7) / g.C;
+    const bool all_in = row_ok && (x_first + kx0 >= 0) && (x_first + kx1 < g.W);
+    const SrcT* src = x + ((sb * g.H + y) * g.W + x_first) * (long long)g.C + e0;
+    const bool vec_ok = (sizeof(SrcT) != 1) || ((reinterpret_cast<uintptr_t>(src) & 7) == 0);
+    if (all_in && vec_ok) {
+      if (sizeof(SrcT) == 1) {
+        const uint2 q = *reinterpret_cast<const uint2*>(src);
+        const uint8_t* bp = reinterpret_cast<const uint8_t*>(&q);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) out[i] = __ushort2half_rn((unsigned short)bp[i]);
+      } else {
+        *reinterpret_cast<uint4*>(out) = *reinterpret_cast<const uint4*>(src);
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int el = e0 + i;
+        const int xx = x_first + el / g.C;
+        float v = 0.0f;
+        if (row_ok && xx >= 0 && xx < g.W) {
+          const SrcT s = x[((sb * g.H + y) * g.W + xx) * (long long)g.C + (el % g.C)];
+          v = (sizeof(SrcT) == 1) ? (float)(*reinterpret_cast<const uint8_t*>(&s))
+                                  : __half2float(*reinterpret_cast<const __half*>(&s));
+        }
+        out[i] = __float2half_rn(v);
+      }
+    }
+    *reinterpret_cast<uint4*>(cols + t * K + (long long)ky * seg + e0) = *reinterpret_cast<const uint4*>(out);
+  }
+}
+
+// one thread = 8 channels of one input pixel; dx = act'(saved) * sum over taps
+__global__ void __launch_bounds__(256)
+col2im_kernel(const __half* __restrict__ dcols, const __half* __restrict__ saved, __half* __restrict__ dx,
+              long long B, ConvGeom g, int act) {
+  const int cg = g.C / 8;
+  const long long K = (long long)g.rf * g.rf * g.C;
+  const long long total = B * g.H * g.W * cg;
+  for (long long id = (long long)blockIdx.x * blockDim.x + threadIdx.x; id < total;
+       id += (long long)gridDim.x * blockDim.x) {
+    const int c0 = (int)(id % cg) * 8;
+    long long t = id / cg;
+    const int xx = (int)(t % g.W);
+    long long t2 = t / g.W;
+    const int y = (int)(t2 % g.H);
+    const long long b = t2 / g.H;
+    float acc[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc[i] = 0.0f;
+    for (int ky = 0; ky < g.rf; ++ky) {
+      const int yy = y + g.pad_t - ky;
+      if (yy < 0 || (yy % g.stride) != 0) continue;
+      const int oy = yy / g.stride;
+      if (oy >= g.OH) continue;
+      for (int kx = 0; kx < g.rf; ++kx) {
+        const int xs = xx + g.pad_l - kx;
+        if (xs < 0 || (xs % g.stride) != 0) continue;
+        const int ox = xs / g.stride;
+        if (ox >= g.OW) continue;
+        const __half* src = dcols + ((b * g.OH + oy) * g.OW + ox) * K + ((long long)ky * g.rf + kx) * g.C + c0;
+        const uint4 q = *reinterpret_cast<const uint4*>(src);
+        const __half2* h = reinterpret_cast<const __half2*>(&q);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const float2 f = __half22float2(h[i]);
+          acc[2 * i] += f.x;
+          acc[2 * i + 1] += f.y;
+        }
+      }
+    }
+    const long long o = ((b * g.H + y) * g.W + xx) * (long long)g.C + c0;
+    if (saved != nullptr && act != 0) {
+      const uint4 q = *reinterpret_cast<const uint4*>(saved + o);
+      const __half* h = reinterpret_cast<const __half*>(&q);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const float s = __half2float(h[i]);
+        acc[i] *= (act == 1) ? (s > 0.0f ? 1.0f : 0.0f) : (1.0f - s * s);
+      }
+    }
+    __half out[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) out[i] = __float2half_rn(acc[i]);
+    *reinterpret_cast<uint4*>(dx + o) = *reinterpret_cast<const uint4*>(out);
+  }
+}
+
+// db[c] += alpha * sum_rows dz[row, c]
+__global__ void __launch_bounds__(256)
+colsum_kernel(const __half* __restrict__ dz, float* __restrict__ db, long long rows, int C, long long ld, float alpha,
+              int rows_per_block) {
+  __shared__ float red[256];
+  const int cw = C < 256 ? C : 256;
+  const int groups = 256 / cw;
+  const int tid = threadIdx.x;
+  const int grp = tid / cw;
+  const int lc = tid % cw;
+  const long long r0 = (long long)blockIdx.x * rows_per_block;
+  const long long r1 = min(rows, r0 + rows_per_block);
+  for (int cbase = 0; cbase < C; cbase += cw) {
+    const int c = cbase + lc;
+    float acc = 0.0f;
+    if (grp < groups && c < C) {
+      for (long long r = r0 + grp; r < r1; r += groups) acc += __half2float(dz[r * ld + c]);
+    }
+    red[tid] = acc;
+    __syncthreads();
+    if (tid < cw && cbase + tid < C) {
+      float s = 0.0f;
+      for (int gI = 0; gI < groups; ++gI) s += red[gI * cw + tid];
+      atomicAdd(db + cbase + tid, s * alpha);
+    }
+    __syncthreads();
+  }
+}
+
+static int grid_for(long long total, int threads) {
+  long long blocks = (total + threads - 1) / threads;
+  const long long cap = 148LL * 32;
+  return (int)(blocks < cap ? (blocks < 1 ? 1 : blocks) : cap);
+}
+
+static int fill_geom(ConvGeom& g, int H, int W, int C, int rf, int stride, int same_pad) {
+  g.H = H; g.W = W; g.C = C; g.rf = rf; g.stride = stride;
+  if (same_pad) {
+    g.OH = (H + stride - 1) / stride;
+    g.OW = (W + stride - 1) / stride;
+    int ph = (g.OH - 1) * stride + rf - H; if (ph < 0) ph = 0;
+    int pw = (g.OW - 1) * stride + rf - W; if (pw < 0) pw = 0;
+    g.pad_t = ph / 2; g.pad_l = pw / 2;      // TF 'SAME': extra pixel goes bottom/right
+  } else {
+    g.OH = (H - rf) / stride + 1;
+    g.OW = (W - rf) / stride + 1;
+    g.pad_t = g.pad_l = 0;
+  }
+  return (g.OH > 0 && g.OW > 0) ? 0 : -1;
+}
+
+int im2col_impl(const void* x, int src_is_u8, const long long* src_idx, void* cols, long long B, int H, int W, int C,
+                int rf, int stride, int same_pad, cudaStream_t stream) {
+  B200RL_REQUIRE(x && cols && B > 0, "im2col: bad args");
+  ConvGeom g;
+  B200RL_REQUIRE(fill_geom(g, H, W, C, rf, stride, same_pad) == 0, "im2col: empty output");
+  B200RL_REQUIRE((rf * C) % 8 == 0, "im2col: rf*C must be a multiple of 8 (got %d)", rf * C);
+  if (src_is_u8)
+    B200RL_REQUIRE((stride * C) % 8 == 0 && (W * C) % 8 == 0 && (reinterpret_cast<uintptr_t>(x) & 7) == 0,
+                   "im2col(u8): stride*C and W*C must be multiples of 8");
+  else
+    B200RL_REQUIRE(C % 8 == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0, "im2col(f16): C must be a multiple of 8");
+  const long long total = B * g.OH * g.OW * rf * ((rf * C) / 8);
+  const int grid = grid_for(total, 256);
+  if (src_is_u8)
+    im2col_kernel<uint8_t><<<grid, 256, 0, stream>>>(reinterpret_cast<const uint8_t*>(x), src_idx,
+                                                     reinterpret_cast<__half*>(cols), B, g);
+  else
+    im2col_kernel<__half><<<grid, 256, 0, stream>>>(reinterpret_cast<const __half*>(x), src_idx,
+                                                    reinterpret_cast<__half*>(cols), B, g);
+  return check_launch("im2col_kernel");
+}
+
+int col2im_impl(const void* dcols, const void* saved, void* dx, long long B, int H, int W, int C, int rf, int stride,
+                int same_pad, int act, cudaStream_t stream) {
+  B200RL_REQUIRE(dcols && dx && B > 0, "col2im: bad args");
+  ConvGeom g;
+  B200RL_REQUIRE(fill_geom(g, H, W, C, rf, stride, same_pad) == 0, "col2im: empty output");
+  B200RL_REQUIRE(C % 8 == 0, "col2im: C must be a multiple of 8");
+  const long long total = B * H * W * (C / 8);
+  col2im_kernel<<<grid_for(total, 256), 256, 0, stream>>>(reinterpret_cast<const __half*>(dcols),
+                                                          reinterpret_cast<const __half*>(saved),
+                                                          reinterpret_cast<__half*>(dx), B, g, act);
+  return check_launch("col2im_kernel");
+}
+
+int colsum_impl(const void* dz, float* db, long long rows, int C, long long ld, float alpha, cudaStream_t stream) {
+  B200RL_REQUIRE(dz && db && rows > 0 && C > 0, "colsum: bad args");
+  long long rpb = (rows + 148LL * 8 - 1) / (148LL * 8);
+  if (rpb < 64) rpb = 64;
+  const int grid = (int)((rows + rpb - 1) / rpb);
+  colsum_kernel<<<grid, 256, 0, stream>>>(reinterpret_cast<const __half*>(dz), db, rows, C, ld, alpha, (int)rpb);
+  return check_launch("colsum_kernel");
+}
+
+}  // namespace b200rl

@@ -1,0 +1,182 @@
+// Flat-buffer optimiser kernels (all HBM-bound; float4 accesses, grid = multiple of 148 SMs).
+//   sumsq            : sum of squares of the flat gradient -> device double (tf.clip_by_global_norm,
+//                      ppo2/model.py:105-107), or per-tensor norms (tf.clip_by_norm, deepq/build_graph.py:416-421)
+//   clip_adam        : g *= clip/max(||g||, clip) fused with TF-Adam exactly as pinned by the reference's
+//                      numpy statement baselines/common/mpi_adam.py:37-42:
+//                          a = lr*sqrt(1-b2^t)/(1-b1^t); m = b1 m + (1-b1) g; v = b2 v + (1-b2) g*g;
+//                          p -= a*m/(sqrt(v)+eps)            (eps OUTSIDE the bias correction)
+//                      28 B of traffic per parameter.  The norm is read from device memory: no host sync.
+//   cast / transpose : refresh the fp16 operand copies (W [in,out] for dgrad, W^T [out,in] for forward)
+#include "common.cuh"
+
+namespace b200rl {
+
+__global__ void __launch_bounds__(256)
+sumsq_kernel(const float* __restrict__ g, long long n, double* __restrict__ out) {
+  __shared__ double red[8];
+  double acc = 0.0;
+  const long long n4 = n >> 2;
+  const float4* g4 = reinterpret_cast<const float4*>(g);
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+    const float4 q = g4[i];
+    acc += (double)q.x * q.x + (double)q.y * q.y + (double)q.z * q.z + (double)q.w * q.w;
+  }
+  if (blockIdx.x == 0 && threadIdx.x < (n & 3)) {
+    const float x = g[(n4 << 2) + threadIdx.x];
+    acc += (double)x * x;
+  }
+  acc = warp_sum_d(acc);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double s = 0.0;
+    for (int w = 0; w < 8; ++w) s += red[w];
+    atomicAdd(out, s);
+  }
+}
+
+// segment s covers [seg_off[s], seg_off[s+1]); one block per (segment, slice)
+__global__ void __launch_bounds__(256)
+seg_sumsq_kernel(const float* __restrict__ g, const long long* __restrict__ seg_off, double* __restrict__ out) {
+  __shared__ double red[8];
+  const int s = blockIdx.x;
+  const long long a = seg_off[s], b = seg_off[s + 1];
+  double acc = 0.0;
+  for (long long i = a + (long long)blockIdx.y * blockDim.x + threadIdx.x; i < b; i += (long long)gridDim.y * blockDim.x) {
+    const float x = g[i];
+    acc += (double)x * x;
+  }
+  acc = warp_sum_d(acc);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+    for (int w = 0; w < 8; ++w) t += red[w];
+    atomicAdd(out + s, t);
+  }
+}
+
+struct AdamArgs {
+  float lr_t;       // lr*sqrt(1-b2^t)/(1-b1^t), computed on the host from the step counter
+  float beta1, beta2, eps;
+  float clip;       // <= 0 : no clipping
+};
+
+__device__ __forceinline__ void adam1(float& p, float g, float& m, float& v, const AdamArgs& a) {
+  m = a.beta1 * m + (1.0f - a.beta1) * g;
+  v = a.beta2 * v + (1.0f - a.beta2) * (g * g);
+  p = p + (-a.lr_t) * m / (sqrtf(v) + a.eps);
+}
+
+// mode 0: one global norm in sumsq[0]; mode 1: per-segment norms (seg_id gives the segment of each 4-block)
+__global__ void __launch_bounds__(256)
+clip_adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
+                 long long n, AdamArgs a, const double* __restrict__ sumsq, const long long* __restrict__ seg_off,
+                 int nseg) {
+  float gscale = 1.0f;
+  if (a.clip > 0.0f && seg_off == nullptr) {
+    const float norm = (float)sqrt(sumsq[0]);
+    gscale = a.clip / fmaxf(norm, a.clip);
+  }
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    float sc = gscale;
+    if (a.clip > 0.0f && seg_off != nullptr) {
+      int lo = 0, hi = nseg;                       // segment of element i (binary search, nseg is tiny)
+      while (hi - lo > 1) {
+        const int mid = (lo + hi) >> 1;
+        if (seg_off[mid] <= i) lo = mid; else hi = mid;
+      }
+      const float norm = (float)sqrt(sumsq[lo]);
+      sc = a.clip / fmaxf(norm, a.clip);
+    }
+    float pp = p[i], mm = m[i], vv = v[i];
+    adam1(pp, g[i] * sc, mm, vv, a);
+    p[i] = pp; m[i] = mm; v[i] = vv;
+  }
+}
+
+// dst16[r, c] = src[r, c]*scale (row pitch ld_dst), and optionally dstT16[c, r] = src[r, c]*scale (pitch ld_t)
+__global__ void __launch_bounds__(256)
+cast_transpose_kernel(const float* __restrict__ src, int R, int C, __half* __restrict__ dst, long long ld_dst,
+                      __half* __restrict__ dstT, long long ld_t, float scale) {
+  __shared__ float tile[32][33];
+  const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;   // 32 x 8
+  for (int i = ty; i < 32; i += 8) {
+    const int r = r0 + i, c = c0 + tx;
+    float x = 0.0f;
+    if (r < R && c < C) {
+      x = src[(long long)r * C + c] * scale;
+      if (dst) dst[(long long)r * ld_dst + c] = __float2half_rn(x);
+    }
+    tile[i][tx] = x;
+  }
+  __syncthreads();
+  if (dstT) {
+    for (int i = ty; i < 32; i += 8) {
+      const int c = c0 + i, r = r0 + tx;
+      if (r < R && c < C) dstT[(long long)c * ld_t + r] = __float2half_rn(tile[tx][i]);
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256)
+cast_f32_f16_kernel(const float* __restrict__ src, __half* __restrict__ dst, long long rows, int cols,
+                    long long ld_src, long long ld_dst, float scale) {
+  const long long total = rows * cols;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long r = i / cols;
+    const int c = (int)(i % cols);
+    dst[r * ld_dst + c] = __float2half_rn(src[r * ld_src + c] * scale);
+  }
+}
+
+static int grid_for(long long n, int threads, int per_sm) {
+  long long blocks = (n + threads - 1) / threads;
+  const long long cap = 148LL * per_sm;
+  return (int)(blocks < 1 ? 1 : (blocks < cap ? blocks : cap));
+}
+
+int sumsq_impl(const float* g, long long n, double* out, cudaStream_t stream) {
+  B200RL_REQUIRE(g && out && n > 0, "sumsq: bad args");
+  B200RL_REQUIRE((reinterpret_cast<uintptr_t>(g) & 15) == 0, "sumsq: gradient buffer must be 16 B aligned");
+  cudaMemsetAsync(out, 0, sizeof(double), stream);
+  sumsq_kernel<<<grid_for(n / 4 + 1, 256, 4), 256, 0, stream>>>(g, n, out);
+  return check_launch("sumsq_kernel");
+}
+
+int seg_sumsq_impl(const float* g, const long long* seg_off, int nseg, double* out, cudaStream_t stream) {
+  B200RL_REQUIRE(g && seg_off && out && nseg > 0, "seg_sumsq: bad args");
+  cudaMemsetAsync(out, 0, sizeof(double) * nseg, stream);
+  seg_sumsq_kernel<<<dim3(nseg, 16), 256, 0, stream>>>(g, seg_off, out);
+  return check_launch("seg_sumsq_kernel");
+}
+
+int clip_adam_impl(float* p, const float* g, float* m, float* v, long long n, float lr_t, float beta1, float beta2,
+                   float eps, float clip, const double* sumsq, const long long* seg_off, int nseg,
+                   cudaStream_t stream) {
+  B200RL_REQUIRE(p && g && m && v && n > 0, "clip_adam: bad args");
+  B200RL_REQUIRE(clip <= 0.0f || sumsq != nullptr, "clip_adam: clipping needs the device sumsq");
+  AdamArgs a{lr_t, beta1, beta2, eps, clip};
+  clip_adam_kernel<<<grid_for(n, 256, 8), 256, 0, stream>>>(p, g, m, v, n, a, sumsq, seg_off, nseg);
+  return check_launch("clip_adam_kernel");
+}
+
+int cast_transpose_impl(const float* src, int R, int C, void* dst, long long ld_dst, void* dstT, long long ld_t,
+                        float scale, cudaStream_t stream) {
+  B200RL_REQUIRE(src && R > 0 && C > 0 && (dst || dstT), "cast_transpose: bad args");
+  dim3 grid(ceil_div(C, 32), ceil_div(R, 32));
+  cast_transpose_kernel<<<grid, 256, 0, stream>>>(src, R, C, reinterpret_cast<__half*>(dst), ld_dst,
+                                                  reinterpret_cast<__half*>(dstT), ld_t, scale);
+  return check_launch("cast_transpose_kernel");
+}
+
+int cast_f32_f16_impl(const float* src, void* dst, long long rows, int cols, long long ld_src, long long ld_dst,
+                      float scale, cudaStream_t stream) {
+  B200RL_REQUIRE(src && dst && rows > 0 && cols > 0, "cast: bad args");
+  cast_f32_f16_kernel<<<grid_for(rows * cols, 256, 8), 256, 0, stream>>>(src, reinterpret_cast<__half*>(dst), rows,
+                                                                         cols, ld_src, ld_dst, scale);
+  return check_launch("cast_f32_f16_kernel");
+}
+
+}  // namespace b200rl

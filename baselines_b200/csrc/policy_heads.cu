@@ -1,0 +1,342 @@
+// Row-wise policy-head kernels (one thread per sample; all HBM/latency bound, no reuse):
+//   * act path  (PolicyWithValue.step, common/policies.py:77-96): Gumbel-max sample
+//     (distributions.py:199-201), neglogp (:164-183) / DiagGaussian sample+neglogp (:238-248)
+//   * train path (ppo2/model.py:57-91): clipped-surrogate + clipped-value + entropy loss, its five
+//     statistics, and the hand-derived gradient w.r.t. the head outputs (logits / mean, value), written
+//     as fp16 in "sum" scaling (the 1/M of tf.reduce_mean is applied as alpha in the wgrad epilogues so
+//     fp16 gradients do not underflow)
+//   * per-minibatch advantage moments (ppo2/model.py:136-139)
+// The rollout arrays are gathered in place through src_idx (no materialised minibatch, ppo2.py:165).
+#include "common.cuh"
+
+namespace b200rl {
+
+// ---------------------------------------------------------------- Philox4x32-10 (counter based)
+__device__ __forceinline__ void philox_round(uint32_t (&c)[4], uint32_t k0, uint32_t k1) {
+  const uint32_t hi0 = __umulhi(0xD2511F53u, c[0]), lo0 = 0xD2511F53u * c[0];
+  const uint32_t hi1 = __umulhi(0xCD9E8D57u, c[2]), lo1 = 0xCD9E8D57u * c[2];
+  const uint32_t n0 = hi1 ^ c[1] ^ k0, n1 = lo1, n2 = hi0 ^ c[3] ^ k1, n3 = lo0;
+  c[0] = n0; c[1] = n1; c[2] = n2; c[3] = n3;
+}
+__device__ __forceinline__ void philox4(uint64_t seed, uint64_t row, uint32_t ctr, uint32_t stream,
+                                        uint32_t (&out)[4]) {
+  uint32_t c[4] = {(uint32_t)row, (uint32_t)(row >> 32), ctr, stream};
+  uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
+#pragma unroll
+  for (int i = 0; i < 10; ++i) {
+    philox_round(c, k0, k1);
+    k0 += 0x9E3779B9u;
+    k1 += 0xBB67AE85u;
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) out[i] = c[i];
+}
+__device__ __forceinline__ float u01_open(uint32_t x) { return ((float)(x >> 8) + 0.5f) * (1.0f / 16777216.0f); }
+
+// ---------------------------------------------------------------- categorical: act
+__global__ void __launch_bounds__(256)
+cat_step_kernel(const float* __restrict__ logits, long long ld, int nA, const float* __restrict__ vpred, long long ldv,
+                const float* __restrict__ uniforms, uint64_t seed, uint64_t offset, long long* __restrict__ actions,
+                float* __restrict__ values, float* __restrict__ neglogp, long long B) {
+  const long long b = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  const float* l = logits + b * ld;
+  float m = -INFINITY;
+  for (int j = 0; j < nA; ++j) m = fmaxf(m, l[j]);
+  float z = 0.0f;
+  for (int j = 0; j < nA; ++j) z += expf(l[j] - m);
+  float best = -INFINITY;
+  int a = 0;
+  uint32_t rnd[4];
+  for (int j = 0; j < nA; ++j) {
+    float u;
+    if (uniforms) {
+      u = uniforms[b * nA + j];
+    } else {
+      if ((j & 3) == 0) philox4(seed, (uint64_t)b, (uint32_t)(j >> 2), (uint32_t)offset, rnd);
+      u = u01_open(rnd[j & 3]);
+    }
+    const float s = l[j] - logf(-logf(u));
+    if (s > best) { best = s; a = j; }      // first max wins (tf.argmax)
+  }
+  actions[b] = a;
+  neglogp[b] = (m + logf(z)) - l[a];
+  values[b] = vpred[b * ldv];
+}
+
+// ---------------------------------------------------------------- gaussian: act
+__global__ void __launch_bounds__(256)
+gauss_step_kernel(const float* __restrict__ mean, long long ld, const float* __restrict__ logstd, int d,
+                  const float* __restrict__ vpred, long long ldv, const float* __restrict__ normals, uint64_t seed,
+                  uint64_t offset, float* __restrict__ actions, float* __restrict__ values,
+                  float* __restrict__ neglogp, long long B) {
+  const long long b = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  float q = 0.0f, sl = 0.0f;
+  uint32_t rnd[4];
+  float z0 = 0.f, z1 = 0.f;
+  for (int j = 0; j < d; ++j) {
+    float n;
+    if (normals) {
+      n = normals[b * d + j];
+    } else {
+      if ((j & 1) == 0) {
+        if ((j & 3) == 0) philox4(seed, (uint64_t)b, (uint32_t)(j >> 2), (uint32_t)offset, rnd);
+        const float u1 = u01_open(rnd[j & 3]), u2 = u01_open(rnd[(j & 3) + 1]);
+        const float r = sqrtf(-2.0f * logf(u1));
+        z0 = r * cospif(2.0f * u2);
+        z1 = r * sinpif(2.0f * u2);
+      }
+      n = (j & 1) ? z1 : z0;
+    }
+    const float mu = mean[b * ld + j], ls = logstd[j];
+    const float sd = expf(ls);
+    const float x = mu + sd * n;                     // distributions.py:247-248
+    actions[b * d + j] = x;
+    const float t = (x - mu) / sd;
+    q += t * t;
+    sl += ls;
+  }
+  neglogp[b] = 0.5f * q + 0.5f * 1.8378770664093453f * (float)d + sl;   // log(2*pi)
+  values[b] = vpred[b * ldv];
+}
+
+// ---------------------------------------------------------------- advantage moments (two pass, one block)
+__global__ void __launch_bounds__(1024)
+adv_stats_kernel(const float* __restrict__ returns, const float* __restrict__ values,
+                 const long long* __restrict__ src_idx, long long M, double* __restrict__ out) {
+  __shared__ double red[32];
+  __shared__ double s_mean;
+  const int tid = threadIdx.x;
+  double acc = 0.0;
+  for (long long i = tid; i < M; i += blockDim.x) {
+    const long long s = src_idx ? src_idx[i] : i;
+    acc += (double)__fsub_rn(returns[s], values[s]);          // float32 subtraction (model.py:136)
+  }
+  acc = warp_sum_d(acc);
+  if ((tid & 31) == 0) red[tid >> 5] = acc;
+  __syncthreads();
+  if (tid < 32) {
+    double v = (tid < (blockDim.x >> 5)) ? red[tid] : 0.0;
+    v = warp_sum_d(v);
+    if (tid == 0) s_mean = v / (double)M;
+  }
+  __syncthreads();
+  const double mean = s_mean;
+  acc = 0.0;
+  for (long long i = tid; i < M; i += blockDim.x) {
+    const long long s = src_idx ? src_idx[i] : i;
+    const double dlt = (double)__fsub_rn(returns[s], values[s]) - mean;
+    acc += dlt * dlt;
+  }
+  acc = warp_sum_d(acc);
+  __syncthreads();
+  if ((tid & 31) == 0) red[tid >> 5] = acc;
+  __syncthreads();
+  if (tid < 32) {
+    double v = (tid < (blockDim.x >> 5)) ? red[tid] : 0.0;
+    v = warp_sum_d(v);
+    if (tid == 0) {
+      out[0] = mean;
+      out[1] = sqrt(v / (double)M);                              // population std (numpy default ddof=0)
+    }
+  }
+}
+
+// ---------------------------------------------------------------- shared pieces of the PPO loss
+struct PpoCommon {
+  const long long* src_idx;
+  const float* returns;
+  const float* old_values;
+  const float* old_neglogp;
+  const double* adv_stats;        // {mean, std}
+  float cliprange, ent_coef, vf_coef;
+  double* stats;                  // [5] sums: pg, vf, entropy, approxkl, clipfrac
+};
+
+__device__ __forceinline__ void block_accumulate5(double (&v)[5], double* stats) {
+  __shared__ double red[5][8];
+  const int tid = threadIdx.x;
+#pragma unroll
+  for (int k = 0; k < 5; ++k) {
+    const double s = warp_sum_d(v[k]);
+    if ((tid & 31) == 0) red[k][tid >> 5] = s;
+  }
+  __syncthreads();
+  if (tid < 5) {
+    double s = 0.0;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) s += red[tid][w];
+    atomicAdd(stats + tid, s);
+  }
+}
+
+// value-loss part: returns dL/dv (sum scaling, already times vf_coef) and the per-sample loss
+__device__ __forceinline__ float value_loss_grad(float v, float oldv, float R, float clip, float vf_coef,
+                                                 float& vloss) {
+  const float dv = v - oldv;
+  const float vclipped = oldv + fminf(fmaxf(dv, -clip), clip);
+  const float l1 = (v - R) * (v - R), l2 = (vclipped - R) * (vclipped - R);
+  vloss = 0.5f * fmaxf(l1, l2);
+  float g;
+  if (l1 >= l2) g = (v - R);                                       // tf.maximum: ties -> first argument
+  else g = (dv >= -clip && dv <= clip) ? (vclipped - R) : 0.0f;    // clip_by_value passes grad inside [lo, hi]
+  return vf_coef * g;
+}
+
+// policy-gradient part: returns dL/dneglogp (sum scaling)
+__device__ __forceinline__ float pg_loss_grad(float nlp, float oldnlp, float adv, float clip, float& pgloss,
+                                              float& kl, float& clipped) {
+  const float ratio = expf(oldnlp - nlp);
+  const float rc = fminf(fmaxf(ratio, 1.0f - clip), 1.0f + clip);
+  const float p1 = -adv * ratio, p2 = -adv * rc;
+  pgloss = fmaxf(p1, p2);
+  const float dn = nlp - oldnlp;
+  kl = 0.5f * dn * dn;
+  clipped = (fabsf(ratio - 1.0f) > clip) ? 1.0f : 0.0f;
+  // d(-A*ratio)/dnlp = A*ratio ; the clipped branch only passes inside the clip interval
+  if (p1 >= p2) return adv * ratio;
+  return (ratio >= 1.0f - clip && ratio <= 1.0f + clip) ? adv * ratio : 0.0f;
+}
+
+// ---------------------------------------------------------------- categorical: loss + gradient
+__global__ void __launch_bounds__(256)
+cat_loss_kernel(const float* __restrict__ logits, long long ld, int nA, const float* __restrict__ vpred,
+                long long ldv, const long long* __restrict__ actions, PpoCommon pc, __half* __restrict__ dlogits,
+                long long ld_dl, __half* __restrict__ dv, long long ld_dv, long long B) {
+  const long long b = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  double st[5] = {0, 0, 0, 0, 0};
+  if (b < B) {
+    const long long s = pc.src_idx ? pc.src_idx[b] : b;
+    const float* l = logits + b * ld;
+    float m = -INFINITY;
+    for (int j = 0; j < nA; ++j) m = fmaxf(m, l[j]);
+    float z = 0.0f;
+    for (int j = 0; j < nA; ++j) z += expf(l[j] - m);
+    const float logz = logf(z);
+    float H = 0.0f;                                    // distributions.py:193-198
+    for (int j = 0; j < nA; ++j) {
+      const float a0 = l[j] - m;
+      H += (expf(a0) / z) * (logz - a0);
+    }
+    const int a = (int)actions[s];
+    const float nlp = (m + logz) - l[a];
+    const float R = pc.returns[s], oldv = pc.old_values[s];
+    const float adv_raw = __fsub_rn(R, oldv);
+    const float adv = (float)(((double)adv_raw - pc.adv_stats[0]) / (pc.adv_stats[1] + 1e-8));
+    float pgl, kl, cf, vl;
+    const float g_nlp = pg_loss_grad(nlp, pc.old_neglogp[s], adv, pc.cliprange, pgl, kl, cf);
+    const float g_v = value_loss_grad(vpred[b * ldv], oldv, R, pc.cliprange, pc.vf_coef, vl);
+    for (int j = 0; j < nA; ++j) {
+      const float a0 = l[j] - m;
+      const float pj = expf(a0) / z;
+      const float logpj = a0 - logz;
+      // d nlp/dl_j = p_j - 1{j=a};  d(-ent_coef*H)/dl_j = ent_coef * p_j * (log p_j + H)
+      const float g = g_nlp * (pj - (j == a ? 1.0f : 0.0f)) + pc.ent_coef * pj * (logpj + H);
+      dlogits[b * ld_dl + j] = __float2half_rn(g);
+    }
+    dv[b * ld_dv] = __float2half_rn(g_v);
+    st[0] = pgl; st[1] = vl; st[2] = H; st[3] = kl; st[4] = cf;
+  }
+  block_accumulate5(st, pc.stats);
+}
+
+// ---------------------------------------------------------------- gaussian: loss + gradient
+__global__ void __launch_bounds__(256)
+gauss_loss_kernel(const float* __restrict__ mean, long long ld, const float* __restrict__ logstd, int d,
+                  const float* __restrict__ vpred, long long ldv, const float* __restrict__ actions, PpoCommon pc,
+                  __half* __restrict__ dmean, long long ld_dm, __half* __restrict__ dv, long long ld_dv,
+                  float* __restrict__ dlogstd, float inv_M, long long B) {
+  extern __shared__ float s_dls[];                   // [d] block partial of dL/dlogstd
+  for (int j = threadIdx.x; j < d; j += blockDim.x) s_dls[j] = 0.0f;
+  __syncthreads();
+  const long long b = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  double st[5] = {0, 0, 0, 0, 0};
+  if (b < B) {
+    const long long s = pc.src_idx ? pc.src_idx[b] : b;
+    float q = 0.0f, sl = 0.0f;
+    for (int j = 0; j < d; ++j) {
+      const float ls = logstd[j];
+      const float t = (actions[s * d + j] - mean[b * ld + j]) / expf(ls);
+      q += t * t;
+      sl += ls;
+    }
+    const float nlp = 0.5f * q + 0.5f * 1.8378770664093453f * (float)d + sl;
+    const float H = sl + 0.5f * 2.8378770664093453f * (float)d;       // sum(logstd + .5*log(2*pi*e))
+    const float R = pc.returns[s], oldv = pc.old_values[s];
+    const float adv_raw = __fsub_rn(R, oldv);
+    const float adv = (float)(((double)adv_raw - pc.adv_stats[0]) / (pc.adv_stats[1] + 1e-8));
+    float pgl, kl, cf, vl;
+    const float g_nlp = pg_loss_grad(nlp, pc.old_neglogp[s], adv, pc.cliprange, pgl, kl, cf);
+    const float g_v = value_loss_grad(vpred[b * ldv], oldv, R, pc.cliprange, pc.vf_coef, vl);
+    for (int j = 0; j < d; ++j) {
+      const float sd = expf(logstd[j]);
+      const float t = (actions[s * d + j] - mean[b * ld + j]) / sd;
+      dmean[b * ld_dm + j] = __float2half_rn(g_nlp * (-t / sd));      // d nlp/d mu = -(x-mu)/sigma^2
+      // d nlp/d logstd = 1 - t^2 ; d(-ent_coef*H)/d logstd = -ent_coef
+      atomicAdd(&s_dls[j], g_nlp * (1.0f - t * t) - pc.ent_coef);
+    }
+    dv[b * ld_dv] = __float2half_rn(g_v);
+    st[0] = pgl; st[1] = vl; st[2] = H; st[3] = kl; st[4] = cf;
+  }
+  __syncthreads();
+  for (int j = threadIdx.x; j < d; j += blockDim.x) atomicAdd(dlogstd + j, s_dls[j] * inv_M);
+  block_accumulate5(st, pc.stats);
+}
+
+// ---------------------------------------------------------------- launchers
+int cat_step_impl(const float* logits, long long ld, int nA, const float* vpred, long long ldv, const float* uniforms,
+                  unsigned long long seed, unsigned long long offset, long long* actions, float* values,
+                  float* neglogp, long long B, cudaStream_t stream) {
+  B200RL_REQUIRE(logits && vpred && actions && values && neglogp && B > 0 && nA > 0, "cat_step: bad args");
+  cat_step_kernel<<<(int)ceil_div_ll(B, 256), 256, 0, stream>>>(logits, ld, nA, vpred, ldv, uniforms, seed, offset,
+                                                                 actions, values, neglogp, B);
+  return check_launch("cat_step_kernel");
+}
+
+int gauss_step_impl(const float* mean, long long ld, const float* logstd, int d, const float* vpred, long long ldv,
+                    const float* normals, unsigned long long seed, unsigned long long offset, float* actions,
+                    float* values, float* neglogp, long long B, cudaStream_t stream) {
+  B200RL_REQUIRE(mean && logstd && vpred && actions && values && neglogp && B > 0 && d > 0, "gauss_step: bad args");
+  gauss_step_kernel<<<(int)ceil_div_ll(B, 256), 256, 0, stream>>>(mean, ld, logstd, d, vpred, ldv, normals, seed,
+                                                                   offset, actions, values, neglogp, B);
+  return check_launch("gauss_step_kernel");
+}
+
+int adv_stats_impl(const float* returns, const float* values, const long long* src_idx, long long M, double* out,
+                   cudaStream_t stream) {
+  B200RL_REQUIRE(returns && values && out && M > 0, "adv_stats: bad args");
+  adv_stats_kernel<<<1, 1024, 0, stream>>>(returns, values, src_idx, M, out);
+  return check_launch("adv_stats_kernel");
+}
+
+int cat_loss_impl(const float* logits, long long ld, int nA, const float* vpred, long long ldv,
+                  const long long* actions, const long long* src_idx, const float* returns, const float* old_values,
+                  const float* old_neglogp, const double* adv_stats, float cliprange, float ent_coef, float vf_coef,
+                  void* dlogits, long long ld_dl, void* dv, long long ld_dv, double* stats, long long B,
+                  cudaStream_t stream) {
+  B200RL_REQUIRE(logits && vpred && actions && returns && old_values && old_neglogp && adv_stats && dlogits && dv &&
+                     stats && B > 0,
+                 "cat_loss: bad args");
+  PpoCommon pc{src_idx, returns, old_values, old_neglogp, adv_stats, cliprange, ent_coef, vf_coef, stats};
+  cat_loss_kernel<<<(int)ceil_div_ll(B, 256), 256, 0, stream>>>(logits, ld, nA, vpred, ldv, actions, pc,
+                                                                 reinterpret_cast<__half*>(dlogits), ld_dl,
+                                                                 reinterpret_cast<__half*>(dv), ld_dv, B);
+  return check_launch("cat_loss_kernel");
+}
+
+int gauss_loss_impl(const float* mean, long long ld, const float* logstd, int d, const float* vpred, long long ldv,
+                    const float* actions, const long long* src_idx, const float* returns, const float* old_values,
+                    const float* old_neglogp, const double* adv_stats, float cliprange, float ent_coef, float vf_coef,
+                    void* dmean, long long ld_dm, void* dv, long long ld_dv, float* dlogstd, float inv_M,
+                    double* stats, long long B, cudaStream_t stream) {
+  B200RL_REQUIRE(mean && logstd && vpred && actions && returns && old_values && old_neglogp && adv_stats && dmean &&
+                     dv && dlogstd && stats && B > 0,
+                 "gauss_loss: bad args");
+  PpoCommon pc{src_idx, returns, old_values, old_neglogp, adv_stats, cliprange, ent_coef, vf_coef, stats};
+  gauss_loss_kernel<<<(int)ceil_div_ll(B, 256), 256, d * sizeof(float), stream>>>(
+      mean, ld, logstd, d, vpred, ldv, actions, pc, reinterpret_cast<__half*>(dmean), ld_dm,
+      reinterpret_cast<__half*>(dv), ld_dv, dlogstd, inv_M, B);
+  return check_launch("gauss_loss_kernel");
+}
+
+}  // namespace b200rl

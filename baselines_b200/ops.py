@@ -1,0 +1,187 @@
+"""Torch-tensor front end of the C-ABI: tensors only supply device pointers and the current stream.
+
+Every function launches hand-written sm_100a kernels from libb200rl.so; nothing here computes with
+torch ops (torch is plumbing: allocation, streams, torch.distributed).
+"""
+import torch
+
+from . import _lib
+
+MODE_F16_ACT, MODE_F32_STORE, MODE_F32_ATOMIC, MODE_F16_DACT = 0, 1, 2, 3
+ACT_NONE, ACT_RELU, ACT_TANH = 0, 1, 2
+ACT_CODES = {None: ACT_NONE, "none": ACT_NONE, "relu": ACT_RELU, "tanh": ACT_TANH}
+
+
+def _ptr(t):
+    return None if t is None else t.data_ptr()
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _chk(t, dtype, name):
+    if t is None:
+        return
+    if not t.is_cuda:
+        raise RuntimeError(f"{name}: expected a CUDA tensor (the hot path has no CPU fallback)")
+    if t.dtype != dtype:
+        raise RuntimeError(f"{name}: expected {dtype}, got {t.dtype}")
+
+
+def gae_scan(rewards, values, dones, last_values, last_dones, advs, returns, gamma, lam, variant=-1):
+    """rewards/values/advs/returns float32 [T,N]; dones uint8 [T,N]; last_* [N]."""
+    T, N = rewards.shape
+    for t, dt, nm in ((rewards, torch.float32, "rewards"), (values, torch.float32, "values"),
+                      (dones, torch.uint8, "dones"), (last_values, torch.float32, "last_values"),
+                      (last_dones, torch.uint8, "last_dones"), (advs, torch.float32, "advs"),
+                      (returns, torch.float32, "returns")):
+        _chk(t, dt, nm)
+        assert t.is_contiguous(), nm
+    _lib.call("b200rl_gae_scan", _ptr(rewards), _ptr(values), _ptr(dones), _ptr(last_values), _ptr(last_dones),
+              _ptr(advs), _ptr(returns), T, N, float(gamma), float(lam), int(variant), _stream())
+
+
+def gemm(A, B, C, *, M, N, K, lda, ldb, ldc, bias=None, saved=None, ld_saved=0, mn_major=False,
+         mode=MODE_F16_ACT, act=ACT_NONE, alpha=1.0, split_k=1, max_ctas=0):
+    _chk(A, torch.float16, "A")
+    _chk(B, torch.float16, "B")
+    _chk(bias, torch.float32, "bias")
+    _chk(saved, torch.float16, "saved")
+    _lib.call("b200rl_gemm_f16", _ptr(A), _ptr(B), _ptr(C), _ptr(bias), _ptr(saved), int(M), int(N), int(K),
+              int(lda), int(ldb), int(ldc), int(ld_saved), int(bool(mn_major)), int(mode), int(act), float(alpha),
+              int(split_k), int(max_ctas), _stream())
+
+
+def im2col(x, cols, B, H, W, C, rf, stride, same_pad=False, src_idx=None):
+    _chk(src_idx, torch.int64, "src_idx")
+    _chk(cols, torch.float16, "cols")
+    src_u8 = x.dtype == torch.uint8
+    if not src_u8:
+        _chk(x, torch.float16, "x")
+    _lib.call("b200rl_im2col", _ptr(x), int(src_u8), _ptr(src_idx), _ptr(cols), int(B), H, W, C, rf, stride,
+              int(bool(same_pad)), _stream())
+
+
+def col2im(dcols, saved, dx, B, H, W, C, rf, stride, same_pad=False, act=ACT_NONE):
+    _chk(dcols, torch.float16, "dcols")
+    _chk(dx, torch.float16, "dx")
+    _lib.call("b200rl_col2im", _ptr(dcols), _ptr(saved), _ptr(dx), int(B), H, W, C, rf, stride, int(bool(same_pad)),
+              int(act), _stream())
+
+
+def colsum(dz, db, rows, C, ld, alpha=1.0):
+    _chk(dz, torch.float16, "dz")
+    _chk(db, torch.float32, "db")
+    _lib.call("b200rl_colsum", _ptr(dz), _ptr(db), int(rows), int(C), int(ld), float(alpha), _stream())
+
+
+def cat_step(logits, ld, nA, vpred, ldv, actions, values, neglogp, B, uniforms=None, seed=0, offset=0):
+    _chk(logits, torch.float32, "logits")
+    _chk(actions, torch.int64, "actions")
+    _chk(uniforms, torch.float32, "uniforms")
+    _lib.call("b200rl_cat_step", _ptr(logits), int(ld), int(nA), _ptr(vpred), int(ldv), _ptr(uniforms), int(seed),
+              int(offset), _ptr(actions), _ptr(values), _ptr(neglogp), int(B), _stream())
+
+
+def gauss_step(mean, ld, logstd, d, vpred, ldv, actions, values, neglogp, B, normals=None, seed=0, offset=0):
+    _chk(mean, torch.float32, "mean")
+    _chk(actions, torch.float32, "actions")
+    _chk(normals, torch.float32, "normals")
+    _lib.call("b200rl_gauss_step", _ptr(mean), int(ld), _ptr(logstd), int(d), _ptr(vpred), int(ldv), _ptr(normals),
+              int(seed), int(offset), _ptr(actions), _ptr(values), _ptr(neglogp), int(B), _stream())
+
+
+def adv_stats(returns, values, src_idx, M, out):
+    _chk(out, torch.float64, "out")
+    _chk(src_idx, torch.int64, "src_idx")
+    _lib.call("b200rl_adv_stats", _ptr(returns), _ptr(values), _ptr(src_idx), int(M), _ptr(out), _stream())
+
+
+def cat_loss(logits, ld, nA, vpred, ldv, actions, src_idx, returns, old_values, old_neglogp, adv_st, cliprange,
+             ent_coef, vf_coef, dlogits, ld_dl, dv, ld_dv, stats, B):
+    _chk(actions, torch.int64, "actions")
+    _chk(stats, torch.float64, "stats")
+    _lib.call("b200rl_cat_loss", _ptr(logits), int(ld), int(nA), _ptr(vpred), int(ldv), _ptr(actions), _ptr(src_idx),
+              _ptr(returns), _ptr(old_values), _ptr(old_neglogp), _ptr(adv_st), float(cliprange), float(ent_coef),
+              float(vf_coef), _ptr(dlogits), int(ld_dl), _ptr(dv), int(ld_dv), _ptr(stats), int(B), _stream())
+
+
+def gauss_loss(mean, ld, logstd, d, vpred, ldv, actions, src_idx, returns, old_values, old_neglogp, adv_st,
+               cliprange, ent_coef, vf_coef, dmean, ld_dm, dv, ld_dv, dlogstd, inv_M, stats, B):
+    _chk(actions, torch.float32, "actions")
+    _lib.call("b200rl_gauss_loss", _ptr(mean), int(ld), _ptr(logstd), int(d), _ptr(vpred), int(ldv), _ptr(actions),
+              _ptr(src_idx), _ptr(returns), _ptr(old_values), _ptr(old_neglogp), _ptr(adv_st), float(cliprange),
+              float(ent_coef), float(vf_coef), _ptr(dmean), int(ld_dm), _ptr(dv), int(ld_dv), _ptr(dlogstd),
+              float(inv_M), _ptr(stats), int(B), _stream())
+
+
+def sumsq(g, out):
+    _chk(g, torch.float32, "g")
+    _chk(out, torch.float64, "out")
+    _lib.call("b200rl_sumsq", _ptr(g), g.numel(), _ptr(out), _stream())
+
+
+def seg_sumsq(g, seg_off, nseg, out):
+    _chk(seg_off, torch.int64, "seg_off")
+    _lib.call("b200rl_seg_sumsq", _ptr(g), _ptr(seg_off), int(nseg), _ptr(out), _stream())
+
+
+def clip_adam(p, g, m, v, lr_t, beta1, beta2, eps, clip, sumsq_buf, seg_off=None, nseg=0):
+    for t, nm in ((p, "p"), (g, "g"), (m, "m"), (v, "v")):
+        _chk(t, torch.float32, nm)
+    _lib.call("b200rl_clip_adam", _ptr(p), _ptr(g), _ptr(m), _ptr(v), p.numel(), float(lr_t), float(beta1),
+              float(beta2), float(eps), float(clip if clip else 0.0), _ptr(sumsq_buf), _ptr(seg_off), int(nseg),
+              _stream())
+
+
+def cast_transpose(src, R, C, dst, ld_dst, dstT, ld_t, scale=1.0):
+    _chk(src, torch.float32, "src")
+    _lib.call("b200rl_cast_transpose", _ptr(src), int(R), int(C), _ptr(dst), int(ld_dst), _ptr(dstT), int(ld_t),
+              float(scale), _stream())
+
+
+def cast_f32_f16(src, dst, rows, cols, ld_src, ld_dst, scale=1.0):
+    _chk(src, torch.float32, "src")
+    _chk(dst, torch.float16, "dst")
+    _lib.call("b200rl_cast_f32_f16", _ptr(src), _ptr(dst), int(rows), int(cols), int(ld_src), int(ld_dst),
+              float(scale), _stream())
+
+
+def tree_set(sum_tree, min_tree, capacity, idx, vals):
+    _chk(sum_tree, torch.float64, "sum_tree")
+    _chk(idx, torch.int64, "idx")
+    _chk(vals, torch.float64, "vals")
+    _lib.call("b200rl_tree_set", _ptr(sum_tree), _ptr(min_tree), int(capacity), _ptr(idx), _ptr(vals), idx.numel(),
+              _stream())
+
+
+def tree_range_sum(tree, capacity, start, end, out):
+    _lib.call("b200rl_tree_range_sum", _ptr(tree), int(capacity), int(start), int(end), _ptr(out), _stream())
+
+
+def per_sample(sum_tree, min_tree, capacity, n_stored, uniforms, beta, idx_out, w_out, w_out_f32=None):
+    _chk(uniforms, torch.float64, "uniforms")
+    _chk(idx_out, torch.int64, "idx_out")
+    _chk(w_out, torch.float64, "w_out")
+    _lib.call("b200rl_per_sample", _ptr(sum_tree), _ptr(min_tree), int(capacity), int(n_stored), _ptr(uniforms),
+              uniforms.numel(), float(beta), _ptr(idx_out), _ptr(w_out), _ptr(w_out_f32), _stream())
+
+
+def per_priorities(td, eps, alpha, powered, max_priority):
+    _chk(td, torch.float32, "td")
+    _lib.call("b200rl_per_priorities", _ptr(td), td.numel(), float(eps), float(alpha), _ptr(powered),
+              _ptr(max_priority), _stream())
+
+
+def dqn_td(a_t, lda_t, s_t, lds_t, a_on, lda_on, s_on, lds_on, a_tg, lda_tg, s_tg, lds_tg, nA, idx, actions,
+           rewards, dones, weights, gamma, double_q, td_out, d_a, ld_da, d_s, ld_ds, loss_sum, B):
+    _lib.call("b200rl_dqn_td", _ptr(a_t), int(lda_t), _ptr(s_t), int(lds_t), _ptr(a_on), int(lda_on), _ptr(s_on),
+              int(lds_on), _ptr(a_tg), int(lda_tg), _ptr(s_tg), int(lds_tg), int(nA), _ptr(idx), _ptr(actions),
+              _ptr(rewards), _ptr(dones), _ptr(weights), float(gamma), int(bool(double_q)), _ptr(td_out), _ptr(d_a),
+              int(ld_da), _ptr(d_s), int(ld_ds), _ptr(loss_sum), int(B), _stream())
+
+
+def dqn_act(a, lda, s, lds, nA, eps, seed, step, actions, B):
+    _lib.call("b200rl_dqn_act", _ptr(a), int(lda), _ptr(s), int(lds), int(nA), float(eps), int(seed), int(step),
+              _ptr(actions), int(B), _stream())

@@ -1,0 +1,128 @@
+/* libb200rl -- C-ABI of the B200-native PPO2 / DQN learner hot path.
+ *
+ * The reference (openai/baselines) has NO FFI: its hot path is TF1 graph ops + numpy loops called from
+ * Python.  Each entry point below therefore names the reference interface (file:line) whose arithmetic it
+ * replaces; INTEGRATION.md shows the ctypes binding a baselines maintainer would add.
+ *
+ * Conventions
+ *  - every pointer is a DEVICE pointer owned by the caller (torch tensors in this repo); no hidden
+ *    allocation, no host synchronisation inside; `stream` is a cudaStream_t passed as void*.
+ *  - return 0 on success, negative on error (see B200RL_ERR_*); b200rl_last_error() gives the text.
+ *  - fp16 tensors are IEEE half; "ld*" are row pitches in ELEMENTS.
+ *  - rollout arrays are time-major [T, N] (env contiguous); `src_idx` arrays hold buffer offsets t*N+e.
+ */
+#ifndef B200RL_H
+#define B200RL_H
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B200RL_OK 0
+#define B200RL_ERR_ARG (-1)
+#define B200RL_ERR_CUDA (-2)
+#define B200RL_ERR_UNSUPPORTED (-3)
+#define B200RL_ERR_DRIVER (-4)
+
+/* GEMM epilogues */
+#define B200RL_MODE_F16_ACT 0    /* C16 = act(alpha*acc + bias)                      (forward)            */
+#define B200RL_MODE_F32_STORE 1  /* C32 = alpha*acc + bias                           (heads)              */
+#define B200RL_MODE_F32_ATOMIC 2 /* C32 += alpha*acc (red.add.f32; split-K capable)  (weight gradients)   */
+#define B200RL_MODE_F16_DACT 3   /* C16 = alpha*acc * act'(saved)                    (data gradients)     */
+#define B200RL_ACT_NONE 0
+#define B200RL_ACT_RELU 1
+#define B200RL_ACT_TANH 2
+
+const char* b200rl_last_error(void);
+int b200rl_version(void);
+
+/* GAE(lambda) backward scan: baselines/ppo2/runner.py:53-65 (bit-exact, float64 carry).
+ * dones[t] = done BEFORE step t (runner.py:34); last_dones = runner.dones after the last step.
+ * variant: -1 auto, 0 register-prefetch kernel, 1 TMA-bulk pipelined kernel (needs N % 32 == 0). */
+int b200rl_gae_scan(const float* rewards, const float* values, const uint8_t* dones, const float* last_values,
+                    const uint8_t* last_dones, float* advs, float* returns, int T, int N, double gamma, double lam,
+                    int variant, void* stream);
+
+/* fp16 x fp16 -> fp32 tcgen05 GEMM: tf.matmul a2c/utils.py:63; after im2col also tf.nn.conv2d a2c/utils.py:56
+ * and their gradients (ppo2/model.py:102).
+ *   mn_major = 0 : A[M,K] (lda), B[N,K] (ldb), C = A * B^T
+ *   mn_major = 1 : A[K,M] (lda), B[K,N] (ldb), C = A^T * B   (reduction over rows; use split_k > 1)
+ * max_ctas <= 0 : one persistent CTA per SM. */
+int b200rl_gemm_f16(const void* A, const void* B, void* C, const float* bias, const void* saved, int M, int N, int K,
+                    long long lda, long long ldb, long long ldc, long long ld_saved, int mn_major, int mode, int act,
+                    float alpha, int split_k, int max_ctas, void* stream);
+
+/* conv lowering (tf.nn.conv2d NHWC, a2c/utils.py:37-56; SAME padding for tf.contrib convolution2d,
+ * common/models.py:241).  src_is_u8 fuses tf.cast(uint8->float) of models.py:19 and, through src_idx,
+ * the minibatch gather arr[mbinds] of ppo2/ppo2.py:165. */
+int b200rl_im2col(const void* x, int src_is_u8, const long long* src_idx, void* cols, long long B, int H, int W,
+                  int C, int rf, int stride, int same_pad, void* stream);
+int b200rl_col2im(const void* dcols, const void* saved, void* dx, long long B, int H, int W, int C, int rf,
+                  int stride, int same_pad, int act, void* stream);
+int b200rl_colsum(const void* dz, float* db, long long rows, int C, long long ld, float alpha, void* stream);
+
+/* act path: PolicyWithValue.step common/policies.py:77-96; CategoricalPd.sample/neglogp
+ * common/distributions.py:164-201; DiagGaussianPd :238-248.  noise == NULL -> counter-based Philox. */
+int b200rl_cat_step(const float* logits, long long ld, int nA, const float* vpred, long long ldv,
+                    const float* uniforms, unsigned long long seed, unsigned long long offset, long long* actions,
+                    float* values, float* neglogp, long long B, void* stream);
+int b200rl_gauss_step(const float* mean, long long ld, const float* logstd, int d, const float* vpred,
+                      long long ldv, const float* normals, unsigned long long seed, unsigned long long offset,
+                      float* actions, float* values, float* neglogp, long long B, void* stream);
+
+/* per-minibatch advantage moments: ppo2/model.py:136-139.  out = {mean, std} (float64). */
+int b200rl_adv_stats(const float* returns, const float* values, const long long* src_idx, long long M, double* out,
+                     void* stream);
+
+/* PPO2 loss + gradient w.r.t. head outputs: ppo2/model.py:57-91.  stats[5] += per-sample sums of
+ * {pg_loss, vf_loss, entropy, approxkl, clipfrac} (model.py:115); gradients in "sum" scaling. */
+int b200rl_cat_loss(const float* logits, long long ld, int nA, const float* vpred, long long ldv,
+                    const long long* actions, const long long* src_idx, const float* returns,
+                    const float* old_values, const float* old_neglogp, const double* adv_stats, float cliprange,
+                    float ent_coef, float vf_coef, void* dlogits, long long ld_dl, void* dv, long long ld_dv,
+                    double* stats, long long B, void* stream);
+int b200rl_gauss_loss(const float* mean, long long ld, const float* logstd, int d, const float* vpred,
+                      long long ldv, const float* actions, const long long* src_idx, const float* returns,
+                      const float* old_values, const float* old_neglogp, const double* adv_stats, float cliprange,
+                      float ent_coef, float vf_coef, void* dmean, long long ld_dm, void* dv, long long ld_dv,
+                      float* dlogstd, float inv_M, double* stats, long long B, void* stream);
+
+/* optimiser: tf.clip_by_global_norm ppo2/model.py:105-107, tf.clip_by_norm deepq/build_graph.py:416-421,
+ * tf.train.AdamOptimizer ppo2/model.py:100 == common/mpi_adam.py:37-42. lr_t = lr*sqrt(1-b2^t)/(1-b1^t). */
+int b200rl_sumsq(const float* g, long long n, double* out, void* stream);
+int b200rl_seg_sumsq(const float* g, const long long* seg_off, int nseg, double* out, void* stream);
+int b200rl_clip_adam(float* p, const float* g, float* m, float* v, long long n, float lr_t, float beta1, float beta2,
+                     float eps, float clip, const double* sumsq, const long long* seg_off, int nseg, void* stream);
+int b200rl_cast_transpose(const float* src, int R, int C, void* dst, long long ld_dst, void* dstT, long long ld_t,
+                          float scale, void* stream);
+int b200rl_cast_f32_f16(const float* src, void* dst, long long rows, int cols, long long ld_src, long long ld_dst,
+                        float scale, void* stream);
+
+/* prioritized replay: common/segment_tree.py:76-86 (__setitem__), :51-74 (reduce), :105-131
+ * (find_prefixsum_idx); deepq/replay_buffer.py:107-115 (_sample_proportional), :157-165 (weights),
+ * :169-191 (update_priorities). */
+int b200rl_tree_set(double* sum_tree, double* min_tree, long long capacity, const long long* idx, const double* vals,
+                    int n, void* stream);
+int b200rl_tree_range_sum(const double* tree, long long capacity, long long start, long long end, double* out,
+                          void* stream);
+int b200rl_per_sample(const double* sum_tree, const double* min_tree, long long capacity, long long n_stored,
+                      const double* uniforms, int batch, double beta, long long* idx_out, double* w_out,
+                      float* w_out_f32, void* stream);
+int b200rl_per_priorities(const float* td, int n, double eps, double alpha, double* powered, double* max_priority,
+                          void* stream);
+
+/* DQN: deepq/build_graph.py:388-413 (double-Q target, Huber tf_util.py:39-45, importance weights),
+ * deepq/models.py:38-40 (dueling), build_graph.py:184-191 (epsilon-greedy). s_* == NULL -> no dueling. */
+int b200rl_dqn_td(const float* a_t, long long lda_t, const float* s_t, long long lds_t, const float* a_on,
+                  long long lda_on, const float* s_on, long long lds_on, const float* a_tg, long long lda_tg,
+                  const float* s_tg, long long lds_tg, int nA, const long long* idx, const long long* actions,
+                  const float* rewards, const float* dones, const float* weights, float gamma, int double_q,
+                  float* td_out, void* d_a, long long ld_da, void* d_s, long long ld_ds, double* loss_sum, int B,
+                  void* stream);
+int b200rl_dqn_act(const float* a, long long lda, const float* s, long long lds, int nA, float eps,
+                   unsigned long long seed, unsigned long long step, long long* actions, int B, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200RL_H */
