@@ -1,0 +1,208 @@
+"""Policy / value network for the PPO2 learner on the B200 kernels.
+
+Behavioural mirror of the reference's common/policies.py (build_policy :121-179, PolicyWithValue
+:13-119), common/distributions.py (CategoricalPd :153-204, DiagGaussianPd :227-251) and
+common/input.py:43-63.  The object protocol (step / value) is kept; the TF graph is replaced by an
+explicit sequence of libb200rl kernel launches.
+"""
+import numpy as np
+import torch
+
+from .. import nn, ops
+from . import spaces
+
+
+class PolicyBuilder:
+    """What `build_policy(env, network, **kwargs)` returns (reference: a `policy_fn` closure,
+    policies.py:126).  Carries the architecture; `Model` instantiates it on a device."""
+
+    def __init__(self, ob_space, ac_space, network, value_network=None, normalize_observations=False,
+                 **network_kwargs):
+        if callable(network) and not isinstance(network, str):
+            raise NotImplementedError("custom network callables build TF graphs in the reference; this learner "
+                                      "supports the registry names 'cnn', 'mlp', 'conv_only'")
+        if normalize_observations:
+            raise NotImplementedError("normalize_observations (policies.py:133-137) is outside the hot path scope")
+        if value_network not in (None, "shared", "copy"):
+            raise NotImplementedError("value_network must be None/'shared'/'copy' (policies.py:154-166)")
+        self.ob_space, self.ac_space = ob_space, ac_space
+        self.network = network
+        self.value_network = "copy" if value_network == "copy" else None
+        self.network_kwargs = network_kwargs
+
+
+def build_policy(env, policy_network, value_network=None, normalize_observations=False, estimate_q=False,
+                 **policy_kwargs):
+    """Same call signature as the reference's build_policy (policies.py:121)."""
+    if estimate_q:
+        raise NotImplementedError("estimate_q is only used by ACER in the reference (out of scope)")
+    return PolicyBuilder(env.observation_space, env.action_space, policy_network, value_network,
+                         normalize_observations, **policy_kwargs)
+
+
+def _pad(n, m):
+    return (n + m - 1) // m * m
+
+
+class PolicyNet:
+    """Towers + heads + workspaces for at most `cap` samples per launch sequence."""
+
+    def __init__(self, builder, cap, device, rng=np.random, scope="ppo2_model"):
+        self.device, self.cap = device, cap
+        ob_space, ac_space = builder.ob_space, builder.ac_space
+        self.ob_shape = tuple(ob_space.shape)
+        self.discrete = spaces.is_discrete(ac_space)
+        if self.discrete:
+            self.nout = int(ac_space.n)
+        elif spaces.is_box(ac_space):
+            assert len(ac_space.shape) == 1                                    # distributions.py:281
+            self.nout = int(ac_space.shape[0])
+        else:
+            raise NotImplementedError("only Discrete and Box action spaces are on the hot path (SURVEY 2, #6)")
+        kind = builder.network
+        self.kind = kind
+        self.copy_vf = builder.value_network == "copy"
+        store = self.store = nn.ParamStore(device)
+        kw = dict(builder.network_kwargs)
+        # creation order == the reference's variable creation order (it fixes the ortho_init RNG stream)
+        self.tower_pi = nn.Tower(store, kind, self.ob_shape, "pi", f"{scope}/pi", rng, cap, **kw)
+        self.tower_vf = nn.Tower(store, kind, self.ob_shape, "vf", f"{scope}/vf", rng, cap, **kw) if self.copy_vf else None
+        L = self.tower_pi.latent_dim
+        if L == self.nout:
+            raise NotImplementedError("_matching_fc latent==action-width shortcut (distributions.py:351-355)")
+        w_pi = nn.ortho_init((L, self.nout), 0.01, rng)                        # policies.py:49 init_scale=0.01
+        if not self.discrete:
+            store.add("pi/logstd", np.zeros((1, self.nout), np.float32))         # distributions.py:104
+            store.map_tf(f"{scope}/pi/logstd:0", "pi/logstd", (1, self.nout))
+        Lv = self.tower_vf.latent_dim if self.copy_vf else L
+        w_vf = nn.ortho_init((Lv, 1), 1.0, rng)                                # policies.py:63
+        if self.copy_vf:
+            self.head_pi = nn.Linear(store, "head_pi", L, self.nout, None, w_pi,
+                                     tf_w=f"{scope}/pi/w:0", tf_b=f"{scope}/pi/b:0")
+            self.head_vf = nn.Linear(store, "head_vf", Lv, 1, None, w_vf,
+                                     tf_w=f"{scope}/vf/w:0", tf_b=f"{scope}/vf/b:0")
+            self.head = None
+        else:
+            # fused [pi | vf] head: one skinny GEMM; TF variables are column slices of it
+            n = self.nout
+            self.head = nn.Linear(store, "head", L, n + 1, None, np.concatenate([w_pi, w_vf], axis=1))
+            store.map_tf(f"{scope}/pi/w:0", "head/w", (L, n), col_slice=slice(0, n))
+            store.map_tf(f"{scope}/pi/b:0", "head/b", (n,), col_slice=slice(0, n))
+            store.map_tf(f"{scope}/vf/w:0", "head/w", (L, 1), col_slice=slice(n, n + 1))
+            store.map_tf(f"{scope}/vf/b:0", "head/b", (1,), col_slice=slice(n, n + 1))
+        store.finalize()
+        self._materialize()
+        self.refresh()
+
+    # ------------------------------------------------------------------------------------------
+    def _materialize(self):
+        dev, cap = self.device, self.cap
+        self.tower_pi.materialize()
+        if self.tower_vf:
+            self.tower_vf.materialize()
+        f32 = dict(dtype=torch.float32, device=dev)
+        f16 = dict(dtype=torch.float16, device=dev)
+        if self.head is not None:
+            self.head.materialize()
+            self.ld_ho = _pad(self.nout + 1, 16)
+            self.headout = torch.zeros(cap, self.ld_ho, **f32)
+            self.pi_out, self.ld_pi = self.headout, self.ld_ho
+            self.v_out, self.ld_v = self.headout[:, self.nout:], self.ld_ho
+            self.ld_dh = _pad(self.nout + 1, 64)
+            self.dhead = torch.zeros(cap, self.ld_dh, **f16)                  # padding columns stay zero
+            self.dpi, self.ld_dpi = self.dhead, self.ld_dh
+            self.dv, self.ld_dv = self.dhead[:, self.nout:], self.ld_dh
+        else:
+            self.head_pi.materialize()
+            self.head_vf.materialize()
+            self.ld_pi = _pad(self.nout, 16)
+            self.pi_out = torch.zeros(cap, self.ld_pi, **f32)
+            self.ld_v = 16
+            self.v_out = torch.zeros(cap, 16, **f32)
+            self.ld_dpi = _pad(self.nout, 64)
+            self.dpi = torch.zeros(cap, self.ld_dpi, **f16)
+            self.ld_dv = 64
+            self.dv = torch.zeros(cap, 64, **f16)
+        if not self.discrete:
+            self.logstd = self.store.views["pi/logstd"].view(-1)
+            self.g_logstd = self.store.gviews["pi/logstd"].view(-1)
+        self.adv_st = torch.zeros(2, dtype=torch.float64, device=dev)
+        self.stats = torch.zeros(5, dtype=torch.float64, device=dev)
+
+    def refresh(self):
+        """Re-derive the fp16 operand copies from the fp32 master weights (after init / Adam / load)."""
+        self.tower_pi.refresh()
+        if self.tower_vf:
+            self.tower_vf.refresh()
+            self.head_pi.refresh()
+            self.head_vf.refresh()
+        else:
+            self.head.refresh()
+
+    # ------------------------------------------------------------------------------------------
+    def encode_obs(self, obs_host_or_dev):
+        """common/input.py:43-63: Box uint8 images stay uint8 (cast fused into the first kernel); float
+        vectors become padded fp16 rows (the GEMM operand format)."""
+        t = obs_host_or_dev if torch.is_tensor(obs_host_or_dev) else torch.from_numpy(np.ascontiguousarray(obs_host_or_dev))
+        t = t.to(self.device, non_blocking=True)
+        if self.tower_pi.in_u8:
+            if t.dtype != torch.uint8:
+                raise NotImplementedError("cnn towers take uint8 images (common/models.py:19)")
+            return t.contiguous()
+        B = t.shape[0]
+        x = torch.zeros(B, self.tower_pi.in_pad, dtype=torch.float16, device=self.device)
+        src = t.reshape(B, -1).to(torch.float32).contiguous()
+        ops.cast_f32_f16(src, x, B, self.tower_pi.in_dim, self.tower_pi.in_dim, self.tower_pi.in_pad)
+        return x
+
+    def forward(self, x, B, src_idx=None):
+        """Towers + heads for B samples of x (optionally gathered through src_idx)."""
+        lat, ldl = self.tower_pi.forward(x, B, src_idx)
+        self._lat_pi, self._ld_lat_pi = lat, ldl
+        if self.head is not None:
+            self.head.forward(lat, ldl, B, self.headout, self.ld_ho, mode=ops.MODE_F32_STORE)
+        else:
+            latv, ldlv = self.tower_vf.forward(x, B, src_idx)
+            self._lat_vf, self._ld_lat_vf = latv, ldlv
+            self.head_pi.forward(lat, ldl, B, self.pi_out, self.ld_pi, mode=ops.MODE_F32_STORE)
+            self.head_vf.forward(latv, ldlv, B, self.v_out, self.ld_v, mode=ops.MODE_F32_STORE)
+
+    def act(self, x, B, actions, values, neglogp, noise=None, seed=0, offset=0):
+        """PolicyWithValue.step (policies.py:77-96) into caller-provided device tensors."""
+        self.forward(x, B)
+        if self.discrete:
+            ops.cat_step(self.pi_out, self.ld_pi, self.nout, self.v_out, self.ld_v, actions, values, neglogp, B,
+                         uniforms=noise, seed=seed, offset=offset)
+        else:
+            ops.gauss_step(self.pi_out, self.ld_pi, self.logstd, self.nout, self.v_out, self.ld_v, actions, values,
+                           neglogp, B, normals=noise, seed=seed, offset=offset)
+
+    def loss_backward(self, x, B, src_idx, actions, returns, old_values, old_neglogp, cliprange, ent_coef, vf_coef,
+                      inv_M):
+        """One chunk of ppo2/model.py:57-114: forward, loss statistics, full backward into store.grads
+        (gradients of the MEAN loss: every wgrad carries alpha = 1/M)."""
+        self.forward(x, B, src_idx)
+        if self.discrete:
+            ops.cat_loss(self.pi_out, self.ld_pi, self.nout, self.v_out, self.ld_v, actions, src_idx, returns,
+                         old_values, old_neglogp, self.adv_st, cliprange, ent_coef, vf_coef, self.dpi, self.ld_dpi,
+                         self.dv, self.ld_dv, self.stats, B)
+        else:
+            ops.gauss_loss(self.pi_out, self.ld_pi, self.logstd, self.nout, self.v_out, self.ld_v, actions, src_idx,
+                           returns, old_values, old_neglogp, self.adv_st, cliprange, ent_coef, vf_coef, self.dpi,
+                           self.ld_dpi, self.dv, self.ld_dv, self.g_logstd, inv_M, self.stats, B)
+        tp = self.tower_pi
+        if self.head is not None:
+            self.head.wgrad(self._lat_pi, self._ld_lat_pi, self.dhead, self.ld_dh, B, inv_M)
+            self.head.dgrad(self.dhead, self.ld_dh, B, tp.dlatent, tp.ld_dlatent, saved=self._lat_pi,
+                            ld_saved=self._ld_lat_pi, act=tp.latent_act)
+            tp.backward(B, inv_M)
+        else:
+            tv = self.tower_vf
+            self.head_pi.wgrad(self._lat_pi, self._ld_lat_pi, self.dpi, self.ld_dpi, B, inv_M)
+            self.head_pi.dgrad(self.dpi, self.ld_dpi, B, tp.dlatent, tp.ld_dlatent, saved=self._lat_pi,
+                               ld_saved=self._ld_lat_pi, act=tp.latent_act)
+            tp.backward(B, inv_M)
+            self.head_vf.wgrad(self._lat_vf, self._ld_lat_vf, self.dv, self.ld_dv, B, inv_M)
+            self.head_vf.dgrad(self.dv, self.ld_dv, B, tv.dlatent, tv.ld_dlatent, saved=self._lat_vf,
+                               ld_saved=self._ld_lat_vf, act=tv.latent_act)
+            tv.backward(B, inv_M)

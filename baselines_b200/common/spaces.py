@@ -1,0 +1,44 @@
+"""Minimal gym.spaces stand-ins (gym is an external dependency of the reference and is absent here).
+
+Only what the learner boundary needs: `.shape`, `.dtype`, `.n`, `.sample()`.  Real
+gym spaces are accepted everywhere too: the code duck-types on these attributes.
+"""
+import numpy as np
+
+
+class Box:
+    def __init__(self, low, high, shape=None, dtype=np.float32):
+        self.dtype = np.dtype(dtype)
+        if shape is None:
+            low, high = np.asarray(low), np.asarray(high)
+            shape = low.shape
+        self.shape = tuple(shape)
+        self.low = np.broadcast_to(np.asarray(low, dtype=self.dtype), self.shape).copy()
+        self.high = np.broadcast_to(np.asarray(high, dtype=self.dtype), self.shape).copy()
+
+    def sample(self):
+        return np.random.uniform(self.low, self.high).astype(self.dtype)
+
+    def __repr__(self):
+        return f"Box{self.shape}"
+
+
+class Discrete:
+    def __init__(self, n):
+        self.n = int(n)
+        self.shape = ()
+        self.dtype = np.dtype(np.int64)
+
+    def sample(self):
+        return np.random.randint(self.n)
+
+    def __repr__(self):
+        return f"Discrete({self.n})"
+
+
+def is_discrete(space):
+    return hasattr(space, "n") and not hasattr(space, "nvec")
+
+
+def is_box(space):
+    return hasattr(space, "low") and hasattr(space, "high")

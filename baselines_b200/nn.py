@@ -1,0 +1,352 @@
+"""Host-side executor for the policy / Q networks: owns the flat fp32 parameter + Adam buffers, the fp16
+operand copies, per-layer activation workspaces, and sequences the libb200rl kernels.
+
+Mirrors (by behaviour, not by code) the layer primitives of the reference:
+  conv / fc / ortho_init            baselines/a2c/utils.py:20-63
+  nature_cnn / mlp / conv_only      baselines/common/models.py:15-26, 74-103, 221-249
+All math runs in hand-written CUDA (ops.*); torch here only allocates memory and provides streams.
+"""
+import math
+from collections import OrderedDict
+
+import numpy as np
+import torch
+
+from . import ops
+
+NATURE_CONVS = (("c1", 32, 8, 4), ("c2", 64, 4, 2), ("c3", 64, 3, 1))   # common/models.py:21-24
+
+
+def _pad8(n):
+    return (n + 7) // 8 * 8
+
+
+def ortho_init(shape, scale, rng=np.random):
+    """Orthogonal init used by every PPO2 layer (a2c/utils.py:20-35): SVD of a gaussian matrix drawn from
+    the (globally seeded) numpy RandomState; host-side, done once."""
+    shape = tuple(shape)
+    flat = shape if len(shape) == 2 else (int(np.prod(shape[:-1])), shape[-1])
+    a = rng.normal(0.0, 1.0, flat)
+    u, _, v = np.linalg.svd(a, full_matrices=False)
+    q = (u if u.shape == flat else v).reshape(shape)
+    return (scale * q[:shape[0], :shape[1]]).astype(np.float32)
+
+
+def xavier_uniform(shape, rng):
+    """tf.contrib.layers default initializer (deepq/models.py:23-37, common/models.py:241)."""
+    if len(shape) == 2:
+        fan_in, fan_out = shape
+    else:
+        rf = int(np.prod(shape[:-2]))
+        fan_in, fan_out = shape[-2] * rf, shape[-1] * rf
+    lim = math.sqrt(6.0 / (fan_in + fan_out))
+    return rng.uniform(-lim, lim, size=shape).astype(np.float32)
+
+
+class ParamStore:
+    """One flat fp32 buffer each for parameters, gradients and the two Adam slots (28 B/param per step),
+    with named views.  `tf_names` maps the reference's TF variable names (tf_util.py:345-355 checkpoint
+    keys) onto (possibly strided) views so checkpoints round-trip."""
+
+    def __init__(self, device):
+        self.device = device
+        self._specs = []          # (name, shape, init ndarray)
+        self.views = OrderedDict()
+        self.gviews = OrderedDict()
+        self.offsets = OrderedDict()
+        self.tf_map = OrderedDict()   # tf name -> (internal name, slicer or None, tf shape)
+        self.params = self.grads = self.m = self.v = None
+
+    def add(self, name, init):
+        init = np.ascontiguousarray(init, dtype=np.float32)
+        assert name not in [s[0] for s in self._specs], name
+        self._specs.append((name, init.shape, init))
+        return name
+
+    def map_tf(self, tf_name, internal, tf_shape, col_slice=None):
+        self.tf_map[tf_name] = (internal, col_slice, tuple(tf_shape))
+
+    def finalize(self):
+        off = 0
+        for name, shape, _ in self._specs:
+            self.offsets[name] = off
+            off += (int(np.prod(shape)) + 3) // 4 * 4
+        self.numel = off
+        dev = self.device
+        self.params = torch.zeros(off, dtype=torch.float32, device=dev)
+        self.grads = torch.zeros(off, dtype=torch.float32, device=dev)
+        self.m = torch.zeros(off, dtype=torch.float32, device=dev)
+        self.v = torch.zeros(off, dtype=torch.float32, device=dev)
+        host = np.zeros(off, np.float32)
+        for name, shape, init in self._specs:
+            o, n = self.offsets[name], int(np.prod(shape))
+            host[o:o + n] = init.ravel()
+            self.views[name] = self.params[o:o + n].view(*shape)
+            self.gviews[name] = self.grads[o:o + n].view(*shape)
+        self.params.copy_(torch.from_numpy(host))
+        self.n_true = sum(int(np.prod(s)) for _, s, _ in self._specs)
+        return self
+
+    def segment_offsets(self):
+        """[nseg+1] element offsets of every variable (for per-variable tf.clip_by_norm)."""
+        offs = [self.offsets[n] for n, _, _ in self._specs] + [self.numel]
+        return np.asarray(offs, dtype=np.int64)
+
+    # ---- checkpoint-format access (TF names / layouts) -------------------------------------------
+    def _tf_view(self, buf_views, tf_name):
+        internal, sl, shape = self.tf_map[tf_name]
+        v = buf_views[internal]
+        if sl is not None:
+            v = v[..., sl]
+        return v, shape
+
+    def _views_of(self, flat):
+        out = {}
+        for name, shape, _ in self._specs:
+            o, n = self.offsets[name], int(np.prod(shape))
+            out[name] = flat[o:o + n].view(*shape)
+        return out
+
+    def export_tf(self, which="params"):
+        flat = {"params": self.params, "grads": self.grads, "m": self.m, "v": self.v}[which]
+        views = self._views_of(flat)
+        out = OrderedDict()
+        for tf_name in self.tf_map:
+            v, shape = self._tf_view(views, tf_name)
+            out[tf_name] = v.detach().cpu().numpy().reshape(shape).copy()
+        return out
+
+    def import_tf(self, values, which="params"):
+        flat = {"params": self.params, "grads": self.grads, "m": self.m, "v": self.v}[which]
+        views = self._views_of(flat)
+        for tf_name, arr in values.items():
+            if tf_name not in self.tf_map:
+                continue
+            v, shape = self._tf_view(views, tf_name)
+            a = torch.from_numpy(np.ascontiguousarray(arr, dtype=np.float32).reshape(v.shape)).to(self.device)
+            v.copy_(a)
+
+
+class Linear:
+    """y = act(x W + b) with W [K, N] fp32 master (TF [in, out] layout) and two fp16 operand copies:
+    w_fwd [N, Kp] (= W^T, forward B operand) and w_bwd [K, Np] (dgrad B operand)."""
+
+    def __init__(self, store, name, K, N, act, w_init, b_init=None, in_scale=1.0, w_shape=None, b_shape=None,
+                 tf_w=None, tf_b=None):
+        self.store, self.name, self.K, self.N, self.act = store, name, K, N, ops.ACT_CODES[act]
+        self.in_scale = float(in_scale)
+        self.Kp, self.Np = _pad8(K), _pad8(N)
+        w_init = np.asarray(w_init, np.float32).reshape(K, N)
+        store.add(name + "/w", w_init)
+        store.add(name + "/b", np.zeros(N, np.float32) if b_init is None else np.asarray(b_init, np.float32).reshape(N))
+        if tf_w:
+            store.map_tf(tf_w, name + "/w", w_shape or (K, N))
+        if tf_b:
+            store.map_tf(tf_b, name + "/b", b_shape or (N,))
+        self.w_fwd = self.w_bwd = None
+
+    def materialize(self):
+        dev = self.store.device
+        self.w = self.store.views[self.name + "/w"]
+        self.b = self.store.views[self.name + "/b"]
+        self.gw = self.store.gviews[self.name + "/w"]
+        self.gb = self.store.gviews[self.name + "/b"]
+        self.w_fwd = torch.zeros(self.N, self.Kp, dtype=torch.float16, device=dev)
+        self.w_bwd = torch.zeros(self.K, self.Np, dtype=torch.float16, device=dev)
+
+    def refresh(self):
+        ops.cast_transpose(self.w, self.K, self.N, self.w_bwd, self.Np, self.w_fwd, self.Kp, scale=self.in_scale)
+
+    def forward(self, x, ldx, M, out, ldo, mode=ops.MODE_F16_ACT, act=None):
+        ops.gemm(x, self.w_fwd, out, M=M, N=self.N, K=self.K, lda=ldx, ldb=self.Kp, ldc=ldo, bias=self.b,
+                 mode=mode, act=self.act if act is None else act)
+
+    def wgrad(self, x, ldx, dz, lddz, M, alpha):
+        """gW += alpha * x^T dz (fp32 atomics, split-K over the batch rows); gb += alpha * colsum(dz)."""
+        tiles = -(-self.K // 128) * -(-self.N // (128 if self.N > 64 else 64))
+        kb = -(-M // 64)
+        split = max(1, min(kb // 2 if kb >= 2 else 1, -(-296 // tiles)))
+        ops.gemm(x, dz, self.gw, M=self.K, N=self.N, K=M, lda=ldx, ldb=lddz, ldc=self.N, mn_major=True,
+                 mode=ops.MODE_F32_ATOMIC, alpha=alpha * self.in_scale, split_k=split)
+        ops.colsum(dz, self.gb, M, self.N, lddz, alpha=alpha)
+
+    def dgrad(self, dz, lddz, M, out, ldo, saved=None, ld_saved=0, act=ops.ACT_NONE):
+        """out[M, K] = (dz W^T) * act'(saved)."""
+        if saved is None or act == ops.ACT_NONE:
+            ops.gemm(dz, self.w_bwd, out, M=M, N=self.K, K=self.N, lda=lddz, ldb=self.Np, ldc=ldo,
+                     mode=ops.MODE_F16_ACT, act=ops.ACT_NONE)
+        else:
+            ops.gemm(dz, self.w_bwd, out, M=M, N=self.K, K=self.N, lda=lddz, ldb=self.Np, ldc=ldo, saved=saved,
+                     ld_saved=ld_saved, mode=ops.MODE_F16_DACT, act=act)
+
+
+class Conv(Linear):
+    """NHWC convolution lowered to im2col + tcgen05 GEMM (a2c/utils.py:37-56)."""
+
+    def __init__(self, store, name, H, W, C, nf, rf, stride, act, w_init, same_pad=False, in_scale=1.0,
+                 tf_w=None, tf_b=None, b_shape=None):
+        self.H, self.W, self.C, self.nf, self.rf, self.stride, self.same = H, W, C, nf, rf, stride, same_pad
+        if same_pad:
+            self.OH, self.OW = -(-H // stride), -(-W // stride)
+        else:
+            self.OH, self.OW = (H - rf) // stride + 1, (W - rf) // stride + 1
+        self.P = self.OH * self.OW
+        super().__init__(store, name, rf * rf * C, nf, act, w_init, in_scale=in_scale, w_shape=(rf, rf, C, nf),
+                         b_shape=b_shape or (1, nf, 1, 1), tf_w=tf_w, tf_b=tf_b)
+
+    def im2col(self, x, cols, B, src_idx=None):
+        ops.im2col(x, cols, B, self.H, self.W, self.C, self.rf, self.stride, self.same, src_idx=src_idx)
+
+    def col2im(self, dcols, saved, dx, B, act):
+        ops.col2im(dcols, saved, dx, B, self.H, self.W, self.C, self.rf, self.stride, self.same, act=act)
+
+
+class Tower:
+    """A latent network (conv stack + fc, or mlp) with its activation workspace for `cap` samples."""
+
+    def __init__(self, store, kind, ob_shape, prefix, tf_prefix, rng, cap, init="ortho", num_layers=2,
+                 num_hidden=64, convs=NATURE_CONVS, same_pad=False, fc_hidden=512, tf_style="a2c"):
+        self.kind, self.cap, self.store = kind, cap, store
+        self.convs, self.fcs = [], []
+        winit = (lambda shape, scale: ortho_init(shape, scale, rng)) if init == "ortho" else \
+                (lambda shape, scale: xavier_uniform(shape, rng))
+        if kind in ("cnn", "conv_only"):
+            H, W, C = ob_shape
+            self.in_u8 = True
+            scale_in = 1.0 / 255.0                                           # models.py:19 folded into c1 weights
+            for i, (nm, nf, rf, stride) in enumerate(convs):
+                if tf_style == "a2c":
+                    tfw, tfb, bshape = f"{tf_prefix}/{nm}/w:0", f"{tf_prefix}/{nm}/b:0", (1, nf, 1, 1)
+                else:
+                    cn = "Conv" if i == 0 else f"Conv_{i}"
+                    tfw, tfb, bshape = f"{tf_prefix}/convnet/{cn}/weights:0", f"{tf_prefix}/convnet/{cn}/biases:0", (nf,)
+                conv = Conv(store, f"{prefix}/{nm}", H, W, C, nf, rf, stride, "relu",
+                            winit((rf, rf, C, nf), math.sqrt(2)), same_pad=same_pad,
+                            in_scale=scale_in if i == 0 else 1.0, tf_w=tfw, tf_b=tfb, b_shape=bshape)
+                self.convs.append(conv)
+                H, W, C = conv.OH, conv.OW, nf
+            self.flat = H * W * C
+            if kind == "cnn":
+                self.fcs.append(Linear(store, f"{prefix}/fc1", self.flat, fc_hidden, "relu",
+                                       winit((self.flat, fc_hidden), math.sqrt(2)),
+                                       tf_w=f"{tf_prefix}/fc1/w:0", tf_b=f"{tf_prefix}/fc1/b:0"))
+                self.latent_dim, self.latent_act = fc_hidden, ops.ACT_RELU
+            else:
+                self.latent_dim, self.latent_act = self.flat, ops.ACT_RELU
+            self.in_dim = None
+        elif kind == "mlp":
+            self.in_u8 = False
+            nin = int(np.prod(ob_shape))
+            self.in_dim, self.in_pad = nin, _pad8(nin)
+            for i in range(num_layers):                                       # models.py:94-99 (tanh)
+                self.fcs.append(Linear(store, f"{prefix}/mlp_fc{i}", nin, num_hidden, "tanh",
+                                       winit((nin, num_hidden), math.sqrt(2)),
+                                       tf_w=f"{tf_prefix}/mlp_fc{i}/w:0", tf_b=f"{tf_prefix}/mlp_fc{i}/b:0"))
+                nin = num_hidden
+            self.latent_dim, self.latent_act = nin, ops.ACT_TANH
+        else:
+            raise ValueError(f"unknown network type {kind!r} (supported: cnn, conv_only, mlp)")
+        self.layers = self.convs + self.fcs
+
+    def materialize(self):
+        dev, cap = self.store.device, self.cap
+        f16 = dict(dtype=torch.float16, device=dev)
+        for l in self.layers:
+            l.materialize()
+        self.cols = [torch.empty(cap * c.P, c.K, **f16) for c in self.convs]
+        self.hconv = [torch.empty(cap * c.P, c.nf, **f16) for c in self.convs]
+        self.dcols = [None] + [torch.empty(cap * c.P, c.K, **f16) for c in self.convs[1:]]
+        self.dzconv = [torch.empty(cap * c.P, c.nf, **f16) for c in self.convs]
+        self.hfc = [torch.empty(cap, l.Np, **f16) for l in self.fcs]
+        self.dzfc = [torch.empty(cap, l.Np, **f16) for l in self.fcs]
+        if self.kind == "mlp":
+            self.x0 = torch.zeros(cap, self.in_pad, **f16)
+        # where the heads write d(loss)/d(latent pre-activation)
+        if self.fcs:
+            self.dlatent, self.ld_dlatent = self.dzfc[-1], self.fcs[-1].Np
+        else:
+            self.dlatent, self.ld_dlatent = self.dzconv[-1], self.flat
+
+    def refresh(self):
+        for l in self.layers:
+            l.refresh()
+
+    # x: uint8 [*,H,W,C] images (cnn) or fp16 [*, in_pad] rows (mlp); src_idx gathers samples from it
+    def forward(self, x, B, src_idx=None):
+        assert B <= self.cap
+        if self.convs:
+            cur = x
+            for i, c in enumerate(self.convs):
+                c.im2col(cur, self.cols[i], B, src_idx=src_idx if i == 0 else None)
+                c.forward(self.cols[i], c.K, B * c.P, self.hconv[i], c.nf)
+                cur = self.hconv[i]
+            h, ldh = cur, self.flat                      # [B, OH*OW*C] view of the NHWC activation (H,W,C order)
+        else:
+            if src_idx is not None:                      # row gather == 1x1 im2col
+                ops.im2col(x, self.x0, B, 1, 1, self.in_pad, 1, 1, False, src_idx=src_idx)
+                h = self.x0
+            else:
+                h = x
+            ldh = self.in_pad
+            self._mlp_in = h
+        for i, l in enumerate(self.fcs):
+            l.forward(h, ldh, B, self.hfc[i], l.Np)
+            h, ldh = self.hfc[i], l.Np
+        return h, ldh                                    # latent [B, latent_dim] fp16, row pitch ldh
+
+    # consumes self.dlatent: fp16 [B, ld_dlatent] gradient w.r.t. the latent PRE-activation
+    def backward(self, B, alpha):
+        nfc = len(self.fcs)
+        dz, lddz = self.dlatent, self.ld_dlatent
+        for i in reversed(range(nfc)):
+            l = self.fcs[i]
+            if i > 0:
+                xin, ldx, act_in = self.hfc[i - 1], self.fcs[i - 1].Np, self.fcs[i - 1].act
+            elif self.convs:
+                xin, ldx, act_in = self.hconv[-1], self.flat, ops.ACT_RELU
+            else:
+                xin, ldx, act_in = self._mlp_in, self.in_pad, None
+            l.wgrad(xin, ldx, dz, lddz, B, alpha)
+            if act_in is None:
+                return
+            if i > 0:
+                out, ldo = self.dzfc[i - 1], self.fcs[i - 1].Np
+            else:
+                out, ldo = self.dzconv[-1], self.flat
+            l.dgrad(dz, lddz, B, out, ldo, saved=xin, ld_saved=ldx, act=act_in)
+            dz, lddz = out, ldo
+        for i in reversed(range(len(self.convs))):
+            c = self.convs[i]
+            dzc = self.dzconv[i]
+            c.wgrad(self.cols[i], c.K, dzc, c.nf, B * c.P, alpha)
+            if i == 0:
+                break
+            c.dgrad(dzc, c.nf, B * c.P, self.dcols[i], c.K)
+            c.col2im(self.dcols[i], self.hconv[i - 1], self.dzconv[i - 1], B, act=ops.ACT_RELU)
+
+
+class Optimizer:
+    """Global-norm clip + TF-Adam on the flat buffers (ppo2/model.py:100-114), or per-variable
+    clip_by_norm (deepq/build_graph.py:416-421).  No host synchronisation."""
+
+    def __init__(self, store, eps, max_grad_norm=None, per_variable=False, beta1=0.9, beta2=0.999):
+        self.store, self.eps, self.clip, self.per_variable = store, eps, max_grad_norm, per_variable
+        self.beta1, self.beta2, self.t = beta1, beta2, 0
+        nseg = len(store._specs) if per_variable else 1
+        self.nseg = nseg
+        self.sumsq = torch.zeros(nseg, dtype=torch.float64, device=store.device)
+        self.seg_off = torch.from_numpy(store.segment_offsets()).to(store.device) if per_variable else None
+
+    def step(self, lr):
+        s = self.store
+        self.t += 1
+        lr_t = lr * math.sqrt(1.0 - self.beta2 ** self.t) / (1.0 - self.beta1 ** self.t)
+        clip = self.clip if self.clip is not None else 0.0
+        if clip > 0:
+            if self.per_variable:
+                ops.seg_sumsq(s.grads, self.seg_off, self.nseg, self.sumsq)
+            else:
+                ops.sumsq(s.grads, self.sumsq)
+        ops.clip_adam(s.params, s.grads, s.m, s.v, lr_t, self.beta1, self.beta2, self.eps, clip,
+                      self.sumsq if clip > 0 else None, self.seg_off if (clip > 0 and self.per_variable) else None,
+                      self.nseg if self.per_variable else 0)

@@ -1,0 +1,181 @@
+"""PPO2 rollout collection with an HBM-resident rollout buffer and the GAE scan on device.
+
+Drop-in for baselines/ppo2/runner.py Runner (+ common/runners.py AbstractEnvRunner):
+  * `Runner(env=, model=, nsteps=, gamma=, lam=)`, `.run()` returns the reference tuple
+    (obs, returns, masks, actions, values, neglogpacs, states, epinfos) as flat env-major numpy arrays
+    (sf01 layout, runner.py:66-74) -- used for parity tests and by foreign callers;
+  * `.run_device()` returns a `Rollout` handle whose arrays never leave HBM; the learner indexes it with
+    the shuffled minibatch indices (ppo2.py:157-165) through `Rollout.src_index`.
+Per env step only the observation (host->device) and the actions (device->host) cross PCIe.
+"""
+import numpy as np
+import torch
+
+from .. import ops
+
+
+class Rollout:
+    """Time-major [T, N] rollout arrays in HBM.  Flat env-major index i = e*T + t (runner.py:69-74) maps to
+    buffer offset t*N + e."""
+
+    def __init__(self, T, N, obs_store_shape, obs_dtype, discrete, act_dim, device):
+        self.T, self.N, self.device = T, N, device
+        f32 = dict(dtype=torch.float32, device=device)
+        self.obs = torch.zeros((T, N) + tuple(obs_store_shape), dtype=obs_dtype, device=device)
+        self.rewards = torch.zeros(T, N, **f32)
+        self.values = torch.zeros(T, N, **f32)
+        self.neglogpacs = torch.zeros(T, N, **f32)
+        self.dones = torch.zeros(T, N, dtype=torch.uint8, device=device)        # done BEFORE step t (runner.py:34)
+        self.actions = torch.zeros((T, N) if discrete else (T, N, act_dim),
+                                   dtype=torch.int64 if discrete else torch.float32, device=device)
+        self.advs = torch.zeros(T, N, **f32)
+        self.returns = torch.zeros(T, N, **f32)
+        self.last_values = torch.zeros(N, **f32)
+        self.last_dones = torch.zeros(N, dtype=torch.uint8, device=device)
+        self._arange = None
+
+    @property
+    def nbatch(self):
+        return self.T * self.N
+
+    def flat(self, name):
+        a = getattr(self, name)
+        return a.view((self.T * self.N,) + tuple(a.shape[2:]))
+
+    def src_index(self, inds):
+        """env-major flat indices (device int64) -> buffer offsets."""
+        return (inds % self.T) * self.N + torch.div(inds, self.T, rounding_mode="floor")
+
+    def to_reference_numpy(self, name):
+        """sf01(arr): swap axes 0,1 and flatten (runner.py:69-74) on the host copy."""
+        a = getattr(self, name).cpu().numpy()
+        s = a.shape
+        return a.swapaxes(0, 1).reshape(s[0] * s[1], *s[2:])
+
+
+class Runner:
+    def __init__(self, *, env, model, nsteps, gamma, lam):
+        self.env, self.model, self.nsteps = env, model, nsteps
+        self.lam, self.gamma = lam, gamma
+        self.nenv = nenv = env.num_envs if hasattr(env, 'num_envs') else 1
+        ob_space = env.observation_space
+        self.batch_ob_shape = (nenv * nsteps,) + tuple(ob_space.shape)
+        self.device = model.device
+        net = model.net
+        self.device_env = hasattr(env, "step_device")
+        self.u8 = net.tower_pi.in_u8
+        store_shape = tuple(ob_space.shape) if self.u8 else (net.tower_pi.in_pad,)
+        self.rollout = Rollout(nsteps, nenv, store_shape, torch.uint8 if self.u8 else torch.float16, net.discrete,
+                               net.nout, self.device)
+        # pinned staging for the per-step host<->device traffic
+        pin = torch.cuda.is_available()
+        np_dtype = np.dtype(ob_space.dtype.name) if hasattr(ob_space.dtype, "name") else np.dtype(ob_space.dtype)
+        self._obs_pin = torch.zeros((nenv,) + tuple(ob_space.shape), dtype=torch.from_numpy(np.zeros(1, np_dtype)).dtype)
+        if pin:
+            self._obs_pin = self._obs_pin.pin_memory()
+        self.obs = self._obs_pin.numpy()                                       # runners.py:10 self.obs
+        act_shape = (nenv,) if net.discrete else (nenv, net.nout)
+        self._act_pin = torch.zeros(act_shape, dtype=torch.int64 if net.discrete else torch.float32)
+        self._rew_host = torch.zeros(nsteps, nenv, dtype=torch.float32)
+        self._done_host = torch.zeros(nsteps, nenv, dtype=torch.uint8)
+        if pin:
+            self._act_pin, self._rew_host, self._done_host = (t.pin_memory() for t in
+                                                              (self._act_pin, self._rew_host, self._done_host))
+        self._f32_stage = None if self.u8 else torch.zeros(nenv, int(np.prod(ob_space.shape)), dtype=torch.float32,
+                                                           device=self.device)
+        self._cur = torch.zeros((nenv,) + store_shape, dtype=self.rollout.obs.dtype, device=self.device)
+        self._obs_src = None
+        if self.device_env:
+            self._dev_obs = env.reset_device()
+        else:
+            self._take_obs(env.reset())                                        # runners.py:11
+        self.states = model.initial_state
+        self.dones = np.zeros(nenv, dtype=np.bool_)                            # runners.py:14
+        self._dev_dones = torch.zeros(nenv, dtype=torch.uint8, device=self.device)
+
+    def _take_obs(self, obs):
+        """`self.obs[:] = obs` of the reference (runner.py:38), except that an env which already hands out
+        PINNED host memory is uploaded from directly (no extra host memcpy)."""
+        t = torch.from_numpy(obs) if isinstance(obs, np.ndarray) and obs.flags.c_contiguous else None
+        if t is not None and t.dtype == self._obs_pin.dtype and t.shape == self._obs_pin.shape and \
+                torch.cuda.is_available() and t.is_pinned():
+            self._obs_src, self.obs = t, obs
+        else:
+            self._obs_src = None
+            self.obs = self._obs_pin.numpy()
+            self.obs[:] = obs
+
+    # -- stage the current observation into `dst` (rollout.obs[t] or a temp) in the network's input format
+    def _upload_obs(self, dst):
+        if self.device_env:
+            src = self._dev_obs
+            if self.u8:
+                dst.copy_(src)
+            else:
+                ops.cast_f32_f16(src.reshape(self.nenv, -1).float().contiguous(), dst, self.nenv,
+                                 self.model.net.tower_pi.in_dim, self.model.net.tower_pi.in_dim,
+                                 self.model.net.tower_pi.in_pad)
+            return
+        src = self._obs_src if self._obs_src is not None else self._obs_pin
+        if self.u8:
+            dst.copy_(src, non_blocking=True)
+        else:
+            self._f32_stage.copy_(src.reshape(self.nenv, -1), non_blocking=True)
+            ops.cast_f32_f16(self._f32_stage, dst, self.nenv, self.model.net.tower_pi.in_dim,
+                             self.model.net.tower_pi.in_dim, self.model.net.tower_pi.in_pad)
+
+    def run_device(self, noise=None):
+        """Collect nsteps transitions; returns (Rollout, epinfos).  noise: optional [T, N, nA|d] float32 host
+        array of injected sampling noise (parity tests)."""
+        ro, model, T, N = self.rollout, self.model, self.nsteps, self.nenv
+        epinfos = []
+        with torch.cuda.device(self.device):
+            nz = None if noise is None else torch.as_tensor(np.ascontiguousarray(noise), dtype=torch.float32).to(self.device)
+            for t in range(T):
+                self._upload_obs(ro.obs[t])
+                model.step_device(ro.obs[t], ro.actions[t], ro.values[t], ro.neglogpacs[t],
+                                  noise=None if nz is None else nz[t])
+                if self.device_env:
+                    ro.dones[t].copy_(self._dev_dones)
+                    self._dev_obs, rew, self._dev_dones = self.env.step_device(ro.actions[t])
+                    ro.rewards[t].copy_(rew)
+                    continue
+                self._done_host[t] = torch.from_numpy(self.dones.astype(np.uint8))       # mb_dones.append(self.dones)
+                self._act_pin.copy_(ro.actions[t], non_blocking=True)
+                torch.cuda.current_stream().synchronize()
+                actions = self._act_pin.numpy()
+                obs, rewards, self.dones, infos = self.env.step(actions)                 # runner.py:38
+                self._take_obs(obs)
+                self.dones = np.asarray(self.dones, dtype=np.bool_)
+                for info in infos:
+                    maybeepinfo = info.get('episode') if info else None
+                    if maybeepinfo:
+                        epinfos.append(maybeepinfo)
+                self._rew_host[t] = torch.from_numpy(np.asarray(rewards, dtype=np.float32))
+            # bootstrap value of the final observation (runner.py:50)
+            self._upload_obs(self._cur)
+            model.value_device(self._cur, ro.last_values)
+            if self.device_env:
+                ro.last_dones.copy_(self._dev_dones)
+            else:
+                ro.rewards.copy_(self._rew_host, non_blocking=True)
+                ro.dones.copy_(self._done_host, non_blocking=True)
+                ro.last_dones.copy_(torch.from_numpy(self.dones.astype(np.uint8)))
+            # GAE(lambda) + returns (runner.py:53-65) in one kernel over the resident buffers
+            ops.gae_scan(ro.rewards, ro.values, ro.dones, ro.last_values, ro.last_dones, ro.advs, ro.returns,
+                         self.gamma, self.lam)
+        return ro, epinfos
+
+    def run(self, noise=None):
+        """Reference-compatible return value (numpy, flat env-major)."""
+        ro, epinfos = self.run_device(noise=noise)
+        torch.cuda.synchronize(self.device)
+        if self.u8:
+            obs = ro.to_reference_numpy("obs")
+        else:
+            o = ro.obs.float().cpu().numpy()[..., :self.model.net.tower_pi.in_dim]
+            o = o.reshape((self.nsteps, self.nenv) + tuple(self.env.observation_space.shape))
+            obs = o.swapaxes(0, 1).reshape(self.batch_ob_shape)
+        masks = ro.to_reference_numpy("dones").astype(np.bool_)
+        return (obs, ro.to_reference_numpy("returns"), masks, ro.to_reference_numpy("actions"),
+                ro.to_reference_numpy("values"), ro.to_reference_numpy("neglogpacs"), self.states, epinfos)

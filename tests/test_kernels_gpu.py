@@ -421,7 +421,8 @@ def test_per_trace_vs_reference_golden(ops):
         assert np.array_equal(idx.cpu().numpy(), g["idxes"][r])                      # bit exact indices
         assert np.allclose(w.cpu().numpy(), g["weights"][r], rtol=1e-13, atol=0)     # pow() may differ by ulps
         pr = g["priorities"][r]
-        ops.tree_set(s, m, cap, idx, dev(pr ** alpha))      # duplicates inside idx: last write wins
+        # python-float pow like the reference (numpy's vectorised pow may differ by an ulp)
+        ops.tree_set(s, m, cap, idx, dev(np.array([float(x) ** alpha for x in pr])))   # duplicates: last write wins
         state["maxp"] = max(state["maxp"], float(pr.max()))
         add(int(g["adds_after_round"][r]))
     assert np.array_equal(s.cpu().numpy(), g["final_sum"])
@@ -441,7 +442,7 @@ def test_per_large_tree_vs_oracle(ops):
     cap = size
     s = torch.zeros(2 * cap, dtype=torch.float64, device="cuda")
     m = torch.full((2 * cap,), float("inf"), dtype=torch.float64, device="cuda")
-    ops.tree_set(s, m, cap, dev(np.arange(size, dtype=np.int64)), dev(pri ** 0.6))
+    ops.tree_set(s, m, cap, dev(np.arange(size, dtype=np.int64)), dev(np.array([float(x) ** 0.6 for x in pri])))
     torch.cuda.synchronize()
     assert np.array_equal(s.cpu().numpy(), per.sum_tree.value)
     assert np.array_equal(m.cpu().numpy(), per.min_tree.value)
