@@ -63,8 +63,44 @@ def load():
     return lib
 
 
-def call(name, *args):
+LAUNCHES = 0          # C-ABI kernel-launching calls made by this process (bench.py reports the delta)
+_prof = None          # list of (label, start_event, end_event, flops, bytes) while profiling
+
+
+def call(name, *args, label=None, flops=0, nbytes=0):
+    global LAUNCHES
     lib = load()
-    rc = getattr(lib, name)(*args)
+    LAUNCHES += 1
+    if _prof is not None:
+        import torch
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        rc = getattr(lib, name)(*args)
+        e1.record()
+        _prof.append((label or name, e0, e1, flops, nbytes))
+    else:
+        rc = getattr(lib, name)(*args)
     if rc != 0:
         raise RuntimeError(f"{name} failed (rc={rc}): {lib.b200rl_last_error().decode()}")
+
+
+def profile_begin():
+    """Start timing every C-ABI call with CUDA events on the launching stream (no host sync is added)."""
+    global _prof
+    _prof = []
+
+
+def profile_end():
+    """-> {label: [total_ms, calls, algorithmic_flops, algorithmic_bytes]}"""
+    global _prof
+    import torch
+    torch.cuda.synchronize()
+    out = {}
+    for label, e0, e1, flops, nbytes in _prof:
+        acc = out.setdefault(label, [0.0, 0, 0.0, 0.0])
+        acc[0] += e0.elapsed_time(e1)
+        acc[1] += 1
+        acc[2] += flops
+        acc[3] += nbytes
+    _prof = None
+    return out

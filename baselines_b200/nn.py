@@ -159,7 +159,7 @@ class Linear:
 
     def forward(self, x, ldx, M, out, ldo, mode=ops.MODE_F16_ACT, act=None):
         ops.gemm(x, self.w_fwd, out, M=M, N=self.N, K=self.K, lda=ldx, ldb=self.Kp, ldc=ldo, bias=self.b,
-                 mode=mode, act=self.act if act is None else act)
+                 mode=mode, act=self.act if act is None else act, tag="fwd." + self.name)
 
     def wgrad(self, x, ldx, dz, lddz, M, alpha):
         """gW += alpha * x^T dz (fp32 atomics, split-K over the batch rows); gb += alpha * colsum(dz)."""
@@ -167,17 +167,17 @@ class Linear:
         kb = -(-M // 64)
         split = max(1, min(kb // 2 if kb >= 2 else 1, -(-296 // tiles)))
         ops.gemm(x, dz, self.gw, M=self.K, N=self.N, K=M, lda=ldx, ldb=lddz, ldc=self.N, mn_major=True,
-                 mode=ops.MODE_F32_ATOMIC, alpha=alpha * self.in_scale, split_k=split)
+                 mode=ops.MODE_F32_ATOMIC, alpha=alpha * self.in_scale, split_k=split, tag="wgrad." + self.name)
         ops.colsum(dz, self.gb, M, self.N, lddz, alpha=alpha)
 
     def dgrad(self, dz, lddz, M, out, ldo, saved=None, ld_saved=0, act=ops.ACT_NONE):
         """out[M, K] = (dz W^T) * act'(saved)."""
         if saved is None or act == ops.ACT_NONE:
             ops.gemm(dz, self.w_bwd, out, M=M, N=self.K, K=self.N, lda=lddz, ldb=self.Np, ldc=ldo,
-                     mode=ops.MODE_F16_ACT, act=ops.ACT_NONE)
+                     mode=ops.MODE_F16_ACT, act=ops.ACT_NONE, tag="dgrad." + self.name)
         else:
             ops.gemm(dz, self.w_bwd, out, M=M, N=self.K, K=self.N, lda=lddz, ldb=self.Np, ldc=ldo, saved=saved,
-                     ld_saved=ld_saved, mode=ops.MODE_F16_DACT, act=act)
+                     ld_saved=ld_saved, mode=ops.MODE_F16_DACT, act=act, tag="dgrad." + self.name)
 
 
 class Conv(Linear):
@@ -195,10 +195,10 @@ class Conv(Linear):
                          b_shape=b_shape or (1, nf, 1, 1), tf_w=tf_w, tf_b=tf_b)
 
     def im2col(self, x, cols, B, src_idx=None):
-        ops.im2col(x, cols, B, self.H, self.W, self.C, self.rf, self.stride, self.same, src_idx=src_idx)
+        ops.im2col(x, cols, B, self.H, self.W, self.C, self.rf, self.stride, self.same, src_idx=src_idx, tag=self.name)
 
     def col2im(self, dcols, saved, dx, B, act):
-        ops.col2im(dcols, saved, dx, B, self.H, self.W, self.C, self.rf, self.stride, self.same, act=act)
+        ops.col2im(dcols, saved, dx, B, self.H, self.W, self.C, self.rf, self.stride, self.same, act=act, tag=self.name)
 
 
 class Tower:

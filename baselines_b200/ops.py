@@ -39,41 +39,56 @@ def gae_scan(rewards, values, dones, last_values, last_dones, advs, returns, gam
         _chk(t, dt, nm)
         assert t.is_contiguous(), nm
     _lib.call("b200rl_gae_scan", _ptr(rewards), _ptr(values), _ptr(dones), _ptr(last_values), _ptr(last_dones),
-              _ptr(advs), _ptr(returns), T, N, float(gamma), float(lam), int(variant), _stream())
+              _ptr(advs), _ptr(returns), T, N, float(gamma), float(lam), int(variant), _stream(),
+              label="gae_scan", nbytes=17.0 * T * N + 5.0 * N)
 
 
 def gemm(A, B, C, *, M, N, K, lda, ldb, ldc, bias=None, saved=None, ld_saved=0, mn_major=False,
-         mode=MODE_F16_ACT, act=ACT_NONE, alpha=1.0, split_k=1, max_ctas=0):
+         mode=MODE_F16_ACT, act=ACT_NONE, alpha=1.0, split_k=1, max_ctas=0, tag=None):
     _chk(A, torch.float16, "A")
     _chk(B, torch.float16, "B")
     _chk(bias, torch.float32, "bias")
     _chk(saved, torch.float16, "saved")
     _lib.call("b200rl_gemm_f16", _ptr(A), _ptr(B), _ptr(C), _ptr(bias), _ptr(saved), int(M), int(N), int(K),
               int(lda), int(ldb), int(ldc), int(ld_saved), int(bool(mn_major)), int(mode), int(act), float(alpha),
-              int(split_k), int(max_ctas), _stream())
+              int(split_k), int(max_ctas), _stream(), label="gemm." + (tag or ("wgrad" if mn_major else "tn")),
+              flops=2.0 * M * N * K,
+              nbytes=2.0 * (M * K + N * K) + M * N * (2 if mode in (MODE_F16_ACT, MODE_F16_DACT) else 4)
+              + (2.0 * M * N if mode == MODE_F16_DACT else 0))
 
 
-def im2col(x, cols, B, H, W, C, rf, stride, same_pad=False, src_idx=None):
+def _conv_out(H, W, rf, stride, same_pad):
+    if same_pad:
+        return -(-H // stride), -(-W // stride)
+    return (H - rf) // stride + 1, (W - rf) // stride + 1
+
+
+def im2col(x, cols, B, H, W, C, rf, stride, same_pad=False, src_idx=None, tag=None):
     _chk(src_idx, torch.int64, "src_idx")
     _chk(cols, torch.float16, "cols")
     src_u8 = x.dtype == torch.uint8
     if not src_u8:
         _chk(x, torch.float16, "x")
+    OH, OW = _conv_out(H, W, rf, stride, same_pad)
     _lib.call("b200rl_im2col", _ptr(x), int(src_u8), _ptr(src_idx), _ptr(cols), int(B), H, W, C, rf, stride,
-              int(bool(same_pad)), _stream())
+              int(bool(same_pad)), _stream(), label="im2col." + (tag or ("u8" if src_u8 else "f16")),
+              nbytes=float(B) * H * W * C * (1 if src_u8 else 2) + 2.0 * B * OH * OW * rf * rf * C)
 
 
-def col2im(dcols, saved, dx, B, H, W, C, rf, stride, same_pad=False, act=ACT_NONE):
+def col2im(dcols, saved, dx, B, H, W, C, rf, stride, same_pad=False, act=ACT_NONE, tag=None):
     _chk(dcols, torch.float16, "dcols")
     _chk(dx, torch.float16, "dx")
+    OH, OW = _conv_out(H, W, rf, stride, same_pad)
     _lib.call("b200rl_col2im", _ptr(dcols), _ptr(saved), _ptr(dx), int(B), H, W, C, rf, stride, int(bool(same_pad)),
-              int(act), _stream())
+              int(act), _stream(), label="col2im." + (tag or ""),
+              nbytes=2.0 * B * OH * OW * rf * rf * C + 2.0 * B * H * W * C * (2 if saved is not None else 1))
 
 
 def colsum(dz, db, rows, C, ld, alpha=1.0):
     _chk(dz, torch.float16, "dz")
     _chk(db, torch.float32, "db")
-    _lib.call("b200rl_colsum", _ptr(dz), _ptr(db), int(rows), int(C), int(ld), float(alpha), _stream())
+    _lib.call("b200rl_colsum", _ptr(dz), _ptr(db), int(rows), int(C), int(ld), float(alpha), _stream(),
+              label="colsum", nbytes=2.0 * rows * C)
 
 
 def cat_step(logits, ld, nA, vpred, ldv, actions, values, neglogp, B, uniforms=None, seed=0, offset=0):
@@ -119,7 +134,7 @@ def gauss_loss(mean, ld, logstd, d, vpred, ldv, actions, src_idx, returns, old_v
 def sumsq(g, out):
     _chk(g, torch.float32, "g")
     _chk(out, torch.float64, "out")
-    _lib.call("b200rl_sumsq", _ptr(g), g.numel(), _ptr(out), _stream())
+    _lib.call("b200rl_sumsq", _ptr(g), g.numel(), _ptr(out), _stream(), label="sumsq", nbytes=4.0 * g.numel())
 
 
 def seg_sumsq(g, seg_off, nseg, out):
@@ -132,7 +147,7 @@ def clip_adam(p, g, m, v, lr_t, beta1, beta2, eps, clip, sumsq_buf, seg_off=None
         _chk(t, torch.float32, nm)
     _lib.call("b200rl_clip_adam", _ptr(p), _ptr(g), _ptr(m), _ptr(v), p.numel(), float(lr_t), float(beta1),
               float(beta2), float(eps), float(clip if clip else 0.0), _ptr(sumsq_buf), _ptr(seg_off), int(nseg),
-              _stream())
+              _stream(), label="clip_adam", nbytes=28.0 * p.numel())
 
 
 def cast_transpose(src, R, C, dst, ld_dst, dstT, ld_t, scale=1.0):
