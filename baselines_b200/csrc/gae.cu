@@ -9,10 +9,10 @@
 // Algorithmic bytes per (t, env) element: r(4) + V(4) + done(1) read, adv(4) + ret(4) written = 17 B.
 //
 // Two kernels:
-//   gae_bulk_kernel  (default when N % 32 == 0): one warp per 32 envs; time tiles of 32 steps are
-//       staged through a 4-deep shared-memory ring by 1-D TMA bulk copies (cp.async.bulk + mbarrier
-//       tx-count), so >100 KB per SM is in flight without holding registers; lanes read their env's
-//       column conflict-free; outputs are 128 B coalesced stores.
+//   gae_tma_kernel   (default when N % 32 == 0): one warp per 32 envs; 32-step x 32-env tiles are staged
+//       through a 4-deep shared-memory ring by 2-D TMA tile loads (cp.async.bulk.tensor + mbarrier
+//       tx-count, three loads per tile), so ~36 KB per warp is in flight without holding registers; lanes
+//       read their env's column conflict-free; outputs are 128 B coalesced streaming stores.
 //   gae_direct_kernel (any N): thread per env with a 16-step register prefetch.
 #include "common.cuh"
 
@@ -85,10 +85,13 @@ struct __align__(128) GaeStage {
   uint8_t d[GAE_TT][32];
 };
 
+// One warp per 32 envs.  Each 32-step x 32-env tile is fetched by THREE 2-D TMA tile loads (rewards,
+// values, dones) into a 4-deep smem ring; tiles beyond T are zero-filled by TMA and never read.
 __global__ void __launch_bounds__(32)
-gae_bulk_kernel(const float* __restrict__ rew, const float* __restrict__ val, const uint8_t* __restrict__ done,
-                const float* __restrict__ last_val, const uint8_t* __restrict__ last_done, float* __restrict__ adv,
-                float* __restrict__ ret, int T, int N, float gamma_f, double gl) {
+gae_tma_kernel(const __grid_constant__ CUtensorMap tm_rew, const __grid_constant__ CUtensorMap tm_val,
+               const __grid_constant__ CUtensorMap tm_done, const float* __restrict__ last_val,
+               const uint8_t* __restrict__ last_done, float* __restrict__ adv, float* __restrict__ ret, int T, int N,
+               float gamma_f, double gl) {
   __shared__ GaeStage stage[GAE_NS];
   __shared__ __align__(8) uint64_t full[GAE_NS];
   const int lane = threadIdx.x;
@@ -97,22 +100,20 @@ gae_bulk_kernel(const float* __restrict__ rew, const float* __restrict__ val, co
   const int nchunks = (T + GAE_TT - 1) / GAE_TT;
 
   if (lane == 0) {
+    tma_prefetch_desc(&tm_rew);
+    tma_prefetch_desc(&tm_val);
+    tma_prefetch_desc(&tm_done);
     for (int s = 0; s < GAE_NS; ++s) mbar_init(&full[s], 1);
     fence_barrier_init();
   }
   __syncwarp();
 
-  // chunk c covers t in [c*TT, min((c+1)*TT, T)); chunks are consumed from the last to the first
   auto issue = [&](int c, int s) {
-    const int t0 = c * GAE_TT;
-    const int rows = min(GAE_TT, T - t0);
-    if (lane == 0) mbar_arrive_expect_tx(&full[s], (uint32_t)rows * (128 + 128 + 32));
-    __syncwarp();
-    if (lane < rows) {
-      const size_t o = (size_t)(t0 + lane) * N + e0;
-      bulk_load_1d(&stage[s].r[lane][0], rew + o, 128, &full[s]);
-      bulk_load_1d(&stage[s].v[lane][0], val + o, 128, &full[s]);
-      bulk_load_1d(&stage[s].d[lane][0], done + o, 32, &full[s]);
+    if (lane == 0) {
+      mbar_arrive_expect_tx(&full[s], (uint32_t)(GAE_TT * (128 + 128 + 32)));
+      tma_load_2d(&stage[s].r[0][0], &tm_rew, &full[s], e0, c * GAE_TT);
+      tma_load_2d(&stage[s].v[0][0], &tm_val, &full[s], e0, c * GAE_TT);
+      tma_load_2d(&stage[s].d[0][0], &tm_done, &full[s], e0, c * GAE_TT);
     }
   };
 
@@ -149,6 +150,37 @@ gae_bulk_kernel(const float* __restrict__ rew, const float* __restrict__ val, co
   }
 }
 
+typedef CUresult (*PFN_encodeTiledGae)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                       const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
+                                       CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
+                                       CUtensorMapFloatOOBfill);
+
+static int make_tmap_tn(CUtensorMap* tm, const void* ptr, int T, int N, int elem_bytes) {
+  static PFN_encodeTiledGae enc = nullptr;
+  if (!enc) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess ||
+        q != cudaDriverEntryPointSuccess) {
+      set_last_error("cuTensorMapEncodeTiled entry point unavailable");
+      return B200RL_ERR_DRIVER;
+    }
+    enc = reinterpret_cast<PFN_encodeTiledGae>(p);
+  }
+  cuuint64_t gdim[2] = {(cuuint64_t)N, (cuuint64_t)T};
+  cuuint64_t gstr[1] = {(cuuint64_t)N * elem_bytes};
+  cuuint32_t box[2] = {32, (cuuint32_t)GAE_TT};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(tm, elem_bytes == 4 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_UINT8, 2,
+                   const_cast<void*>(ptr), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_last_error("gae: cuTensorMapEncodeTiled failed (%d) T=%d N=%d elem=%d", (int)r, T, N, elem_bytes);
+    return B200RL_ERR_DRIVER;
+  }
+  return B200RL_OK;
+}
+
 int gae_scan_impl(const float* rew, const float* val, const uint8_t* done, const float* last_val,
                   const uint8_t* last_done, float* adv, float* ret, int T, int N, double gamma, double lam,
                   int variant, cudaStream_t stream) {
@@ -161,8 +193,13 @@ int gae_scan_impl(const float* rew, const float* val, const uint8_t* done, const
   if (variant == 1) B200RL_REQUIRE(aligned, "gae: bulk variant needs N %% 32 == 0 and 16 B aligned inputs");
   const bool bulk = (variant == 1) || (variant < 0 && aligned);
   if (bulk) {
-    gae_bulk_kernel<<<N / 32, 32, 0, stream>>>(rew, val, done, last_val, last_done, adv, ret, T, N, gamma_f, gl);
-    return check_launch("gae_bulk_kernel");
+    CUtensorMap tr, tv, td;
+    int rc;
+    if ((rc = make_tmap_tn(&tr, rew, T, N, 4)) != 0) return rc;
+    if ((rc = make_tmap_tn(&tv, val, T, N, 4)) != 0) return rc;
+    if ((rc = make_tmap_tn(&td, done, T, N, 1)) != 0) return rc;
+    gae_tma_kernel<<<N / 32, 32, 0, stream>>>(tr, tv, td, last_val, last_done, adv, ret, T, N, gamma_f, gl);
+    return check_launch("gae_tma_kernel");
   }
   const int threads = 64;
   gae_direct_kernel<16><<<ceil_div(N, threads), threads, 0, stream>>>(rew, val, done, last_val, last_done, adv, ret,

@@ -123,6 +123,30 @@ def cpu_reference_update(cfg, nenvs_sample, threads=None, steps=1, warmup=0):
     return n * T, times
 
 
+def pick_cpu_threads():
+    """All the host threads the CPU path can USE: torch intra-op threads beyond the physical cores this
+    process may run on only add contention (128 threads were 100x slower than 8 on the first box), so probe a
+    small conv workload over candidate counts <= the affinity mask and keep the fastest."""
+    import torch
+    import torch.nn.functional as F
+    avail = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    cands = sorted({c for c in (4, 8, 16, 32, 64, avail) if c <= avail}) or [1]
+    x = torch.randn(64, 4, 84, 84)
+    w = torch.randn(32, 4, 8, 8)
+    best, best_t = cands[0], float("inf")
+    for c in cands:
+        torch.set_num_threads(c)
+        F.conv2d(x, w, stride=4)
+        t0 = time.perf_counter()
+        for _ in range(3):
+            F.conv2d(x, w, stride=4)
+        dt = time.perf_counter() - t0
+        if dt < best_t:
+            best, best_t = c, dt
+    torch.set_num_threads(best)
+    return best
+
+
 def run_reference(args):
     import torch
     rank = int(os.environ.get("RANK", "0"))
@@ -130,7 +154,7 @@ def run_reference(args):
         return
     cfg = CFG2
     n = args.ref_envs
-    threads = os.cpu_count()
+    threads = pick_cpu_threads()
     nb, times = cpu_reference_update(cfg, n, threads=threads, steps=args.steps, warmup=min(args.warmup, 1))
     ms = 1000.0 * float(np.mean(times))
     val = nb / (ms / 1000.0)
@@ -201,10 +225,12 @@ def main():
         st = run_epochs(model, ro, cfg["lr"], cfg["cliprange"], nbatch, nbatch_train, cfg["noptepochs"], dev)
         return torch.stack(st).mean(dim=0)
 
-    def timed(model, runner, steps, warmup, read_back):
+    def timed(model, runner, steps, warmup, read_back, profile=False):
         for _ in range(warmup):
             update(model, runner)
         torch.cuda.synchronize()
+        if profile:
+            _lib.profile_begin()
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
@@ -231,9 +257,7 @@ def main():
     if rank == 0:
         sampler.start()
     prof = None
-    if not args.no_profile:
-        _lib.profile_begin()
-    ms_step, launches = timed(model, runner, args.steps, args.warmup, read_back=False)
+    ms_step, launches = timed(model, runner, args.steps, args.warmup, read_back=False, profile=not args.no_profile)
     if not args.no_profile:
         prof = _lib.profile_end()
     clocks = sampler.stop() if rank == 0 else None
@@ -286,10 +310,26 @@ def main():
     cpu_baseline = None
     if not args.no_cpu_baseline:
         n = args.ref_envs
-        nb, times = cpu_reference_update(cfg, n, threads=os.cpu_count(), steps=1, warmup=0)
+        nb, times = cpu_reference_update(cfg, n, threads=pick_cpu_threads(), steps=1, warmup=0)
         cpu_baseline = {"value": nb / times[0], "unit": "env-steps/s", "cores": torch.get_num_threads(),
                         "kind": "port", "sample": f"one PPO2 update on {n} envs x {T} steps (same per-sample work), "
                                                   f"torch-CPU fp32 oracle port of the TF1 graph"}
+
+    targets = None
+    try:
+        sys.path.insert(0, os.path.join(ROOT, "tools"))
+        import microbench
+        mb = microbench.run(quick=True)
+        g3 = mb["gae"][1]
+        targets = {"gae_cfg3": {"T": g3["T"], "N": g3["N"], "ms": g3["ms"], "achieved_gbs": g3["gbs"],
+                                "peak_gbs": peaks["hbm_gbs"], "frac": g3["gbs"] / peaks["hbm_gbs"], "target": 0.6},
+                   "gae_cfg2": {"ms": mb["gae"][0]["ms"], "achieved_gbs": mb["gae"][0]["gbs"],
+                                "note": "8.9 MB: L2-resident / launch-bound, not an HBM measurement"},
+                   "fc1": [{"kind": c["kind"], "M": c["M"], "tflops": c["tflops"], "peak": peaks["bf16_tflops"],
+                            "frac": c["tflops"] / peaks["bf16_tflops"], "target": 0.5} for c in mb["fc1"]],
+                   "how": mb["l2_flush"] + "; CUDA events per launch, median of 10 after 3 warm-ups"}
+    except Exception as ex:                                    # never lose the headline line to an extra
+        targets = {"error": repr(ex)}
 
     out = {"metric": "PPO2 learner env-steps/sec", "value": value, "unit": "env-steps/s", "n_gpus": world,
            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
@@ -300,7 +340,7 @@ def main():
                       "l2": "inputs larger than L2 (rollout obs 14.8 GB, every minibatch streams 3.7 GB)",
                       "train_chunk": model.chunk},
            "tflops_per_step": 127.5 * N / 4096, "gpu_launches": launches, "clocks": clocks, "e2e": e2e,
-           "roofline": roofline, "cpu_baseline": cpu_baseline, "kernels": kernels}
+           "roofline": roofline, "cpu_baseline": cpu_baseline, "targets": targets, "kernels": kernels}
     print(json.dumps(out), flush=True)
     if world > 1:
         dist.destroy_process_group()
