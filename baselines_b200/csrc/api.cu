@@ -18,6 +18,10 @@ void set_last_error(const char* fmt, ...) {
 
 int gemm_f16_impl(const void*, const void*, void*, const float*, const void*, int, int, int, long long, long long,
                   long long, long long, int, int, int, float, int, int, cudaStream_t);
+int conv_gemm_impl(const void*, long long, int, int, int, int, int, int, int, int, int, int, int, const void*,
+                   long long, void*, long long, const float*, const void*, long long, int, int, int, int, float, int,
+                   int, int, int, int, cudaStream_t);
+int dgrad_weights_impl(const float*, void*, int, int, int, int, int, long long, cudaStream_t);
 int gae_scan_impl(const float*, const float*, const uint8_t*, const float*, const uint8_t*, float*, float*, int, int,
                   double, double, int, cudaStream_t);
 int im2col_impl(const void*, int, const long long*, void*, long long, int, int, int, int, int, int, cudaStream_t);
@@ -74,6 +78,19 @@ int b200rl_gemm_f16(const void* A, const void* B, void* C, const float* bias, co
                     float alpha, int split_k, int max_ctas, void* stream) {
   return gemm_f16_impl(A, B, C, bias, saved, M, N, K, lda, ldb, ldc, ld_saved, mn_major, mode, act, alpha, split_k,
                        max_ctas, S(stream));
+}
+
+int b200rl_conv_gemm(const void* x, long long B, int H, int W, int C, int R, int S, int stride_h, int stride_w,
+                     int pad_h, int pad_w, int OH, int OW, const void* Wt_or_dz, long long ldb, void* out,
+                     long long ldc, const float* bias, const void* saved, long long ld_saved, int N, int kind,
+                     int mode, int act, float alpha, int split_k, int sh_H, int sh_W, int sh_C, int sh_s,
+                     void* stream) {
+  return conv_gemm_impl(x, B, H, W, C, R, S, stride_h, stride_w, pad_h, pad_w, OH, OW, Wt_or_dz, ldb, out, ldc, bias,
+                        saved, ld_saved, N, kind, mode, act, alpha, split_k, sh_H, sh_W, sh_C, sh_s, S(stream));
+}
+int b200rl_dgrad_weights(const float* w, void* out, int R, int S_, int Cin, int Cout, int s, long long ld,
+                         void* stream) {
+  return dgrad_weights_impl(w, out, R, S_, Cin, Cout, s, ld, S(stream));
 }
 
 int b200rl_im2col(const void* x, int src_is_u8, const long long* src_idx, void* cols, long long B, int H, int W,

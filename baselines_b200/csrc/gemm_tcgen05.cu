@@ -1,17 +1,23 @@
-// Persistent warp-specialised tcgen05 GEMM for sm_100a (fp16 operands, fp32 accumulate in TMEM).
+// Persistent warp-specialised tcgen05 GEMM / implicit-GEMM convolution for sm_100a
+// (fp16 operands, fp32 accumulate in TMEM).
 //
-//   warp 0      : TMA producer   (cp.async.bulk.tensor.2d -> 128B-swizzled smem ring, mbarrier tx-count)
+//   warp 0      : TMA producer   (tiled or IM2COL-mode cp.async.bulk.tensor -> swizzled smem ring, mbarrier tx)
 //   warp 1      : MMA issuer     (one lane issues tcgen05.mma.cta_group::1.kind::f16, commits to mbarriers)
-//   warp 2      : TMEM allocator (2 accumulator stages so the epilogue of tile i overlaps the MMAs of i+1)
-//   warps 4..7  : epilogue       (tcgen05.ld 32x32b -> registers -> fused bias / activation / mask / atomics)
+//   warp 2      : TMEM allocator (2 accumulator stages: the epilogue of tile i overlaps the MMAs of tile i+1)
+//   warps 4..7  : epilogue       (tcgen05.ld 32x32b -> registers -> fused bias / activation / mask / atomics /
+//                                 pixel-shuffle scatter)
 //
-// Two operand layouts:
-//   K-major  : A[M,K] row-major, B[N,K] row-major            C = A * B^T          (forward, dgrad)
-//   MN-major : A[K,M] row-major, B[K,N] row-major            C = A^T * B          (wgrad; K = batch rows)
-// plus split-K over the reduction dimension with an fp32 atomic epilogue (wgrad).
+// The reduction dimension is processed in stages of 64 elements made of 64/CPT "taps" of CPT elements
+// (CPT = 64, 32 or 16 -> 128 B / 64 B / 32 B swizzled smem rows):
+//   plain GEMM      : a tap is a 64-wide K chunk                                 (CPT = 64)
+//   implicit conv   : a tap is one filter position (r, s) x CPT input channels, fetched straight from the NHWC
+//                     activation by TMA im2col mode -- the im2col matrix is never materialised
+// Operand layouts:
+//   K-major  : A[M,K] rows = output pixels, B[N,K] = weights          C = A * B^T     (forward, dgrad)
+//   MN-major : A[K,M], B[K,N] with K = batch pixels                    C = A^T * B     (wgrad, split-K atomics)
 //
-// This replaces the TF1 ops tf.matmul (a2c/utils.py:63) and -- after lowering by conv_lowering.cu --
-// tf.nn.conv2d (a2c/utils.py:56) and their gradients (ppo2/model.py:102) of the reference.
+// Replaces tf.matmul (a2c/utils.py:63), tf.nn.conv2d (a2c/utils.py:56) and their gradients
+// (tf.gradients via ppo2/model.py:102) of the reference.
 #include <stdarg.h>
 #include <stdio.h>
 
@@ -22,12 +28,23 @@
 namespace b200rl {
 
 static constexpr int BM = 128;
-static constexpr int BK = 64;          // 64 fp16 = 128 bytes = one swizzle row
+static constexpr int BK = 64;          // elements of the reduction dimension per pipeline stage
 static constexpr int UMMA_K = 16;
 static constexpr int NUM_THREADS = 256;
 
-enum : int { MODE_F16_ACT = 0, MODE_F32_STORE = 1, MODE_F32_ATOMIC = 2, MODE_F16_DACT = 3 };
+enum : int { MODE_F16_ACT = 0, MODE_F32_STORE = 1, MODE_F32_ATOMIC = 2, MODE_F16_DACT = 3, MODE_F16_SHUFFLE = 4 };
 enum : int { ACT_NONE = 0, ACT_RELU = 1, ACT_TANH = 2 };
+
+struct ConvCoords {       // im2col traversal of the A operand (all zero for plain GEMMs)
+  int OW, OH;             // grid of base pixels per image (GEMM rows = n*OH*OW + p*OW + q)
+  int stride_w, stride_h; // traversal strides (input pixels per base-pixel step)
+  int lower_w, lower_h;   // coordinate of base pixel 0 (= -padding)
+  int S, taps;            // filter width (taps per filter row) and total number of taps R*S
+};
+
+struct ShuffleOut {       // MODE_F16_SHUFFLE: GEMM row (n,i,j), col (py,px,c) -> dx[n, s*i+py, s*j+px, c]
+  int H, W, C, s;
+};
 
 struct GemmParams {
   int M, N, K;
@@ -35,10 +52,12 @@ struct GemmParams {
   void* C;
   long long ldc;
   const float* bias;
-  const __half* saved;     // saved activation for MODE_F16_DACT
+  const __half* saved;     // saved activation for MODE_F16_DACT / SHUFFLE masks
   long long ld_saved;
   float alpha;
   int mode, act;
+  ConvCoords cv;
+  ShuffleOut sh;
 };
 
 template <int BN>
@@ -52,14 +71,24 @@ struct Cfg {
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
 };
 
-__device__ __forceinline__ uint64_t make_sdesc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+// smem matrix descriptor; layout: 2 = SWIZZLE_128B, 4 = SWIZZLE_64B, 6 = SWIZZLE_32B
+__device__ __forceinline__ uint64_t make_sdesc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes, uint32_t layout) {
   uint64_t d = 0;
   d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);
   d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16;
   d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32;
   d |= 1ull << 46;  // descriptor version (Blackwell)
-  d |= 2ull << 61;  // SWIZZLE_128B
+  d |= (uint64_t)layout << 61;
   return d;
+}
+
+__device__ __forceinline__ void tma_load_im2col_4d(void* smem_dst, const CUtensorMap* tmap, uint64_t* bar, int c, int w,
+                                                   int h, int n, uint16_t off_w, uint16_t off_h) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.im2col.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%3, %4, %5, %6}], [%2], {%7, %8};"
+      ::"r"(smem_u32(smem_dst)), "l"(tmap), "r"(smem_u32(bar)), "r"(c), "r"(w), "r"(h), "r"(n), "h"(off_w), "h"(off_h)
+      : "memory");
 }
 
 __device__ __forceinline__ float apply_act(float x, int act) {
@@ -73,12 +102,61 @@ __device__ __forceinline__ float act_grad_from_saved(float h, int act) {
   return 1.0f;
 }
 
-template <int BN, bool MN_MAJOR>
+// v[16] *= act'(saved[0..16)) with 16-byte loads when aligned
+__device__ __forceinline__ void mask16(float (&v)[16], const __half* sv, bool vec, int nvalid, int act) {
+  if (vec) {
+    uint4 q0 = *reinterpret_cast<const uint4*>(sv);
+    uint4 q1 = *reinterpret_cast<const uint4*>(sv + 8);
+    const __half2* h0 = reinterpret_cast<const __half2*>(&q0);
+    const __half2* h1 = reinterpret_cast<const __half2*>(&q1);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      float2 f = __half22float2(h0[i]);
+      v[2 * i] *= act_grad_from_saved(f.x, act);
+      v[2 * i + 1] *= act_grad_from_saved(f.y, act);
+      float2 g = __half22float2(h1[i]);
+      v[8 + 2 * i] *= act_grad_from_saved(g.x, act);
+      v[8 + 2 * i + 1] *= act_grad_from_saved(g.y, act);
+    }
+  } else {
+#pragma unroll
+    for (int i = 0; i < 16; ++i)
+      if (i < nvalid) v[i] *= act_grad_from_saved(__half2float(sv[i]), act);
+  }
+}
+__device__ __forceinline__ void store16_f16(const float (&v)[16], __half* out, bool vec, int nvalid) {
+  if (vec) {
+    uint4 q0, q1;
+    __half2* h0 = reinterpret_cast<__half2*>(&q0);
+    __half2* h1 = reinterpret_cast<__half2*>(&q1);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      h0[i] = __floats2half2_rn(v[2 * i], v[2 * i + 1]);
+      h1[i] = __floats2half2_rn(v[8 + 2 * i], v[8 + 2 * i + 1]);
+    }
+    *reinterpret_cast<uint4*>(out) = q0;
+    *reinterpret_cast<uint4*>(out + 8) = q1;
+  } else {
+#pragma unroll
+    for (int i = 0; i < 16; ++i)
+      if (i < nvalid) out[i] = __float2half_rn(v[i]);
+  }
+}
+
+// CPT: channels per tap (64 / 32 / 16); MN_MAJOR: wgrad layout; IM2COL: A operand through TMA im2col mode
+template <int BN, int CPT, bool MN_MAJOR, bool IM2COL>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                     const GemmParams p) {
   using C_ = Cfg<BN>;
   constexpr int STAGES = C_::STAGES;
+  constexpr int TPS = BK / CPT;                     // taps per stage
+  constexpr int ROWB = CPT * 2;                     // bytes per smem row of a K-major / A-MN sub-tile
+  constexpr uint32_t LAYOUT_A = (ROWB == 128) ? 2u : (ROWB == 64) ? 4u : 6u;
+  constexpr int A_SUB = BM * ROWB;                  // K-major: one tap of 128 rows
+  constexpr int B_SUB = BN * ROWB;                  // K-major: one tap of BN weight rows
+  constexpr int A_CHUNK = BK * ROWB;                // MN-major: 64 pixel rows x CPT channels (one tap)
+  constexpr int MCH = BM / CPT;                     // MN-major: taps (M chunks) per M tile
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * C_::STAGE_BYTES);
@@ -125,18 +203,56 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         const int split = t2 / p.m_tiles;
         const int kb0 = split * p.kb_per_split;
         const int kb1 = min(kb0 + p.kb_per_split, p.kb_total);
+        int cw = 0, ch = 0, cn = 0;
+        if (IM2COL && !MN_MAJOR) {                 // base pixel of this 128-row tile
+          const int m0 = m_tile * BM;
+          const int q = m0 % p.cv.OW, t3 = m0 / p.cv.OW;
+          cw = q * p.cv.stride_w + p.cv.lower_w;
+          ch = (t3 % p.cv.OH) * p.cv.stride_h + p.cv.lower_h;
+          cn = t3 / p.cv.OH;
+        }
         for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(&empty_bar[s], ph ^ 1);
           uint8_t* sa = smem + s * C_::STAGE_BYTES;
           uint8_t* sb = sa + C_::A_BYTES;
-          mbar_arrive_expect_tx(&full_bar[s], C_::STAGE_BYTES);
           if (!MN_MAJOR) {
-            tma_load_2d(sa, &tmA, &full_bar[s], kb * BK, m_tile * BM);
-            tma_load_2d(sb, &tmB, &full_bar[s], kb * BK, n_tile * BN);
-          } else {
+            const int ntap = IM2COL ? min(TPS, p.cv.taps - kb * TPS) : TPS;
+            mbar_arrive_expect_tx(&full_bar[s], (uint32_t)ntap * (A_SUB + B_SUB));
 #pragma unroll
-            for (int j = 0; j < BM / 64; ++j)
-              tma_load_2d(sa + j * (64 * BK * 2), &tmA, &full_bar[s], m_tile * BM + j * 64, kb * BK);
+            for (int t = 0; t < TPS; ++t) {
+              if (t < ntap) {
+                const int g = kb * TPS + t;
+                if (IM2COL)
+                  tma_load_im2col_4d(sa + t * A_SUB, &tmA, &full_bar[s], 0, cw, ch, cn, (uint16_t)(g % p.cv.S),
+                                     (uint16_t)(g / p.cv.S));
+                else
+                  tma_load_2d(sa + t * A_SUB, &tmA, &full_bar[s], g * CPT, m_tile * BM);
+                tma_load_2d(sb + t * B_SUB, &tmB, &full_bar[s], g * CPT, n_tile * BN);
+              }
+            }
+          } else {
+            int nch = MCH;
+            if (IM2COL) {
+              nch = min(MCH, p.cv.taps - m_tile * MCH);
+              const int k0 = kb * BK;              // first pixel row of this K block
+              const int q = k0 % p.cv.OW, t3 = k0 / p.cv.OW;
+              cw = q * p.cv.stride_w + p.cv.lower_w;
+              ch = (t3 % p.cv.OH) * p.cv.stride_h + p.cv.lower_h;
+              cn = t3 / p.cv.OH;
+            }
+            mbar_arrive_expect_tx(&full_bar[s], (uint32_t)nch * A_CHUNK + C_::B_BYTES);
+#pragma unroll
+            for (int j = 0; j < MCH; ++j) {
+              if (j < nch) {
+                if (IM2COL) {
+                  const int g = m_tile * MCH + j;
+                  tma_load_im2col_4d(sa + j * A_CHUNK, &tmA, &full_bar[s], 0, cw, ch, cn, (uint16_t)(g % p.cv.S),
+                                     (uint16_t)(g / p.cv.S));
+                } else {
+                  tma_load_2d(sa + j * A_CHUNK, &tmA, &full_bar[s], m_tile * BM + j * CPT, kb * BK);
+                }
+              }
+            }
 #pragma unroll
             for (int j = 0; j < BN / 64; ++j)
               tma_load_2d(sb + j * (64 * BK * 2), &tmB, &full_bar[s], n_tile * BN + j * 64, kb * BK);
@@ -164,22 +280,34 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         mbar_wait(&tempty_bar[as], aph ^ 1);
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + (uint32_t)(as * BN);
+        uint32_t acc = 0;
         for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(&full_bar[s], ph);
           tc_fence_after();
           const uint32_t a_addr = smem_u32(smem + s * C_::STAGE_BYTES);
           const uint32_t b_addr = a_addr + C_::A_BYTES;
+          if (!MN_MAJOR) {
+            const int ntap = IM2COL ? min(TPS, p.cv.taps - kb * TPS) : TPS;
 #pragma unroll
-          for (int k = 0; k < BK / UMMA_K; ++k) {
-            uint64_t adesc, bdesc;
-            if (!MN_MAJOR) {
-              adesc = make_sdesc(a_addr + k * (UMMA_K * 2), 16, 1024);
-              bdesc = make_sdesc(b_addr + k * (UMMA_K * 2), 16, 1024);
-            } else {
-              adesc = make_sdesc(a_addr + k * (UMMA_K * 128), 64 * BK * 2, 1024);
-              bdesc = make_sdesc(b_addr + k * (UMMA_K * 128), 64 * BK * 2, 1024);
+            for (int t = 0; t < TPS; ++t) {
+              if (t < ntap) {
+#pragma unroll
+                for (int k = 0; k < CPT / UMMA_K; ++k) {
+                  const uint64_t adesc = make_sdesc(a_addr + t * A_SUB + k * (UMMA_K * 2), 16, 8 * ROWB, LAYOUT_A);
+                  const uint64_t bdesc = make_sdesc(b_addr + t * B_SUB + k * (UMMA_K * 2), 16, 8 * ROWB, LAYOUT_A);
+                  umma_f16(tmem_d, adesc, bdesc, IDESC, acc);
+                  acc = 1;
+                }
+              }
             }
-            umma_f16(tmem_d, adesc, bdesc, IDESC, (kb > kb0 || k > 0) ? 1u : 0u);
+          } else {
+#pragma unroll
+            for (int k = 0; k < BK / UMMA_K; ++k) {
+              const uint64_t adesc = make_sdesc(a_addr + k * (UMMA_K * ROWB), A_CHUNK, 8 * ROWB, LAYOUT_A);
+              const uint64_t bdesc = make_sdesc(b_addr + k * (UMMA_K * 128), 64 * BK * 2, 1024, 2u);
+              umma_f16(tmem_d, adesc, bdesc, IDESC, acc);
+              acc = 1;
+            }
           }
           umma_commit(&empty_bar[s]);   // smem slot reusable once these MMAs retire
           if (++s == STAGES) { s = 0; ph ^= 1; }
@@ -201,6 +329,13 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       tc_fence_after();
       const int row = m_tile * BM + ew * 32 + lane;
       const bool row_ok = row < p.M;
+      int sh_n = 0, sh_i = 0, sh_j = 0;
+      if (p.mode == MODE_F16_SHUFFLE) {
+        sh_j = row % p.cv.OW;
+        const int t3 = row / p.cv.OW;
+        sh_i = t3 % p.cv.OH;
+        sh_n = t3 / p.cv.OH;
+      }
       const uint32_t taddr0 = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(as * BN);
 #pragma unroll 1
       for (int c = 0; c < BN; c += 16) {
@@ -213,62 +348,38 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 #pragma unroll
           for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]) * p.alpha;
           const bool full = (col0 + 16 <= p.N);
+          const int nvalid = full ? 16 : p.N - col0;
           if (p.mode == MODE_F32_ATOMIC) {
             float* out = reinterpret_cast<float*>(p.C) + (long long)row * p.ldc + col0;
 #pragma unroll
             for (int i = 0; i < 16; ++i)
-              if (full || col0 + i < p.N) atomicAdd(out + i, v[i]);
+              if (i < nvalid) atomicAdd(out + i, v[i]);
           } else if (p.mode == MODE_F32_STORE) {
             float* out = reinterpret_cast<float*>(p.C) + (long long)row * p.ldc + col0;
 #pragma unroll
             for (int i = 0; i < 16; ++i)
-              if (full || col0 + i < p.N) out[i] = v[i] + (p.bias ? p.bias[col0 + i] : 0.0f);
+              if (i < nvalid) out[i] = v[i] + (p.bias ? p.bias[col0 + i] : 0.0f);
+          } else if (p.mode == MODE_F16_SHUFFLE) {
+            // dgrad of a strided conv: column block (py, px, c0..c0+15) of GEMM row (n, i, j)
+            const int cls = col0 / p.sh.C, c0 = col0 % p.sh.C;
+            const int y = p.sh.s * sh_i + cls / p.sh.s, x = p.sh.s * sh_j + cls % p.sh.s;
+            if (y < p.sh.H && x < p.sh.W) {
+              const long long o = (((long long)sh_n * p.sh.H + y) * p.sh.W + x) * p.sh.C + c0;
+              if (p.saved) mask16(v, p.saved + o, true, 16, p.act);
+              store16_f16(v, reinterpret_cast<__half*>(p.C) + o, true, 16);
+            }
           } else {
             if (p.mode == MODE_F16_ACT) {
 #pragma unroll
               for (int i = 0; i < 16; ++i) {
-                float b = (p.bias && (full || col0 + i < p.N)) ? __ldg(p.bias + col0 + i) : 0.0f;
+                float b = (p.bias && i < nvalid) ? __ldg(p.bias + col0 + i) : 0.0f;
                 v[i] = apply_act(v[i] + b, p.act);
               }
             } else {  // MODE_F16_DACT: dX = (dY W^T) * act'(saved activation)
-              const __half* sv = p.saved + (long long)row * p.ld_saved + col0;
-              if (full && ((p.ld_saved & 7) == 0)) {
-                uint4 q0 = *reinterpret_cast<const uint4*>(sv);
-                uint4 q1 = *reinterpret_cast<const uint4*>(sv + 8);
-                const __half2* h0 = reinterpret_cast<const __half2*>(&q0);
-                const __half2* h1 = reinterpret_cast<const __half2*>(&q1);
-#pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                  float2 f = __half22float2(h0[i]);
-                  v[2 * i] *= act_grad_from_saved(f.x, p.act);
-                  v[2 * i + 1] *= act_grad_from_saved(f.y, p.act);
-                  float2 g = __half22float2(h1[i]);
-                  v[8 + 2 * i] *= act_grad_from_saved(g.x, p.act);
-                  v[8 + 2 * i + 1] *= act_grad_from_saved(g.y, p.act);
-                }
-              } else {
-#pragma unroll
-                for (int i = 0; i < 16; ++i)
-                  if (col0 + i < p.N) v[i] *= act_grad_from_saved(__half2float(sv[i]), p.act);
-              }
+              mask16(v, p.saved + (long long)row * p.ld_saved + col0, full && ((p.ld_saved & 7) == 0), nvalid, p.act);
             }
-            __half* out = reinterpret_cast<__half*>(p.C) + (long long)row * p.ldc + col0;
-            if (full && ((p.ldc & 7) == 0)) {
-              uint4 q0, q1;
-              __half2* h0 = reinterpret_cast<__half2*>(&q0);
-              __half2* h1 = reinterpret_cast<__half2*>(&q1);
-#pragma unroll
-              for (int i = 0; i < 4; ++i) {
-                h0[i] = __floats2half2_rn(v[2 * i], v[2 * i + 1]);
-                h1[i] = __floats2half2_rn(v[8 + 2 * i], v[8 + 2 * i + 1]);
-              }
-              *reinterpret_cast<uint4*>(out) = q0;
-              *reinterpret_cast<uint4*>(out + 8) = q1;
-            } else {
-#pragma unroll
-              for (int i = 0; i < 16; ++i)
-                if (col0 + i < p.N) out[i] = __float2half_rn(v[i]);
-            }
+            store16_f16(v, reinterpret_cast<__half*>(p.C) + (long long)row * p.ldc + col0,
+                        full && ((p.ldc & 7) == 0), nvalid);
           }
         }
       }
@@ -290,23 +401,27 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                     const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                     CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+typedef CUresult (*PFN_encodeIm2col)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                     const cuuint64_t*, const int*, const int*, cuuint32_t, cuuint32_t,
+                                     const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                     CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
-static PFN_encodeTiled get_encode_fn() {
-  static PFN_encodeTiled fn = nullptr;
-  static std::once_flag once;
-  std::call_once(once, [] {
-    void* ptr = nullptr;
-    cudaDriverEntryPointQueryResult qres;
-    cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres);
-    if (e == cudaSuccess && qres == cudaDriverEntryPointSuccess) fn = reinterpret_cast<PFN_encodeTiled>(ptr);
-  });
-  return fn;
+static void* driver_fn(const char* name) {
+  void* ptr = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  cudaError_t e = cudaGetDriverEntryPoint(name, &ptr, cudaEnableDefault, &qres);
+  return (e == cudaSuccess && qres == cudaDriverEntryPointSuccess) ? ptr : nullptr;
+}
+
+static CUtensorMapSwizzle swizzle_for(int row_bytes) {
+  return row_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : row_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B
+                                                                          : CU_TENSOR_MAP_SWIZZLE_32B;
 }
 
 // 2-D fp16 tensor [rows, cols] with row pitch ld (elements); box = {box_cols (inner), box_rows}
 static int make_tmap(CUtensorMap* tm, const void* ptr, long long rows, long long cols, long long ld, int box_cols,
                      int box_rows) {
-  PFN_encodeTiled enc = get_encode_fn();
+  static PFN_encodeTiled enc = reinterpret_cast<PFN_encodeTiled>(driver_fn("cuTensorMapEncodeTiled"));
   if (!enc) {
     set_last_error("cuTensorMapEncodeTiled entry point unavailable (no CUDA driver?)");
     return B200RL_ERR_DRIVER;
@@ -316,11 +431,35 @@ static int make_tmap(CUtensorMap* tm, const void* ptr, long long rows, long long
   cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
   cuuint32_t estr[2] = {1, 1};
   CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(ptr), gdim, gstr, box, estr,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_for(box_cols * 2), CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     set_last_error("cuTensorMapEncodeTiled failed (%d): rows=%lld cols=%lld ld=%lld box=%dx%d ptr=%p", (int)r, rows,
                    cols, ld, box_cols, box_rows, ptr);
+    return B200RL_ERR_DRIVER;
+  }
+  return B200RL_OK;
+}
+
+// NHWC fp16 activation [B, H, W, C] read in im2col mode: `pixels` base pixels x C channels per load
+static int make_tmap_im2col(CUtensorMap* tm, const void* ptr, long long B, int H, int W, int C, int lower_w,
+                            int lower_h, int upper_w, int upper_h, int stride_w, int stride_h, int pixels) {
+  static PFN_encodeIm2col enc = reinterpret_cast<PFN_encodeIm2col>(driver_fn("cuTensorMapEncodeIm2col"));
+  if (!enc) {
+    set_last_error("cuTensorMapEncodeIm2col entry point unavailable");
+    return B200RL_ERR_DRIVER;
+  }
+  cuuint64_t gdim[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
+  cuuint64_t gstr[3] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2};
+  int lo[2] = {lower_w, lower_h};
+  int hi[2] = {upper_w, upper_h};
+  cuuint32_t estr[4] = {1, (cuuint32_t)stride_w, (cuuint32_t)stride_h, 1};
+  CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<void*>(ptr), gdim, gstr, lo, hi, (cuuint32_t)C,
+                   (cuuint32_t)pixels, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_for(C * 2),
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_last_error("cuTensorMapEncodeIm2col failed (%d): B=%lld H=%d W=%d C=%d lo=(%d,%d) hi=(%d,%d) st=(%d,%d) px=%d",
+                   (int)r, B, H, W, C, lower_w, lower_h, upper_w, upper_h, stride_w, stride_h, pixels);
     return B200RL_ERR_DRIVER;
   }
   return B200RL_OK;
@@ -337,12 +476,12 @@ static int num_sms() {
   return g_num_sms;
 }
 
-template <int BN, bool MN>
+template <int BN, int CPT, bool MN, bool IM2COL>
 static int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p, int max_ctas,
                   cudaStream_t stream) {
   using C_ = Cfg<BN>;
   static bool attr_set = false;
-  auto kern = gemm_tcgen05_kernel<BN, MN>;
+  auto kern = gemm_tcgen05_kernel<BN, CPT, MN, IM2COL>;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C_::SMEM_BYTES);
     if (e != cudaSuccess) {
@@ -356,6 +495,13 @@ static int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmPara
   if (max_ctas > 0 && grid > max_ctas) grid = max_ctas;
   kern<<<grid, NUM_THREADS, C_::SMEM_BYTES, stream>>>(tmA, tmB, p);
   return check_launch("gemm_tcgen05_kernel");
+}
+
+static void fill_splits(GemmParams& p, int split_k) {
+  int splits = split_k < 1 ? 1 : split_k;
+  if (splits > p.kb_total) splits = p.kb_total;
+  p.kb_per_split = ceil_div(p.kb_total, splits);
+  p.splits = ceil_div(p.kb_total, p.kb_per_split);
 }
 
 // C-ABI body (declared in include/b200rl.h)
@@ -375,16 +521,13 @@ int gemm_f16_impl(const void* A, const void* B, void* C, const float* bias, cons
   if (mn_major) BN = (N > 64) ? 128 : 64;
   else BN = (N > 128 && (N % 256 == 0)) ? 256 : (N > 64) ? 128 : (N > 32) ? 64 : 32;
 
-  GemmParams p;
+  GemmParams p = {};
   p.M = M; p.N = N; p.K = K;
   p.m_tiles = ceil_div(M, BM);
   p.n_tiles = ceil_div(N, BN);
   p.kb_total = ceil_div(K, BK);
-  int splits = split_k < 1 ? 1 : split_k;
-  if (splits > p.kb_total) splits = p.kb_total;
-  B200RL_REQUIRE(splits == 1 || mode == MODE_F32_ATOMIC, "gemm: split_k needs the fp32 atomic epilogue");
-  p.kb_per_split = ceil_div(p.kb_total, splits);
-  p.splits = ceil_div(p.kb_total, p.kb_per_split);
+  B200RL_REQUIRE(split_k <= 1 || mode == MODE_F32_ATOMIC, "gemm: split_k needs the fp32 atomic epilogue");
+  fill_splits(p, split_k);
   p.C = C; p.ldc = ldc; p.bias = bias; p.saved = reinterpret_cast<const __half*>(saved); p.ld_saved = ld_saved;
   p.alpha = alpha; p.mode = mode; p.act = act;
 
@@ -398,15 +541,87 @@ int gemm_f16_impl(const void* A, const void* B, void* C, const float* bias, cons
     if ((rc = make_tmap(&tmB, B, K, N, ldb, 64, BK)) != 0) return rc;
   }
   if (mn_major) {
-    if (BN == 64) return launch<64, true>(tmA, tmB, p, max_ctas, stream);
-    return launch<128, true>(tmA, tmB, p, max_ctas, stream);
+    if (BN == 64) return launch<64, 64, true, false>(tmA, tmB, p, max_ctas, stream);
+    return launch<128, 64, true, false>(tmA, tmB, p, max_ctas, stream);
   }
   switch (BN) {
-    case 32: return launch<32, false>(tmA, tmB, p, max_ctas, stream);
-    case 64: return launch<64, false>(tmA, tmB, p, max_ctas, stream);
-    case 128: return launch<128, false>(tmA, tmB, p, max_ctas, stream);
-    default: return launch<256, false>(tmA, tmB, p, max_ctas, stream);
+    case 32: return launch<32, 64, false, false>(tmA, tmB, p, max_ctas, stream);
+    case 64: return launch<64, 64, false, false>(tmA, tmB, p, max_ctas, stream);
+    case 128: return launch<128, 64, false, false>(tmA, tmB, p, max_ctas, stream);
+    default: return launch<256, 64, false, false>(tmA, tmB, p, max_ctas, stream);
   }
+}
+
+template <int CPT, bool MN>
+static int launch_conv(int BN, const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p, cudaStream_t st) {
+  switch (BN) {
+    case 32: if (!MN) return launch<32, CPT, false, true>(tmA, tmB, p, 0, st); break;
+    case 64: return launch<64, CPT, MN, true>(tmA, tmB, p, 0, st);
+    case 128: return launch<128, CPT, MN, true>(tmA, tmB, p, 0, st);
+    default: break;
+  }
+  set_last_error("conv_gemm: unsupported tile N=%d", BN);
+  return B200RL_ERR_UNSUPPORTED;
+}
+
+// Implicit-GEMM convolution on an NHWC fp16 tensor x[B, H, W, C] whose filter window is described by
+// (R x S taps, stride, lower padding).  kind: 0 = forward / dgrad-style (rows = base pixels, K = taps*C,
+// Wt = [N, taps*C] K-major), 1 = wgrad (out[taps*C, N] += x_patches^T * dz, dz = [B*OH*OW, N]).
+int conv_gemm_impl(const void* x, long long B, int H, int W, int C, int R, int S, int stride_h, int stride_w,
+                   int pad_h, int pad_w, int OH, int OW, const void* Wt_or_dz, long long ldb, void* out, long long ldc,
+                   const float* bias, const void* saved, long long ld_saved, int N, int kind, int mode, int act,
+                   float alpha, int split_k, int sh_H, int sh_W, int sh_C, int sh_s, cudaStream_t stream) {
+  B200RL_REQUIRE(x && Wt_or_dz && out && B > 0, "conv_gemm: null operand");
+  B200RL_REQUIRE(C == 16 || C == 32 || C == 64, "conv_gemm: channels per tap must be 16, 32 or 64 (got %d)", C);
+  B200RL_REQUIRE((reinterpret_cast<uintptr_t>(x) & 15) == 0 && (ldb % 8) == 0, "conv_gemm: alignment");
+  B200RL_REQUIRE(kind == 0 || kind == 1, "conv_gemm: bad kind");
+  const int taps = R * S;
+  const long long rows = B * OH * OW;
+  B200RL_REQUIRE(rows < (1LL << 31), "conv_gemm: too many rows");
+  // bounding box of base pixels: lower = -pad, upper chosen so that exactly OW x OH base pixels exist:
+  //   OW = (W + upper_w - lower_w - 1) / stride_w + 1   (cute::make_im2col_tma_copy_desc convention)
+  const int lower_w = -pad_w, lower_h = -pad_h;
+  const int upper_w = (OW - 1) * stride_w + 1 + lower_w - W;
+  const int upper_h = (OH - 1) * stride_h + 1 + lower_h - H;
+
+  GemmParams p = {};
+  p.C = out; p.ldc = ldc; p.bias = bias; p.saved = reinterpret_cast<const __half*>(saved); p.ld_saved = ld_saved;
+  p.alpha = alpha; p.mode = mode; p.act = act;
+  p.cv.OW = OW; p.cv.OH = OH; p.cv.stride_w = stride_w; p.cv.stride_h = stride_h;
+  p.cv.lower_w = lower_w; p.cv.lower_h = lower_h; p.cv.S = S; p.cv.taps = taps;
+  p.sh.H = sh_H; p.sh.W = sh_W; p.sh.C = sh_C; p.sh.s = sh_s;
+  CUtensorMap tmA, tmB;
+  int rc;
+  if (kind == 0) {
+    B200RL_REQUIRE(mode == MODE_F16_ACT || mode == MODE_F16_DACT || mode == MODE_F16_SHUFFLE, "conv_gemm: bad mode");
+    B200RL_REQUIRE(mode != MODE_F16_SHUFFLE || (sh_C % 16 == 0 && sh_s >= 1 && N == sh_s * sh_s * sh_C),
+                   "conv_gemm: shuffle epilogue needs N == s*s*C and C %% 16 == 0");
+    const int BN = (N > 64) ? 128 : (N > 32) ? 64 : 32;
+    p.M = (int)rows; p.N = N; p.K = taps * C;
+    p.m_tiles = ceil_div(p.M, BM);
+    p.n_tiles = ceil_div(N, BN);
+    p.kb_total = ceil_div(taps, BK / C);
+    fill_splits(p, 1);
+    if ((rc = make_tmap_im2col(&tmA, x, B, H, W, C, lower_w, lower_h, upper_w, upper_h, stride_w, stride_h, BM)) != 0)
+      return rc;
+    if ((rc = make_tmap(&tmB, Wt_or_dz, N, (long long)taps * C, ldb, C, BN)) != 0) return rc;
+    if (C == 64) return launch_conv<64, false>(BN, tmA, tmB, p, stream);
+    if (C == 32) return launch_conv<32, false>(BN, tmA, tmB, p, stream);
+    return launch_conv<16, false>(BN, tmA, tmB, p, stream);
+  }
+  B200RL_REQUIRE(mode == MODE_F32_ATOMIC, "conv_gemm: wgrad needs the fp32 atomic epilogue");
+  const int BN = (N > 64) ? 128 : 64;
+  p.M = taps * C; p.N = N; p.K = (int)rows;
+  p.m_tiles = ceil_div(p.M, BM);
+  p.n_tiles = ceil_div(N, BN);
+  p.kb_total = ceil_div(p.K, BK);
+  fill_splits(p, split_k);
+  if ((rc = make_tmap_im2col(&tmA, x, B, H, W, C, lower_w, lower_h, upper_w, upper_h, stride_w, stride_h, BK)) != 0)
+    return rc;
+  if ((rc = make_tmap(&tmB, Wt_or_dz, rows, N, ldb, 64, BK)) != 0) return rc;
+  if (C == 64) return launch_conv<64, true>(BN, tmA, tmB, p, stream);
+  if (C == 32) return launch_conv<32, true>(BN, tmA, tmB, p, stream);
+  return launch_conv<16, true>(BN, tmA, tmB, p, stream);
 }
 
 }  // namespace b200rl

@@ -131,6 +131,27 @@ cast_f32_f16_kernel(const float* __restrict__ src, __half* __restrict__ dst, lon
   }
 }
 
+// Weight operand of the implicit-GEMM data gradient of a strided convolution ("pixel shuffle" form):
+//   out[(py, px, c), (a', b', co)] = W[s*(An-1-a') + py, s*(An-1-b') + px, c, co]   (0 when outside the filter)
+// with W in HWIO [R, S, Cin, Cout] fp32, An = ceil(R/s); out is fp16 [s*s*Cin, An*An*Cout] (row pitch ld).
+__global__ void __launch_bounds__(256)
+dgrad_weights_kernel(const float* __restrict__ w, __half* __restrict__ out, int R, int S, int Cin, int Cout, int s,
+                     int An, long long ld) {
+  const long long cols = (long long)An * An * Cout;
+  const long long total = (long long)s * s * Cin * cols;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long row = i / cols, col = i % cols;
+    const int c = (int)(row % Cin), cls = (int)(row / Cin);
+    const int py = cls / s, px = cls % s;
+    const int co = (int)(col % Cout), tap = (int)(col / Cout);
+    const int ap = tap / An, bp = tap % An;
+    const int ky = s * (An - 1 - ap) + py, kx = s * (An - 1 - bp) + px;
+    float v = 0.0f;
+    if (ky < R && kx < S) v = w[(((long long)ky * S + kx) * Cin + c) * Cout + co];
+    out[row * ld + col] = __float2half_rn(v);
+  }
+}
+
 static int grid_for(long long n, int threads, int per_sm) {
   long long blocks = (n + threads - 1) / threads;
   const long long cap = 148LL * per_sm;
@@ -169,6 +190,16 @@ int cast_transpose_impl(const float* src, int R, int C, void* dst, long long ld_
   cast_transpose_kernel<<<grid, 256, 0, stream>>>(src, R, C, reinterpret_cast<__half*>(dst), ld_dst,
                                                   reinterpret_cast<__half*>(dstT), ld_t, scale);
   return check_launch("cast_transpose_kernel");
+}
+
+int dgrad_weights_impl(const float* w, void* out, int R, int S, int Cin, int Cout, int s, long long ld,
+                       cudaStream_t stream) {
+  B200RL_REQUIRE(w && out && R > 0 && S > 0 && s > 0, "dgrad_weights: bad args");
+  const int An = (R + s - 1) / s;
+  const long long total = (long long)s * s * Cin * An * An * Cout;
+  dgrad_weights_kernel<<<grid_for(total, 256, 8), 256, 0, stream>>>(w, reinterpret_cast<__half*>(out), R, S, Cin,
+                                                                     Cout, s, An, ld);
+  return check_launch("dgrad_weights_kernel");
 }
 
 int cast_f32_f16_impl(const float* src, void* dst, long long rows, int cols, long long ld_src, long long ld_dst,

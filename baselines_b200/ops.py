@@ -7,7 +7,7 @@ import torch
 
 from . import _lib
 
-MODE_F16_ACT, MODE_F32_STORE, MODE_F32_ATOMIC, MODE_F16_DACT = 0, 1, 2, 3
+MODE_F16_ACT, MODE_F32_STORE, MODE_F32_ATOMIC, MODE_F16_DACT, MODE_F16_SHUFFLE = 0, 1, 2, 3, 4
 ACT_NONE, ACT_RELU, ACT_TANH = 0, 1, 2
 ACT_CODES = {None: ACT_NONE, "none": ACT_NONE, "relu": ACT_RELU, "tanh": ACT_TANH}
 
@@ -55,6 +55,26 @@ def gemm(A, B, C, *, M, N, K, lda, ldb, ldc, bias=None, saved=None, ld_saved=0, 
               flops=2.0 * M * N * K,
               nbytes=2.0 * (M * K + N * K) + M * N * (2 if mode in (MODE_F16_ACT, MODE_F16_DACT) else 4)
               + (2.0 * M * N if mode == MODE_F16_DACT else 0))
+
+
+def conv_gemm(x, B, H, W, C, R, S, stride_h, stride_w, pad_h, pad_w, OH, OW, wt_or_dz, ldb, out, ldc, N, kind,
+              mode, act=ACT_NONE, alpha=1.0, bias=None, saved=None, ld_saved=0, split_k=1, shuffle=None, tag=None):
+    """Implicit-GEMM convolution (TMA im2col A operand).  kind 0: forward / data-gradient form; kind 1: wgrad."""
+    _chk(x, torch.float16, "x")
+    _chk(wt_or_dz, torch.float16, "wt_or_dz")
+    sh = shuffle or (0, 0, 0, 0)
+    rows = B * OH * OW
+    _lib.call("b200rl_conv_gemm", _ptr(x), int(B), H, W, C, R, S, stride_h, stride_w, pad_h, pad_w, OH, OW,
+              _ptr(wt_or_dz), int(ldb), _ptr(out), int(ldc), _ptr(bias), _ptr(saved), int(ld_saved), int(N), int(kind),
+              int(mode), int(act), float(alpha), int(split_k), int(sh[0]), int(sh[1]), int(sh[2]), int(sh[3]),
+              _stream(), label="conv." + (tag or str(kind)), flops=2.0 * rows * N * R * S * C,
+              nbytes=2.0 * B * H * W * C + 2.0 * R * S * C * N + rows * N * (2.0 if kind == 0 else 2.0))
+
+
+def dgrad_weights(w, out, R, S, Cin, Cout, s, ld):
+    _chk(w, torch.float32, "w")
+    _chk(out, torch.float16, "out")
+    _lib.call("b200rl_dgrad_weights", _ptr(w), _ptr(out), R, S, Cin, Cout, s, int(ld), _stream())
 
 
 def _conv_out(H, W, rf, stride, same_pad):

@@ -29,6 +29,8 @@ extern "C" {
 #define B200RL_MODE_F32_STORE 1  /* C32 = alpha*acc + bias                           (heads)              */
 #define B200RL_MODE_F32_ATOMIC 2 /* C32 += alpha*acc (red.add.f32; split-K capable)  (weight gradients)   */
 #define B200RL_MODE_F16_DACT 3   /* C16 = alpha*acc * act'(saved)                    (data gradients)     */
+#define B200RL_MODE_F16_SHUFFLE 4 /* conv data gradient, pixel-shuffle scatter: row (n,i,j), col (py,px,c)
+                                     -> dx[n, s*i+py, s*j+px, c] * act'(saved there)  (b200rl_conv_gemm only) */
 #define B200RL_ACT_NONE 0
 #define B200RL_ACT_RELU 1
 #define B200RL_ACT_TANH 2
@@ -51,6 +53,20 @@ int b200rl_gae_scan(const float* rewards, const float* values, const uint8_t* do
 int b200rl_gemm_f16(const void* A, const void* B, void* C, const float* bias, const void* saved, int M, int N, int K,
                     long long lda, long long ldb, long long ldc, long long ld_saved, int mn_major, int mode, int act,
                     float alpha, int split_k, int max_ctas, void* stream);
+
+/* Implicit-GEMM convolution (tf.nn.conv2d a2c/utils.py:56 and its gradients): the A operand is read
+ * straight from the NHWC fp16 activation x[B,H,W,C] by TMA im2col mode (C = 16, 32 or 64 channels per tap).
+ *   kind 0: out[B*OH*OW, N] = patches(x) * Wt^T, Wt = [N, R*S*C] fp16 (ldb); modes F16_ACT / F16_DACT /
+ *           F16_SHUFFLE (data gradient of a stride-s conv written through the sh_* geometry)
+ *   kind 1: out[R*S*C, N] (fp32, ldc) += alpha * patches(x)^T * dz, dz = [B*OH*OW, N] fp16 (ldb); split_k >= 1 */
+int b200rl_conv_gemm(const void* x, long long B, int H, int W, int C, int R, int S, int stride_h, int stride_w,
+                     int pad_h, int pad_w, int OH, int OW, const void* Wt_or_dz, long long ldb, void* out,
+                     long long ldc, const float* bias, const void* saved, long long ld_saved, int N, int kind,
+                     int mode, int act, float alpha, int split_k, int sh_H, int sh_W, int sh_C, int sh_s,
+                     void* stream);
+/* fp16 weight operand for the pixel-shuffle data gradient: out[s*s*Cin, ceil(R/s)^2*Cout] from HWIO fp32 w */
+int b200rl_dgrad_weights(const float* w, void* out, int R, int S, int Cin, int Cout, int s, long long ld,
+                         void* stream);
 
 /* conv lowering (tf.nn.conv2d NHWC, a2c/utils.py:37-56; SAME padding for tf.contrib convolution2d,
  * common/models.py:241).  src_is_u8 fuses tf.cast(uint8->float) of models.py:19 and, through src_idx,

@@ -506,3 +506,83 @@ def test_dqn_td_vs_oracle(ops):
         assert np.allclose(dA.float().cpu().numpy()[:, :nA], At.grad.numpy(), atol=2e-3, rtol=2e-3)
         if dueling:
             assert np.allclose(dA.float().cpu().numpy()[:, nA], St.grad.numpy(), atol=2e-3, rtol=2e-3)
+
+
+# ------------------------------------------------------------------------------------------ implicit-GEMM conv
+def _patches(x, R, S, sh, sw, ph, pw, OH, OW):
+    """x [B,H,W,C] float -> [B*OH*OW, R*S*C] with K ordered (r, s, c); zero padding (ph, pw) on the low side and
+    whatever is needed on the high side."""
+    import torch.nn.functional as F
+    B, H, W, C = x.shape
+    hi_h = max((OH - 1) * sh + R - ph - H, 0)
+    hi_w = max((OW - 1) * sw + S - pw - W, 0)
+    xp = F.pad(x.permute(0, 3, 1, 2), (pw, hi_w, ph, hi_h))
+    un = F.unfold(xp, (R, S), stride=(sh, sw))                        # [B, C*R*S, L]
+    L = un.shape[-1]
+    oh_full = (xp.shape[2] - R) // sh + 1
+    ow_full = (xp.shape[3] - S) // sw + 1
+    un = un.view(B, C, R, S, oh_full, ow_full)[:, :, :, :, :OH, :OW]
+    return un.permute(0, 4, 5, 2, 3, 1).reshape(B * OH * OW, R * S * C)
+
+
+CONV_CASES = [
+    # name, B, H, W, C, R, S, sh, sw, N
+    ("c1_superpixel", 5, 84, 21, 16, 8, 2, 4, 1, 32),
+    ("c2", 7, 20, 20, 32, 4, 4, 2, 2, 64),
+    ("c3", 11, 9, 9, 64, 3, 3, 1, 1, 64),
+]
+
+
+@pytest.mark.parametrize("name,B,H,W,C,R,S,sh,sw,N", CONV_CASES)
+def test_conv_gemm_forward_and_wgrad(ops, name, B, H, W, C, R, S, sh, sw, N):
+    torch.manual_seed(hash(name) % 1000)
+    OH, OW = (H - R) // sh + 1, (W - S) // sw + 1
+    x = (torch.randn(B, H, W, C, device="cuda") * 0.5).half()
+    K = R * S * C
+    wt = (torch.randn(N, K, device="cuda") * 0.2).half()
+    bias = torch.randn(N, device="cuda")
+    rows = B * OH * OW
+    P = _patches(x.float(), R, S, sh, sw, 0, 0, OH, OW)
+    out = torch.zeros(rows, N, dtype=torch.float16, device="cuda")
+    ops.conv_gemm(x, B, H, W, C, R, S, sh, sw, 0, 0, OH, OW, wt, K, out, N, N, 0, ops.MODE_F16_ACT, act=ops.ACT_RELU,
+                  bias=bias)
+    torch.cuda.synchronize()
+    want = torch.relu(P @ wt.float().t() + bias)
+    err = float((out.float() - want).abs().max())
+    assert torch.allclose(out.float(), want, atol=2e-2, rtol=5e-3), (name, err)
+    # wgrad: gw[K, N] += alpha * patches^T dz
+    dz = (torch.randn(rows, N, device="cuda") * 0.5).half()
+    gw = torch.ones(K, N, dtype=torch.float32, device="cuda")
+    ops.conv_gemm(x, B, H, W, C, R, S, sh, sw, 0, 0, OH, OW, dz, N, gw, N, N, 1, ops.MODE_F32_ATOMIC, alpha=0.5,
+                  split_k=3)
+    torch.cuda.synchronize()
+    want = 1.0 + 0.5 * (P.t() @ dz.float())
+    err = float((gw - want).abs().max())
+    assert torch.allclose(gw, want, atol=2e-3 * rows ** 0.5, rtol=2e-3), (name, err)
+
+
+@pytest.mark.parametrize("B,Hin,Cin,Cout,rf,s", [(7, 20, 32, 64, 4, 2), (11, 9, 64, 64, 3, 1), (3, 84, 16, 32, 8, 4)])
+def test_conv_gemm_dgrad_pixel_shuffle(ops, B, Hin, Cin, Cout, rf, s):
+    """dx = conv_transpose(dz, W) * relu'(h_in), computed as ONE implicit GEMM over dz with the rearranged
+    weights and the pixel-shuffle epilogue; reference = autograd of F.conv2d."""
+    import torch.nn.functional as F
+    torch.manual_seed(Hin + Cin)
+    OHc = (Hin - rf) // s + 1                                 # conv output size
+    w = (torch.randn(rf, rf, Cin, Cout, device="cuda") * 0.2)
+    h_in = torch.randn(B, Hin, Hin, Cin, device="cuda").half()   # saved activation of the layer below
+    dz = (torch.randn(B, OHc, OHc, Cout, device="cuda") * 0.5).half()
+    An = -(-rf // s)
+    ldw = An * An * Cout
+    wdg = torch.zeros(s * s * Cin, ldw, dtype=torch.float16, device="cuda")
+    ops.dgrad_weights(w.contiguous(), wdg, rf, rf, Cin, Cout, s, ldw)
+    G = -(-Hin // s)                                          # base-pixel grid of the GEMM rows
+    dx = torch.zeros(B, Hin, Hin, Cin, dtype=torch.float16, device="cuda")
+    ops.conv_gemm(dz, B, OHc, OHc, Cout, An, An, 1, 1, An - 1, An - 1, G, G, wdg, ldw, dx, 0, s * s * Cin, 0,
+                  ops.MODE_F16_SHUFFLE, act=ops.ACT_RELU, saved=h_in, shuffle=(Hin, Hin, Cin, s))
+    torch.cuda.synchronize()
+    xin = torch.zeros(B, Cin, Hin, Hin, device="cuda", requires_grad=True)
+    y = F.conv2d(xin, w.half().float().permute(3, 2, 0, 1), stride=s)
+    y.backward(dz.float().permute(0, 3, 1, 2))
+    want = xin.grad.permute(0, 2, 3, 1) * (h_in.float() > 0)
+    err = float((dx.float() - want).abs().max())
+    assert torch.allclose(dx.float(), want, atol=3e-2, rtol=5e-3), err
