@@ -200,6 +200,65 @@ class Conv(Linear):
     def col2im(self, dcols, saved, dx, B, act):
         ops.col2im(dcols, saved, dx, B, self.H, self.W, self.C, self.rf, self.stride, self.same, act=act, tag=self.name)
 
+    # ---- implicit-GEMM path (TMA im2col): no cols / dcols buffers ----------------------------------------
+    def plan_implicit(self):
+        """Geometry as seen by TMA.  Channels per tap must be 16/32/64; a first layer with few channels is
+        viewed through "super-pixels" of 16 consecutive (x, c) elements when the stride allows it."""
+        C, W, rf, st = self.C, self.W, self.rf, self.stride
+        pad_t = pad_l = 0
+        if self.same:
+            ph = max((self.OH - 1) * st + rf - self.H, 0)
+            pw = max((self.OW - 1) * st + rf - W, 0)
+            pad_t, pad_l = ph // 2, pw // 2
+        if C in (16, 32, 64):
+            g = (self.H, W, C, rf, rf, st, st, pad_t, pad_l)
+        elif 16 % C == 0 and (W * C) % 16 == 0 and (rf * C) % 16 == 0 and (st * C) % 16 == 0 and (pad_l * C) % 16 == 0:
+            k = 16 // C
+            g = (self.H, W // k, 16, rf, rf // k, st, st // k, pad_t, pad_l // k)
+        else:
+            return None
+        self.geom = g
+        return g
+
+    def materialize(self):
+        super().materialize()
+        self.implicit = self.plan_implicit() is not None
+        self.wdg = None
+
+    def enable_dgrad(self):
+        An = -(-self.rf // self.stride)
+        self.An, self.ld_wdg = An, An * An * self.nf
+        self.wdg = torch.zeros(self.stride * self.stride * self.C, self.ld_wdg, dtype=torch.float16,
+                               device=self.store.device)
+
+    def refresh(self):
+        super().refresh()
+        if self.wdg is not None:
+            ops.dgrad_weights(self.w, self.wdg, self.rf, self.rf, self.C, self.nf, self.stride, self.ld_wdg)
+
+    def fwd_implicit(self, x, B, out):
+        H, W, C, R, S, sh, sw, pt, pl = self.geom
+        ops.conv_gemm(x, B, H, W, C, R, S, sh, sw, pt, pl, self.OH, self.OW, self.w_fwd, self.Kp, out, self.nf,
+                      self.nf, 0, ops.MODE_F16_ACT, act=self.act, bias=self.b, tag="fwd." + self.name)
+
+    def wgrad_implicit(self, x, dz, B, alpha):
+        H, W, C, R, S, sh, sw, pt, pl = self.geom
+        tiles = -(-self.K // 128)
+        rows = B * self.P
+        split = max(1, min((rows // 64) // 2 if rows >= 128 else 1, -(-296 // tiles)))
+        ops.conv_gemm(x, B, H, W, C, R, S, sh, sw, pt, pl, self.OH, self.OW, dz, self.nf, self.gw, self.nf, self.nf, 1,
+                      ops.MODE_F32_ATOMIC, alpha=alpha * self.in_scale, split_k=split, tag="wgrad." + self.name)
+        ops.colsum(dz, self.gb, rows, self.nf, self.nf, alpha=alpha)
+
+    def dgrad_implicit(self, dz, B, saved_in, dx, act):
+        """dx[B,H,W,C] = conv_transpose(dz) * act'(saved_in): one implicit GEMM over dz with the pixel-shuffle
+        epilogue.  (VALID padding only.)"""
+        s, An = self.stride, self.An
+        G_h, G_w = -(-self.H // s), -(-self.W // s)
+        ops.conv_gemm(dz, B, self.OH, self.OW, self.nf, An, An, 1, 1, An - 1, An - 1, G_h, G_w, self.wdg, self.ld_wdg,
+                      dx, 0, s * s * self.C, 0, ops.MODE_F16_SHUFFLE, act=act, saved=saved_in,
+                      shuffle=(self.H, self.W, self.C, s), tag="dgrad." + self.name)
+
 
 class Tower:
     """A latent network (conv stack + fc, or mlp) with its activation workspace for `cap` samples."""
@@ -253,10 +312,22 @@ class Tower:
         f16 = dict(dtype=torch.float16, device=dev)
         for l in self.layers:
             l.materialize()
-        self.cols = [torch.empty(cap * c.P, c.K, **f16) for c in self.convs]
+        import os
+        allow = os.environ.get("B200RL_EXPLICIT_CONV", "0") != "1"
+        # implicit dgrad needs VALID padding, the dz tensor's channels in {16,32,64} and a zero-initialised dx
+        for i, c in enumerate(self.convs):
+            c.implicit = c.implicit and allow
+            c.implicit_dgrad = (i > 0 and c.implicit and not c.same and c.nf in (16, 32, 64) and c.C % 16 == 0)
+            if c.implicit_dgrad:
+                c.enable_dgrad()
+        self.cols = [None if c.implicit else torch.empty(cap * c.P, c.K, **f16) for c in self.convs]
         self.hconv = [torch.empty(cap * c.P, c.nf, **f16) for c in self.convs]
-        self.dcols = [None] + [torch.empty(cap * c.P, c.K, **f16) for c in self.convs[1:]]
-        self.dzconv = [torch.empty(cap * c.P, c.nf, **f16) for c in self.convs]
+        self.dcols = [None] + [None if c.implicit_dgrad else torch.empty(cap * c.P, c.K, **f16)
+                               for c in self.convs[1:]]
+        self.dzconv = [torch.zeros(cap * c.P, c.nf, **f16) for c in self.convs]
+        if self.convs and self.convs[0].implicit and self.in_u8:
+            c0 = self.convs[0]
+            self.x16 = torch.empty(cap, c0.H * c0.W * c0.C, **f16)     # gathered uint8 -> fp16 observations
         self.hfc = [torch.empty(cap, l.Np, **f16) for l in self.fcs]
         self.dzfc = [torch.empty(cap, l.Np, **f16) for l in self.fcs]
         if self.kind == "mlp":
@@ -277,9 +348,20 @@ class Tower:
         if self.convs:
             cur = x
             for i, c in enumerate(self.convs):
-                c.im2col(cur, self.cols[i], B, src_idx=src_idx if i == 0 else None)
-                c.forward(self.cols[i], c.K, B * c.P, self.hconv[i], c.nf)
+                if c.implicit:
+                    if i == 0 and self.in_u8:
+                        # fused minibatch gather + uint8->fp16 cast (models.py:19, ppo2.py:165): 84 B/elem of traffic
+                        n_el = c.H * c.W * c.C
+                        ops.im2col(cur, self.x16, B, 1, 1, n_el, 1, 1, False, src_idx=src_idx, tag="gather_cast")
+                        cur = self.x16
+                    elif i == 0 and src_idx is not None:
+                        raise NotImplementedError("gather of fp16 image inputs")
+                    c.fwd_implicit(cur, B, self.hconv[i])
+                else:
+                    c.im2col(cur, self.cols[i], B, src_idx=src_idx if i == 0 else None)
+                    c.forward(self.cols[i], c.K, B * c.P, self.hconv[i], c.nf)
                 cur = self.hconv[i]
+            self._conv_in0 = self.x16 if (self.convs[0].implicit and self.in_u8) else x
             h, ldh = cur, self.flat                      # [B, OH*OW*C] view of the NHWC activation (H,W,C order)
         else:
             if src_idx is not None:                      # row gather == 1x1 im2col
@@ -318,11 +400,19 @@ class Tower:
         for i in reversed(range(len(self.convs))):
             c = self.convs[i]
             dzc = self.dzconv[i]
-            c.wgrad(self.cols[i], c.K, dzc, c.nf, B * c.P, alpha)
+            if c.implicit:
+                c.wgrad_implicit(self._conv_in0 if i == 0 else self.hconv[i - 1], dzc, B, alpha)
+            else:
+                c.wgrad(self.cols[i], c.K, dzc, c.nf, B * c.P, alpha)
             if i == 0:
                 break
-            c.dgrad(dzc, c.nf, B * c.P, self.dcols[i], c.K)
-            c.col2im(self.dcols[i], self.hconv[i - 1], self.dzconv[i - 1], B, act=ops.ACT_RELU)
+            if c.implicit_dgrad:
+                c.dgrad_implicit(dzc, B, self.hconv[i - 1], self.dzconv[i - 1], ops.ACT_RELU)
+            else:
+                if self.dcols[i] is None:
+                    raise RuntimeError("explicit dgrad workspace missing")
+                c.dgrad(dzc, c.nf, B * c.P, self.dcols[i], c.K)
+                c.col2im(self.dcols[i], self.hconv[i - 1], self.dzconv[i - 1], B, act=ops.ACT_RELU)
 
 
 class Optimizer:
