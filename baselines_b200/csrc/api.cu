@@ -25,6 +25,7 @@ int dgrad_weights_impl(const float*, void*, int, int, int, int, int, long long, 
 int gae_scan_impl(const float*, const float*, const uint8_t*, const float*, const uint8_t*, float*, float*, int, int,
                   double, double, int, cudaStream_t);
 int im2col_impl(const void*, int, const long long*, void*, long long, int, int, int, int, int, int, cudaStream_t);
+int s2d_gather_impl(const void*, const long long*, void*, long long, int, int, int, int, cudaStream_t);
 int col2im_impl(const void*, const void*, void*, long long, int, int, int, int, int, int, int, cudaStream_t);
 int colsum_impl(const void*, float*, long long, int, long long, float, cudaStream_t);
 int cat_step_impl(const float*, long long, int, const float*, long long, const float*, unsigned long long,
@@ -96,6 +97,10 @@ int b200rl_dgrad_weights(const float* w, void* out, int R, int S_, int Cin, int 
 int b200rl_im2col(const void* x, int src_is_u8, const long long* src_idx, void* cols, long long B, int H, int W,
                   int C, int rf, int stride, int same_pad, void* stream) {
   return im2col_impl(x, src_is_u8, src_idx, cols, B, H, W, C, rf, stride, same_pad, S(stream));
+}
+int b200rl_s2d_gather(const void* x, const long long* src_idx, void* out, long long B, int H, int W, int C, int s,
+                      void* stream) {
+  return s2d_gather_impl(x, src_idx, out, B, H, W, C, s, S(stream));
 }
 int b200rl_col2im(const void* dcols, const void* saved, void* dx, long long B, int H, int W, int C, int rf,
                   int stride, int same_pad, int act, void* stream) {

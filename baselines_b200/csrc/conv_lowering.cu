@@ -127,6 +127,39 @@ col2im_kernel(const __half* __restrict__ dcols, const __half* __restrict__ saved
   }
 }
 
+// Fused minibatch gather + uint8->fp16 cast + space-to-depth for the first conv layer:
+//   out[b, Y, X, (dy*s + dx)*C + c] = x[src_idx[b], s*Y + dy, s*X + dx, c]
+// A stride-s conv with filter rf = k*s over x becomes a stride-1 conv with filter k over `out`, whose
+// s*s*C channels give TMA im2col full 128-byte rows.  One thread = 8 consecutive elements of one (dy) segment.
+__global__ void __launch_bounds__(256)
+s2d_gather_kernel(const uint8_t* __restrict__ x, const long long* __restrict__ src_idx, __half* __restrict__ out,
+                  long long B, int H, int W, int C, int s) {
+  const int seg = s * C;                   // contiguous elements per (Y, X, dy)
+  const int cps = seg / 8;                 // 8-element chunks per segment
+  const int HY = H / s, WX = W / s;
+  const long long total = B * HY * WX * s * cps;
+  for (long long id = (long long)blockIdx.x * blockDim.x + threadIdx.x; id < total;
+       id += (long long)gridDim.x * blockDim.x) {
+    const int j = (int)(id % cps);
+    long long t = id / cps;
+    const int dy = (int)(t % s);
+    t /= s;
+    const int X = (int)(t % WX);
+    t /= WX;
+    const int Y = (int)(t % HY);
+    const long long b = t / HY;
+    const long long sb = src_idx ? src_idx[b] : b;
+    const uint8_t* src = x + ((sb * H + (long long)s * Y + dy) * W + (long long)s * X) * C + j * 8;
+    const uint2 q = *reinterpret_cast<const uint2*>(src);
+    const uint8_t* bp = reinterpret_cast<const uint8_t*>(&q);
+    __half o[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) o[i] = __ushort2half_rn((unsigned short)bp[i]);
+    __half* dst = out + (((b * HY + Y) * WX + X) * (long long)s + dy) * seg + j * 8;
+    *reinterpret_cast<uint4*>(dst) = *reinterpret_cast<const uint4*>(o);
+  }
+}
+
 // db[c] += alpha * sum_rows dz[row, c]
 __global__ void __launch_bounds__(256)
 colsum_kernel(const __half* __restrict__ dz, float* __restrict__ db, long long rows, int C, long long ld, float alpha,
@@ -198,6 +231,18 @@ int im2col_impl(const void* x, int src_is_u8, const long long* src_idx, void* co
     im2col_kernel<__half><<<grid, 256, 0, stream>>>(reinterpret_cast<const __half*>(x), src_idx,
                                                     reinterpret_cast<__half*>(cols), B, g);
   return check_launch("im2col_kernel");
+}
+
+int s2d_gather_impl(const void* x, const long long* src_idx, void* out, long long B, int H, int W, int C, int s,
+                    cudaStream_t stream) {
+  B200RL_REQUIRE(x && out && B > 0 && s > 0, "s2d_gather: bad args");
+  B200RL_REQUIRE(H % s == 0 && W % s == 0 && (s * C) % 8 == 0 && (reinterpret_cast<uintptr_t>(x) & 7) == 0 &&
+                     (W * C) % 8 == 0,
+                 "s2d_gather: need H,W multiples of s and s*C, W*C multiples of 8");
+  const long long total = B * (H / s) * (W / s) * s * ((s * C) / 8);
+  s2d_gather_kernel<<<grid_for(total, 256), 256, 0, stream>>>(reinterpret_cast<const uint8_t*>(x), src_idx,
+                                                             reinterpret_cast<__half*>(out), B, H, W, C, s);
+  return check_launch("s2d_gather_kernel");
 }
 
 int col2im_impl(const void* dcols, const void* saved, void* dx, long long B, int H, int W, int C, int rf, int stride,

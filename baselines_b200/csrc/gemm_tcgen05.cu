@@ -144,12 +144,22 @@ __device__ __forceinline__ void store16_f16(const float (&v)[16], __half* out, b
 }
 
 // CPT: channels per tap (64 / 32 / 16); MN_MAJOR: wgrad layout; IM2COL: A operand through TMA im2col mode
-template <int BN, int CPT, bool MN_MAJOR, bool IM2COL>
+// BRES (K-major implicit conv only): the whole weight matrix (taps x [BN x CPT]) is loaded ONCE per CTA and
+// stays resident in shared memory; the ring then carries only the A (activation patch) tiles.
+static constexpr int BRES_STAGES = 7;
+static constexpr int BRES_B_BYTES = 80 * 1024;
+
+template <int BN, int CPT, bool MN_MAJOR, bool IM2COL, bool BRES>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                     const GemmParams p) {
   using C_ = Cfg<BN>;
-  constexpr int STAGES = C_::STAGES;
+  static_assert(!BRES || (IM2COL && !MN_MAJOR), "resident weights: K-major implicit conv only");
+  constexpr int STAGES = BRES ? BRES_STAGES : C_::STAGES;
+  constexpr int STAGE_BYTES = BRES ? C_::A_BYTES : C_::STAGE_BYTES;
+  constexpr int BROWB = MN_MAJOR ? (BN >= 64 ? 128 : BN * 2) : 0;     // MN-major B: bytes per pixel row
+  constexpr uint32_t LAYOUT_B = (BROWB == 64) ? 4u : 2u;
+  constexpr int BCHUNKS = (BN >= 64) ? BN / 64 : 1;
   constexpr int TPS = BK / CPT;                     // taps per stage
   constexpr int ROWB = CPT * 2;                     // bytes per smem row of a K-major / A-MN sub-tile
   constexpr uint32_t LAYOUT_A = (ROWB == 128) ? 2u : (ROWB == 64) ? 4u : 6u;
@@ -159,12 +169,14 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   constexpr int MCH = BM / CPT;                     // MN-major: taps (M chunks) per M tile
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * C_::STAGE_BYTES);
+  uint8_t* bres = smem + STAGES * STAGE_BYTES;            // resident weights (BRES only)
+  uint64_t* bars = reinterpret_cast<uint64_t*>(bres + (BRES ? BRES_B_BYTES : 0));
   uint64_t* full_bar = bars;                  // [STAGES]
   uint64_t* empty_bar = bars + STAGES;        // [STAGES]
   uint64_t* tfull_bar = bars + 2 * STAGES;    // [2]
   uint64_t* tempty_bar = bars + 2 * STAGES + 2;  // [2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
+  uint64_t* bres_bar = bars + 2 * STAGES + 4;    // [1]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 5);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -183,6 +195,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       mbar_init(&tfull_bar[s], 1);
       mbar_init(&tempty_bar[s], 128);
     }
+    mbar_init(bres_bar, 1);
     fence_barrier_init();
   }
   if (warp == 2) tmem_alloc<C_::TMEM_COLS>(tmem_slot);
@@ -194,6 +207,10 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
     if (lane == 0) {
+      if (BRES) {
+        mbar_arrive_expect_tx(bres_bar, (uint32_t)p.cv.taps * B_SUB);
+        for (int g = 0; g < p.cv.taps; ++g) tma_load_2d(bres + g * B_SUB, &tmB, bres_bar, g * CPT, 0);
+      }
       int s = 0;
       uint32_t ph = 0;
       for (int work = blockIdx.x; work < total_work; work += gridDim.x) {
@@ -213,11 +230,11 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         }
         for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(&empty_bar[s], ph ^ 1);
-          uint8_t* sa = smem + s * C_::STAGE_BYTES;
+          uint8_t* sa = smem + s * STAGE_BYTES;
           uint8_t* sb = sa + C_::A_BYTES;
           if (!MN_MAJOR) {
             const int ntap = IM2COL ? min(TPS, p.cv.taps - kb * TPS) : TPS;
-            mbar_arrive_expect_tx(&full_bar[s], (uint32_t)ntap * (A_SUB + B_SUB));
+            mbar_arrive_expect_tx(&full_bar[s], (uint32_t)ntap * (A_SUB + (BRES ? 0 : B_SUB)));
 #pragma unroll
             for (int t = 0; t < TPS; ++t) {
               if (t < ntap) {
@@ -227,7 +244,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                                      (uint16_t)(g / p.cv.S));
                 else
                   tma_load_2d(sa + t * A_SUB, &tmA, &full_bar[s], g * CPT, m_tile * BM);
-                tma_load_2d(sb + t * B_SUB, &tmB, &full_bar[s], g * CPT, n_tile * BN);
+                if (!BRES) tma_load_2d(sb + t * B_SUB, &tmB, &full_bar[s], g * CPT, n_tile * BN);
               }
             }
           } else {
@@ -254,8 +271,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
               }
             }
 #pragma unroll
-            for (int j = 0; j < BN / 64; ++j)
-              tma_load_2d(sb + j * (64 * BK * 2), &tmB, &full_bar[s], n_tile * BN + j * 64, kb * BK);
+            for (int j = 0; j < BCHUNKS; ++j)
+              tma_load_2d(sb + j * (BK * BROWB), &tmB, &full_bar[s], n_tile * BN + j * 64, kb * BK);
           }
           if (++s == STAGES) { s = 0; ph ^= 1; }
         }
@@ -278,14 +295,15 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         const int kb0 = split * p.kb_per_split;
         const int kb1 = min(kb0 + p.kb_per_split, p.kb_total);
         mbar_wait(&tempty_bar[as], aph ^ 1);
+        if (BRES) mbar_wait(bres_bar, 0);
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + (uint32_t)(as * BN);
         uint32_t acc = 0;
         for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(&full_bar[s], ph);
           tc_fence_after();
-          const uint32_t a_addr = smem_u32(smem + s * C_::STAGE_BYTES);
-          const uint32_t b_addr = a_addr + C_::A_BYTES;
+          const uint32_t a_addr = smem_u32(smem + s * STAGE_BYTES);
+          const uint32_t b_addr = BRES ? smem_u32(bres) + (uint32_t)(kb * TPS) * B_SUB : a_addr + C_::A_BYTES;
           if (!MN_MAJOR) {
             const int ntap = IM2COL ? min(TPS, p.cv.taps - kb * TPS) : TPS;
 #pragma unroll
@@ -304,7 +322,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 #pragma unroll
             for (int k = 0; k < BK / UMMA_K; ++k) {
               const uint64_t adesc = make_sdesc(a_addr + k * (UMMA_K * ROWB), A_CHUNK, 8 * ROWB, LAYOUT_A);
-              const uint64_t bdesc = make_sdesc(b_addr + k * (UMMA_K * 128), 64 * BK * 2, 1024, 2u);
+              const uint64_t bdesc = make_sdesc(b_addr + k * (UMMA_K * BROWB), BK * BROWB, 8 * BROWB, LAYOUT_B);
               umma_f16(tmem_d, adesc, bdesc, IDESC, acc);
               acc = 1;
             }
@@ -476,16 +494,17 @@ static int num_sms() {
   return g_num_sms;
 }
 
-template <int BN, int CPT, bool MN, bool IM2COL>
+template <int BN, int CPT, bool MN, bool IM2COL, bool BRES = false>
 static int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p, int max_ctas,
                   cudaStream_t stream) {
   using C_ = Cfg<BN>;
+  constexpr int SMEM = BRES ? (BRES_STAGES * C_::A_BYTES + BRES_B_BYTES + 1024 + 256) : C_::SMEM_BYTES;
   static bool attr_set = false;
-  auto kern = gemm_tcgen05_kernel<BN, CPT, MN, IM2COL>;
+  auto kern = gemm_tcgen05_kernel<BN, CPT, MN, IM2COL, BRES>;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C_::SMEM_BYTES);
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
     if (e != cudaSuccess) {
-      set_last_error("cudaFuncSetAttribute(smem=%d): %s", C_::SMEM_BYTES, cudaGetErrorString(e));
+      set_last_error("cudaFuncSetAttribute(smem=%d): %s", SMEM, cudaGetErrorString(e));
       return B200RL_ERR_CUDA;
     }
     attr_set = true;
@@ -493,7 +512,7 @@ static int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmPara
   const int total = p.m_tiles * p.n_tiles * p.splits;
   int grid = total < num_sms() ? total : num_sms();
   if (max_ctas > 0 && grid > max_ctas) grid = max_ctas;
-  kern<<<grid, NUM_THREADS, C_::SMEM_BYTES, stream>>>(tmA, tmB, p);
+  kern<<<grid, NUM_THREADS, SMEM, stream>>>(tmA, tmB, p);
   return check_launch("gemm_tcgen05_kernel");
 }
 
@@ -553,12 +572,29 @@ int gemm_f16_impl(const void* A, const void* B, void* C, const float* bias, cons
 }
 
 template <int CPT, bool MN>
-static int launch_conv(int BN, const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p, cudaStream_t st) {
-  switch (BN) {
-    case 32: if (!MN) return launch<32, CPT, false, true>(tmA, tmB, p, 0, st); break;
-    case 64: return launch<64, CPT, MN, true>(tmA, tmB, p, 0, st);
-    case 128: return launch<128, CPT, MN, true>(tmA, tmB, p, 0, st);
-    default: break;
+static int launch_conv(int BN, bool bres, const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p,
+                       cudaStream_t st) {
+  if (MN) {
+    switch (BN) {
+      case 32: return launch<32, CPT, MN, true>(tmA, tmB, p, 0, st);
+      case 64: return launch<64, CPT, MN, true>(tmA, tmB, p, 0, st);
+      case 128: return launch<128, CPT, MN, true>(tmA, tmB, p, 0, st);
+      default: break;
+    }
+  } else if (bres) {
+    switch (BN) {
+      case 32: return launch<32, CPT, false, true, !MN>(tmA, tmB, p, 0, st);
+      case 64: return launch<64, CPT, false, true, !MN>(tmA, tmB, p, 0, st);
+      case 128: return launch<128, CPT, false, true, !MN>(tmA, tmB, p, 0, st);
+      default: break;
+    }
+  } else {
+    switch (BN) {
+      case 32: return launch<32, CPT, false, true>(tmA, tmB, p, 0, st);
+      case 64: return launch<64, CPT, false, true>(tmA, tmB, p, 0, st);
+      case 128: return launch<128, CPT, false, true>(tmA, tmB, p, 0, st);
+      default: break;
+    }
   }
   set_last_error("conv_gemm: unsupported tile N=%d", BN);
   return B200RL_ERR_UNSUPPORTED;
@@ -605,12 +641,14 @@ int conv_gemm_impl(const void* x, long long B, int H, int W, int C, int R, int S
     if ((rc = make_tmap_im2col(&tmA, x, B, H, W, C, lower_w, lower_h, upper_w, upper_h, stride_w, stride_h, BM)) != 0)
       return rc;
     if ((rc = make_tmap(&tmB, Wt_or_dz, N, (long long)taps * C, ldb, C, BN)) != 0) return rc;
-    if (C == 64) return launch_conv<64, false>(BN, tmA, tmB, p, stream);
-    if (C == 32) return launch_conv<32, false>(BN, tmA, tmB, p, stream);
-    return launch_conv<16, false>(BN, tmA, tmB, p, stream);
+    // weights resident in smem when the whole [N, taps*C] matrix fits next to the A ring
+    const bool bres = (p.n_tiles == 1) && ((long long)taps * BN * C * 2 <= BRES_B_BYTES) && (split_k != -1);
+    if (C == 64) return launch_conv<64, false>(BN, bres, tmA, tmB, p, stream);
+    if (C == 32) return launch_conv<32, false>(BN, bres, tmA, tmB, p, stream);
+    return launch_conv<16, false>(BN, bres, tmA, tmB, p, stream);
   }
   B200RL_REQUIRE(mode == MODE_F32_ATOMIC, "conv_gemm: wgrad needs the fp32 atomic epilogue");
-  const int BN = (N > 64) ? 128 : 64;
+  const int BN = (N > 64) ? 128 : (N > 32) ? 64 : 32;
   p.M = taps * C; p.N = N; p.K = (int)rows;
   p.m_tiles = ceil_div(p.M, BM);
   p.n_tiles = ceil_div(N, BN);
@@ -618,10 +656,10 @@ int conv_gemm_impl(const void* x, long long B, int H, int W, int C, int R, int S
   fill_splits(p, split_k);
   if ((rc = make_tmap_im2col(&tmA, x, B, H, W, C, lower_w, lower_h, upper_w, upper_h, stride_w, stride_h, BK)) != 0)
     return rc;
-  if ((rc = make_tmap(&tmB, Wt_or_dz, rows, N, ldb, 64, BK)) != 0) return rc;
-  if (C == 64) return launch_conv<64, true>(BN, tmA, tmB, p, stream);
-  if (C == 32) return launch_conv<32, true>(BN, tmA, tmB, p, stream);
-  return launch_conv<16, true>(BN, tmA, tmB, p, stream);
+  if ((rc = make_tmap(&tmB, Wt_or_dz, rows, N, ldb, BN < 64 ? BN : 64, BK)) != 0) return rc;
+  if (C == 64) return launch_conv<64, true>(BN, false, tmA, tmB, p, stream);
+  if (C == 32) return launch_conv<32, true>(BN, false, tmA, tmB, p, stream);
+  return launch_conv<16, true>(BN, false, tmA, tmB, p, stream);
 }
 
 }  // namespace b200rl

@@ -55,6 +55,7 @@ class ParamStore:
         self.gviews = OrderedDict()
         self.offsets = OrderedDict()
         self.tf_map = OrderedDict()   # tf name -> (internal name, slicer or None, tf shape)
+        self.row_perms = {}
         self.params = self.grads = self.m = self.v = None
 
     def add(self, name, init):
@@ -63,8 +64,11 @@ class ParamStore:
         self._specs.append((name, init.shape, init))
         return name
 
-    def map_tf(self, tf_name, internal, tf_shape, col_slice=None):
+    def map_tf(self, tf_name, internal, tf_shape, col_slice=None, row_perm=None):
+        """row_perm[i] = row of the TF-layout [K, N] matrix stored at internal row i."""
         self.tf_map[tf_name] = (internal, col_slice, tuple(tf_shape))
+        if row_perm is not None:
+            self.row_perms[tf_name] = np.asarray(row_perm, dtype=np.int64)
 
     def finalize(self):
         off = 0
@@ -113,7 +117,12 @@ class ParamStore:
         out = OrderedDict()
         for tf_name in self.tf_map:
             v, shape = self._tf_view(views, tf_name)
-            out[tf_name] = v.detach().cpu().numpy().reshape(shape).copy()
+            a = v.detach().cpu().numpy()
+            if tf_name in self.row_perms:
+                b = np.empty_like(a)
+                b[self.row_perms[tf_name]] = a
+                a = b
+            out[tf_name] = a.reshape(shape).copy()
         return out
 
     def import_tf(self, values, which="params"):
@@ -123,8 +132,10 @@ class ParamStore:
             if tf_name not in self.tf_map:
                 continue
             v, shape = self._tf_view(views, tf_name)
-            a = torch.from_numpy(np.ascontiguousarray(arr, dtype=np.float32).reshape(v.shape)).to(self.device)
-            v.copy_(a)
+            a = np.ascontiguousarray(arr, dtype=np.float32).reshape(v.shape)
+            if tf_name in self.row_perms:
+                a = np.ascontiguousarray(a[self.row_perms[tf_name]])
+            v.copy_(torch.from_numpy(a).to(self.device))
 
 
 class Linear:
@@ -132,15 +143,17 @@ class Linear:
     w_fwd [N, Kp] (= W^T, forward B operand) and w_bwd [K, Np] (dgrad B operand)."""
 
     def __init__(self, store, name, K, N, act, w_init, b_init=None, in_scale=1.0, w_shape=None, b_shape=None,
-                 tf_w=None, tf_b=None):
+                 tf_w=None, tf_b=None, row_perm=None):
         self.store, self.name, self.K, self.N, self.act = store, name, K, N, ops.ACT_CODES[act]
         self.in_scale = float(in_scale)
         self.Kp, self.Np = _pad8(K), _pad8(N)
         w_init = np.asarray(w_init, np.float32).reshape(K, N)
+        if row_perm is not None:
+            w_init = w_init[np.asarray(row_perm)]
         store.add(name + "/w", w_init)
         store.add(name + "/b", np.zeros(N, np.float32) if b_init is None else np.asarray(b_init, np.float32).reshape(N))
         if tf_w:
-            store.map_tf(tf_w, name + "/w", w_shape or (K, N))
+            store.map_tf(tf_w, name + "/w", w_shape or (K, N), row_perm=row_perm)
         if tf_b:
             store.map_tf(tf_b, name + "/b", b_shape or (N,))
         self.w_fwd = self.w_bwd = None
@@ -184,15 +197,33 @@ class Conv(Linear):
     """NHWC convolution lowered to im2col + tcgen05 GEMM (a2c/utils.py:37-56)."""
 
     def __init__(self, store, name, H, W, C, nf, rf, stride, act, w_init, same_pad=False, in_scale=1.0,
-                 tf_w=None, tf_b=None, b_shape=None):
+                 tf_w=None, tf_b=None, b_shape=None, allow_s2d=False):
         self.H, self.W, self.C, self.nf, self.rf, self.stride, self.same = H, W, C, nf, rf, stride, same_pad
         if same_pad:
             self.OH, self.OW = -(-H // stride), -(-W // stride)
         else:
             self.OH, self.OW = (H - rf) // stride + 1, (W - rf) // stride + 1
         self.P = self.OH * self.OW
+        # space-to-depth view of a uint8 first layer: stride-s conv, filter k*s  ->  stride-1 conv, filter k, over
+        # s*s*C channels.  The fp32 master weight is stored with its K rows in (a, b, dy, dx, c) order; row_perm
+        # maps them back to the reference's HWIO (ky, kx, c) order for checkpoints.
+        self.s2d = bool(allow_s2d and not same_pad and rf % stride == 0 and H % stride == 0 and W % stride == 0 and
+                        C * stride * stride in (16, 32, 64) and (stride * C) % 8 == 0 and (W * C) % 8 == 0)
+        row_perm = None
+        if self.s2d:
+            s_, k = stride, rf // stride
+            idx = np.empty(rf * rf * C, dtype=np.int64)
+            i = 0
+            for a in range(k):
+                for b in range(k):
+                    for dy in range(s_):
+                        for dx in range(s_):
+                            for c in range(C):
+                                idx[i] = ((a * s_ + dy) * rf + (b * s_ + dx)) * C + c
+                                i += 1
+            row_perm = idx
         super().__init__(store, name, rf * rf * C, nf, act, w_init, in_scale=in_scale, w_shape=(rf, rf, C, nf),
-                         b_shape=b_shape or (1, nf, 1, 1), tf_w=tf_w, tf_b=tf_b)
+                         b_shape=b_shape or (1, nf, 1, 1), tf_w=tf_w, tf_b=tf_b, row_perm=row_perm)
 
     def im2col(self, x, cols, B, src_idx=None):
         ops.im2col(x, cols, B, self.H, self.W, self.C, self.rf, self.stride, self.same, src_idx=src_idx, tag=self.name)
@@ -205,6 +236,9 @@ class Conv(Linear):
         """Geometry as seen by TMA.  Channels per tap must be 16/32/64; a first layer with few channels is
         viewed through "super-pixels" of 16 consecutive (x, c) elements when the stride allows it."""
         C, W, rf, st = self.C, self.W, self.rf, self.stride
+        if self.s2d:
+            self.geom = (self.H // st, W // st, C * st * st, rf // st, rf // st, 1, 1, 0, 0)
+            return self.geom
         pad_t = pad_l = 0
         if self.same:
             ph = max((self.OH - 1) * st + rf - self.H, 0)
@@ -279,9 +313,12 @@ class Tower:
                 else:
                     cn = "Conv" if i == 0 else f"Conv_{i}"
                     tfw, tfb, bshape = f"{tf_prefix}/convnet/{cn}/weights:0", f"{tf_prefix}/convnet/{cn}/biases:0", (nf,)
+                import os
                 conv = Conv(store, f"{prefix}/{nm}", H, W, C, nf, rf, stride, "relu",
                             winit((rf, rf, C, nf), math.sqrt(2)), same_pad=same_pad,
-                            in_scale=scale_in if i == 0 else 1.0, tf_w=tfw, tf_b=tfb, b_shape=bshape)
+                            in_scale=scale_in if i == 0 else 1.0, tf_w=tfw, tf_b=tfb, b_shape=bshape,
+                            allow_s2d=(i == 0 and os.environ.get("B200RL_EXPLICIT_CONV", "0") != "1"
+                                       and os.environ.get("B200RL_NO_S2D", "0") != "1"))
                 self.convs.append(conv)
                 H, W, C = conv.OH, conv.OW, nf
             self.flat = H * W * C
@@ -351,8 +388,11 @@ class Tower:
                 if c.implicit:
                     if i == 0 and self.in_u8:
                         # fused minibatch gather + uint8->fp16 cast (models.py:19, ppo2.py:165): 84 B/elem of traffic
-                        n_el = c.H * c.W * c.C
-                        ops.im2col(cur, self.x16, B, 1, 1, n_el, 1, 1, False, src_idx=src_idx, tag="gather_cast")
+                        if c.s2d:
+                            ops.s2d_gather(cur, self.x16, B, c.H, c.W, c.C, c.stride, src_idx=src_idx)
+                        else:
+                            n_el = c.H * c.W * c.C
+                            ops.im2col(cur, self.x16, B, 1, 1, n_el, 1, 1, False, src_idx=src_idx, tag="gather_cast")
                         cur = self.x16
                     elif i == 0 and src_idx is not None:
                         raise NotImplementedError("gather of fp16 image inputs")

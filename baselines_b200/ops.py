@@ -95,6 +95,14 @@ def im2col(x, cols, B, H, W, C, rf, stride, same_pad=False, src_idx=None, tag=No
               nbytes=float(B) * H * W * C * (1 if src_u8 else 2) + 2.0 * B * OH * OW * rf * rf * C)
 
 
+def s2d_gather(x, out, B, H, W, C, s, src_idx=None):
+    _chk(x, torch.uint8, "x")
+    _chk(out, torch.float16, "out")
+    _chk(src_idx, torch.int64, "src_idx")
+    _lib.call("b200rl_s2d_gather", _ptr(x), _ptr(src_idx), _ptr(out), int(B), H, W, C, s, _stream(),
+              label="s2d_gather", nbytes=3.0 * B * H * W * C)
+
+
 def col2im(dcols, saved, dx, B, H, W, C, rf, stride, same_pad=False, act=ACT_NONE, tag=None):
     _chk(dcols, torch.float16, "dcols")
     _chk(dx, torch.float16, "dx")

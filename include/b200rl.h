@@ -73,6 +73,9 @@ int b200rl_dgrad_weights(const float* w, void* out, int R, int S, int Cin, int C
  * the minibatch gather arr[mbinds] of ppo2/ppo2.py:165. */
 int b200rl_im2col(const void* x, int src_is_u8, const long long* src_idx, void* cols, long long B, int H, int W,
                   int C, int rf, int stride, int same_pad, void* stream);
+/* gather + uint8->fp16 + space-to-depth: out[b,Y,X,(dy*s+dx)*C+c] = x[src_idx[b], s*Y+dy, s*X+dx, c] */
+int b200rl_s2d_gather(const void* x, const long long* src_idx, void* out, long long B, int H, int W, int C, int s,
+                      void* stream);
 int b200rl_col2im(const void* dcols, const void* saved, void* dx, long long B, int H, int W, int C, int rf,
                   int stride, int same_pad, int act, void* stream);
 int b200rl_colsum(const void* dz, float* db, long long rows, int C, long long ld, float alpha, void* stream);
