@@ -244,7 +244,12 @@ class Conv(Linear):
             ph = max((self.OH - 1) * st + rf - self.H, 0)
             pw = max((self.OW - 1) * st + rf - W, 0)
             pad_t, pad_l = ph // 2, pw // 2
-        if C in (16, 32, 64):
+        m = 64 // C if C in (16, 32) else 1
+        if m > 1 and W % m == 0 and rf % m == 0 and st % m == 0 and pad_l % m == 0:
+            # merge m horizontally adjacent pixels into one 64-channel "pixel": same memory, same K order,
+            # but full 128-byte TMA rows and m x fewer taps
+            g = (self.H, W // m, C * m, rf, rf // m, st, st // m, pad_t, pad_l // m)
+        elif C in (16, 32, 64):
             g = (self.H, W, C, rf, rf, st, st, pad_t, pad_l)
         elif 16 % C == 0 and (W * C) % 16 == 0 and (rf * C) % 16 == 0 and (st * C) % 16 == 0 and (pad_l * C) % 16 == 0:
             k = 16 // C
