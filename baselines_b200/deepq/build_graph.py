@@ -80,7 +80,8 @@ class QNet:
         self.dhid = [[torch.zeros(cap, l.Np, **f16) for l in layers[1:-1]] for layers in self.streams]
         self.ld_out = 16 * ((self.nA + 1 + 15) // 16)
         self.out = torch.zeros(cap, self.ld_out, dtype=torch.float32, device=dev)    # [A scores | S] per row
-        self.ld_dout = 64 * ((self.nA + 1 + 63) // 64)
+        self.s_col = nn._pad8(self.nA)               # dS lives at a 16-byte aligned column of dout
+        self.ld_dout = 64 * ((self.s_col + 1 + 63) // 64)
         self.dout = torch.zeros(cap, self.ld_dout, **f16)
 
     def refresh(self):
@@ -130,7 +131,7 @@ class QNet:
         direct = len(self.streams[0]) == 1             # no hidden layers: streams read the latent directly
         for si, layers in enumerate(self.streams):
             nl = len(layers)
-            col = 0 if si == 0 else self.nA
+            col = 0 if si == 0 else self.s_col
             dz, lddz = self.dout[:, col:], self.ld_dout
             for j in reversed(range(nl)):
                 l = layers[j]
@@ -222,7 +223,7 @@ class DQNModel:
             self.loss.zero_()
             ops.dqn_td(q.out, ld, sp(q.out), ld, self.on_out, ld, sp(self.on_out), ld, qt.out, ld, sp(qt.out), ld, nA,
                        idx, actions, rewards, dones, weights, self.gamma, self.double_q, self.td, q.dout, q.ld_dout,
-                       q.dout[:, nA:] if q.dueling else None, q.ld_dout, self.loss, B)
+                       q.dout[:, q.s_col:] if q.dueling else None, q.ld_dout, self.loss, B)
             q.backward(B, 1.0 / B)
             self.opt.step(self.lr if lr is None else lr)
             q.refresh()
