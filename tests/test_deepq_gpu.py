@@ -45,6 +45,10 @@ def test_dqn_train_step_matches_oracle(network, ob_shape, dtype, dueling):
         rew = rng.randn(B).astype(np.float32)
         done = (rng.rand(B) < 0.1).astype(np.float32)
         w = (rng.rand(B) * 0.9 + 0.1).astype(np.float32)
+        # double-Q picks argmax_a q_online(s'): where the top-2 gap is inside the fp16 error the two paths may
+        # legitimately pick different actions, so mark those transitions terminal (target = reward only)
+        qn = np.sort(oracle.q_values(o_1), axis=1)
+        done[(qn[:, -1] - qn[:, -2]) < 3e-2] = 1.0
         f = lambda z: torch.as_tensor(z).to(dev)
         td = model.train_device(f(o_t), f(o_1), f(act), f(rew), f(done), f(w), None, B).cpu().numpy()
         td_o = oracle.train(1e-4, o_t, act, rew, o_1, done, w)
