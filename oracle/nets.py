@@ -471,13 +471,13 @@ class DQNOracle:
         grads = [g if g is not None else torch.zeros_like(p) for g, p in zip(grads, self.tp.values())]
         for t in self.tp.values():
             t.requires_grad_(False)
+        self.last_grads = OrderedDict((k, g.numpy().copy()) for k, g in zip(self.tp.keys(), grads))   # pre-clip
         if self.clip is not None:                                     # per-variable tf.clip_by_norm :416-421
             out = []
             for g in grads:
                 n = torch.sqrt((g.double() ** 2).sum()).to(g.dtype)
                 out.append(g * self.clip / torch.maximum(n, torch.tensor(self.clip, dtype=g.dtype)))
             grads = out
-        self.last_grads = OrderedDict((k, g.numpy().copy()) for k, g in zip(self.tp.keys(), grads))
         self.t += 1
         for (k, p), g in zip(list(self.tp.items()), grads):
             self.tp[k], self.m[k], self.v[k] = adam_tf(p, g, self.m[k], self.v[k], self.t, lr, eps=adam_eps)
