@@ -41,6 +41,16 @@ def test_dqn_train_step_matches_oracle(network, ob_shape, dtype, dueling):
 
     dev = model.device
     for it in range(3):
+        # Adam's first steps move every weight by ~lr regardless of |g| (m/sqrt(v) = +-1), so sign flips of
+        # near-zero gradients make two correct implementations drift apart; re-synchronise the state so that
+        # every iteration compares ONE step from identical parameters / Adam slots / target network.
+        model.q.store.import_tf({k: v.numpy() for k, v in oracle.tp.items()}, "params")
+        model.q.store.import_tf({k: v.numpy() for k, v in oracle.m.items()}, "m")
+        model.q.store.import_tf({k: v.numpy() for k, v in oracle.v.items()}, "v")
+        model.qt.store.import_tf({k: v.numpy() for k, v in oracle.tt.items()}, "params")
+        model.opt.t = oracle.t
+        model.q.refresh()
+        model.qt.refresh()
         o_t, o_1 = obs(), obs()
         act = rng.randint(0, nA, B).astype(np.int64)
         rew = rng.randn(B).astype(np.float32)
@@ -60,7 +70,7 @@ def test_dqn_train_step_matches_oracle(network, ob_shape, dtype, dueling):
         per = {k.split("q_func/")[-1]: round(float((((g[k] - oracle.last_grads[k]) ** 2).sum() /
                                                     max((oracle.last_grads[k] ** 2).sum(), 1e-30)) ** 0.5), 4) for k in g}
         print(f"[{network}] it={it} grad rel err total={(num / den) ** 0.5:.4f} per-var={per}")
-        assert (num / den) ** 0.5 < 4e-2, (it, (num / den) ** 0.5, per)
+        assert (num / den) ** 0.5 < 3e-2, (it, (num / den) ** 0.5, per)
         p, po = model.q.store.export_tf("params"), {k: v.numpy() for k, v in oracle.tp.items()}
         err = max(float(np.abs(p[k] - po[k]).max()) for k in p)
         assert err < 3e-3, (it, err)
