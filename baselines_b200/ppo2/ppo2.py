@@ -67,6 +67,19 @@ def learn(*, network, env, total_timesteps, eval_env=None, seed=None, nsteps=204
         cliprangenow = cliprange(frac)
         if update % log_interval == 0 and is_root: logger.info('Stepping environment...')
 
+        if not hasattr(model, "train_rollout"):
+            # foreign Model (model_fn=...): the reference's host-side minibatch loop, ppo2.py:142-166
+            mblossvals = _reference_style_update(runner, model, lrnow, cliprangenow, nbatch, nbatch_train,
+                                                 noptepochs, epinfobuf)
+            lossvals = np.mean(mblossvals, axis=0)
+            tnow = time.perf_counter()
+            if update % log_interval == 0 or update == 1:
+                logger.logkv("misc/nupdates", update)
+                logger.logkv("fps", int(nbatch / (tnow - tstart)))
+                for (lossval, lossname) in zip(lossvals, model.loss_names):
+                    logger.logkv('loss/' + lossname, float(lossval))
+                logger.dumpkvs()
+            continue
         ro, epinfos = runner.run_device()                                   # ppo2.py:142
         if eval_runner is not None:
             _, eval_epinfos = eval_runner.run_device()
@@ -110,6 +123,20 @@ def learn(*, network, env, total_timesteps, eval_env=None, seed=None, nsteps=204
             print('Saving to', savepath)
             model.save(savepath)
     return model
+
+
+def _reference_style_update(runner, model, lrnow, cliprangenow, nbatch, nbatch_train, noptepochs, epinfobuf):
+    obs, returns, masks, actions, values, neglogpacs, states, epinfos = runner.run()
+    epinfobuf.extend(epinfos)
+    out = []
+    inds = np.arange(nbatch)
+    for _ in range(noptepochs):
+        np.random.shuffle(inds)
+        for start in range(0, nbatch, nbatch_train):
+            mbinds = inds[start:start + nbatch_train]
+            slices = (arr[mbinds] for arr in (obs, returns, masks, actions, values, neglogpacs))
+            out.append(model.train(lrnow, cliprangenow, *slices))
+    return out
 
 
 def run_epochs(model, ro, lrnow, cliprangenow, nbatch, nbatch_train, noptepochs, device, perms=None):
