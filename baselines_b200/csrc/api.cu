@@ -17,7 +17,12 @@ void set_last_error(const char* fmt, ...) {
 }
 
 int gemm_f16_impl(const void*, const void*, void*, const float*, const void*, int, int, int, long long, long long,
-                  long long, long long, int, int, int, float, int, int, cudaStream_t);
+                  long long, long long, int, int, int, float, int, int, int, int, int, cudaStream_t);
+int conv_shift_fwd_impl(const void*, long long, int, int, int, const void*, long long, int, int, const int*, int, int,
+                        void*, const long long*, const void*, const long long*, const float*, int, int, float,
+                        cudaStream_t);
+int conv_shift_wgrad_impl(const void*, long long, int, const void*, int, int, const int*, float*, long long, float, int,
+                          cudaStream_t);
 int conv_gemm_impl(const void*, long long, int, int, int, int, int, int, int, int, int, int, int, const void*,
                    long long, void*, long long, const float*, const void*, long long, int, int, int, int, float, int,
                    int, int, int, int, cudaStream_t);
@@ -76,9 +81,21 @@ int b200rl_gae_scan(const float* rewards, const float* values, const uint8_t* do
 
 int b200rl_gemm_f16(const void* A, const void* B, void* C, const float* bias, const void* saved, int M, int N, int K,
                     long long lda, long long ldb, long long ldc, long long ld_saved, int mn_major, int mode, int act,
-                    float alpha, int split_k, int max_ctas, void* stream) {
+                    float alpha, int split_k, int max_ctas, int rm_C, int rm_OW, int rm_Wg, void* stream) {
   return gemm_f16_impl(A, B, C, bias, saved, M, N, K, lda, ldb, ldc, ld_saved, mn_major, mode, act, alpha, split_k,
-                       max_ctas, S(stream));
+                       max_ctas, rm_C, rm_OW, rm_Wg, S(stream));
+}
+
+int b200rl_conv_shift_fwd(const void* X, long long B, int Hg, int Wg, int C, const void* W, long long ldw, int N,
+                          int taps, const int* shifts, int vy, int vx, void* out, const long long* omap,
+                          const void* saved, const long long* smap, const float* bias, int act, int dact, float alpha,
+                          void* stream) {
+  return conv_shift_fwd_impl(X, B, Hg, Wg, C, W, ldw, N, taps, shifts, vy, vx, out, omap, saved, smap, bias, act, dact,
+                             alpha, S(stream));
+}
+int b200rl_conv_shift_wgrad(const void* X, long long rows, int C, const void* dY, int N, int taps, const int* shifts,
+                            float* G, long long ldg, float alpha, int max_ctas, void* stream) {
+  return conv_shift_wgrad_impl(X, rows, C, dY, N, taps, shifts, G, ldg, alpha, max_ctas, S(stream));
 }
 
 int b200rl_conv_gemm(const void* x, long long B, int H, int W, int C, int R, int S, int stride_h, int stride_w,

@@ -1,0 +1,436 @@
+// "Shift-GEMM" convolutions for sm_100a: stride-1 convolutions over an NHWC fp16 activation viewed as a plain
+// 2-D matrix X[rows = (n, y, x) grid positions, C] (strided convs are brought to this form by space-to-depth).
+//
+// Every input row is loaded into shared memory ONCE per tile by a tiled 2-D TMA; each filter tap (r, s) is then
+// just the same smem buffer read through a UMMA descriptor whose start address is shifted by (r*Wg + s) rows
+// (a SWIZZLE_128B descriptor may start at any 128-byte row: the swizzle is a function of the smem address).
+// This removes the R*S-fold duplication of an im2col operand on the L2->SM path.
+//
+//   conv_shift_fwd_kernel   (K-major):  OUT[m, :] = act( sum_t X[m + sh_t, :] * W_t^T + b )          forward
+//                                       and, with negative shifts over a zero-bordered dY, the data gradient
+//                                       dX[m, :] = ( sum_t dY[m - sh_t, :] * W_t ) * act'(saved)
+//   conv_shift_wgrad_kernel (MN-major): G[t, c, n] += alpha * sum_m X[m + sh_t, c] * dY[m, n]         wgrad
+//                                       (all taps' accumulators live in TMEM at once; X and dY are read once)
+//
+// Outputs at grid positions that are not valid conv outputs are computed from wrapped rows and discarded (fwd),
+// or multiply a zero of the zero-bordered dY (wgrad / dgrad) -- so dY tensors live on the conv's INPUT grid.
+// Replaces tf.nn.conv2d (a2c/utils.py:56) and its gradients (ppo2/model.py:102) of the reference.
+#include <stdlib.h>
+
+#include "common.cuh"
+#include "tc_common.cuh"
+
+namespace b200rl {
+
+static constexpr int SH_BM = 128;
+static constexpr int SH_THREADS = 256;
+static constexpr int SH_MAX_TAPS = 16;
+static constexpr int SH_AROWS = 160;                 // 128 + max shift span (<= 32)
+static constexpr int SH_ABYTES = SH_AROWS * 128;     // one 64-channel half of an A stage
+static constexpr int SH_WROWS_K = 96;                // wgrad: 64 + max shift span (<= 32)
+static constexpr int SH_WABYTES = SH_WROWS_K * 128;
+
+// address map of an output / saved tensor: grid position (n, y, x) + column -> element offset
+struct AddrMap {
+  int mode;              // 0: n*sN + y*sY + x*sX + col
+                         // 1: depth->space: cls = col/Cq: (s*y + cls/s, s*x + cls%s, col%Cq)
+                         // 2: space->depth: (y/s, x/s, ((y%s)*s + x%s)*Cq + col)
+  long long sN, sY, sX;
+  int Cq, s;
+};
+
+__device__ __forceinline__ long long map_addr(const AddrMap& a, int n, int y, int x, int col) {
+  if (a.mode == 1) {
+    const int cls = col / a.Cq;
+    return (long long)n * a.sN + (long long)(a.s * y + cls / a.s) * a.sY + (long long)(a.s * x + cls % a.s) * a.sX +
+           (col % a.Cq);
+  }
+  if (a.mode == 2)
+    return (long long)n * a.sN + (long long)(y / a.s) * a.sY + (long long)(x / a.s) * a.sX +
+           ((y % a.s) * a.s + (x % a.s)) * a.Cq + col;
+  return (long long)n * a.sN + (long long)y * a.sY + (long long)x * a.sX + col;
+}
+
+struct ShiftParams {
+  long long M;             // grid rows = B*Hg*Wg
+  int Hg, Wg;              // grid
+  int N;                   // output channels of the GEMM
+  int taps;
+  int shift[SH_MAX_TAPS];  // row shift of tap t, relative to min_shift (>= 0)
+  int min_shift;           // smallest absolute shift (negative for dgrad)
+  int vy, vx;              // rows with y < vy && x < vx produce an output
+  __half* out;
+  AddrMap omap;
+  const __half* saved;
+  AddrMap smap;
+  const float* bias;
+  int act, dact;           // dact = 1: multiply by act'(saved) instead of applying act
+  float alpha;
+  int num_tiles;
+};
+
+// ------------------------------------------------------------------------------------------------ forward / dgrad
+template <int BN, int KH>
+__global__ void __launch_bounds__(SH_THREADS, 1)
+conv_shift_fwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW,
+                      const ShiftParams p) {
+  constexpr int STAGE_BYTES = KH * SH_ABYTES;
+  constexpr int STAGES = (KH == 1) ? 6 : 3;
+  constexpr int W_SUB = BN * 128;                    // one (tap, half) weight sub-tile
+  constexpr int TMEM_COLS = (2 * BN <= 64) ? 64 : (2 * BN <= 128) ? 128 : 256;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* wres = smem + STAGES * STAGE_BYTES;       // resident weights: taps*KH sub-tiles
+  uint64_t* bars = reinterpret_cast<uint64_t*>(wres + 80 * 1024);
+  uint64_t* full_bar = bars;
+  uint64_t* empty_bar = bars + STAGES;
+  uint64_t* tfull_bar = bars + 2 * STAGES;
+  uint64_t* tempty_bar = bars + 2 * STAGES + 2;
+  uint64_t* w_bar = bars + 2 * STAGES + 4;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 5);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmX);
+    tma_prefetch_desc(&tmW);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+    for (int s = 0; s < 2; ++s) { mbar_init(&tfull_bar[s], 1); mbar_init(&tempty_bar[s], 128); }
+    mbar_init(w_bar, 1);
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc<TMEM_COLS>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      mbar_arrive_expect_tx(w_bar, (uint32_t)(p.taps * KH) * W_SUB);
+      for (int q = 0; q < p.taps * KH; ++q) tma_load_2d(wres + q * W_SUB, &tmW, w_bar, q * 64, 0);
+      int s = 0;
+      uint32_t ph = 0;
+      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+        mbar_wait(&empty_bar[s], ph ^ 1);
+        uint8_t* sa = smem + s * STAGE_BYTES;
+        mbar_arrive_expect_tx(&full_bar[s], (uint32_t)STAGE_BYTES);
+        const int row0 = tile * SH_BM + p.min_shift;                  // may be negative: TMA zero-fills
+#pragma unroll
+        for (int h = 0; h < KH; ++h) tma_load_2d(sa + h * SH_ABYTES, &tmX, &full_bar[s], h * 64, row0);
+        if (++s == STAGES) { s = 0; ph ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    constexpr uint32_t IDESC = (1u << 4) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(SH_BM >> 4) << 24);
+    if (lane == 0) {
+      int s = 0, as = 0;
+      uint32_t ph = 0, aph = 0;
+      mbar_wait(w_bar, 0);
+      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+        mbar_wait(&tempty_bar[as], aph ^ 1);
+        mbar_wait(&full_bar[s], ph);
+        tc_fence_after();
+        const uint32_t a_addr = smem_u32(smem + s * STAGE_BYTES);
+        const uint32_t w_addr = smem_u32(wres);
+        const uint32_t tmem_d = tmem_base + (uint32_t)(as * BN);
+        uint32_t acc = 0;
+        for (int t = 0; t < p.taps; ++t) {
+#pragma unroll
+          for (int h = 0; h < KH; ++h) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              const uint64_t adesc = make_sdesc(a_addr + h * SH_ABYTES + p.shift[t] * 128 + k * 32, 16, 1024, 2u);
+              const uint64_t bdesc = make_sdesc(w_addr + (t * KH + h) * W_SUB + k * 32, 16, 1024, 2u);
+              umma_f16(tmem_d, adesc, bdesc, IDESC, acc);
+              acc = 1;
+            }
+          }
+        }
+        umma_commit(&empty_bar[s]);
+        umma_commit(&tfull_bar[as]);
+        if (++s == STAGES) { s = 0; ph ^= 1; }
+        if (++as == 2) { as = 0; aph ^= 1; }
+      }
+    }
+  } else if (warp >= 4) {
+    const int ew = warp - 4;
+    int as = 0;
+    uint32_t aph = 0;
+    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+      mbar_wait(&tfull_bar[as], aph);
+      tc_fence_after();
+      const long long m = (long long)tile * SH_BM + ew * 32 + lane;
+      const int x = (int)(m % p.Wg);
+      const long long t2 = m / p.Wg;
+      const int y = (int)(t2 % p.Hg);
+      const int n = (int)(t2 / p.Hg);
+      const bool ok = (m < p.M) && (y < p.vy) && (x < p.vx);
+      const uint32_t taddr0 = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(as * BN);
+#pragma unroll 1
+      for (int c = 0; c < BN; c += 16) {
+        uint32_t r[16];
+        tmem_ld16(taddr0 + c, r);
+        tmem_ld_wait();
+        if (ok && c < p.N) {
+          float v[16];
+#pragma unroll
+          for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]) * p.alpha;
+          if (p.dact) {
+            if (p.saved) mask16(v, p.saved + map_addr(p.smap, n, y, x, c), true, 16, p.act);
+          } else {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) v[i] = apply_act(v[i] + (p.bias ? __ldg(p.bias + c + i) : 0.0f), p.act);
+          }
+          store16_f16(v, p.out + map_addr(p.omap, n, y, x, c), true, 16);
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(&tempty_bar[as]);
+      if (++as == 2) { as = 0; aph ^= 1; }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc<TMEM_COLS>(tmem_base);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ wgrad
+struct ShiftWgradParams {
+  long long M;             // reduction rows = B*Hg*Wg
+  int N;                   // dY channels
+  int taps;
+  int shift[SH_MAX_TAPS];  // >= 0
+  float* G;                // [taps*KH*64, N] fp32, row pitch ldg
+  long long ldg;
+  float alpha;
+  int kb_total, kb_per_cta;
+};
+
+template <int BN, int KH>
+__global__ void __launch_bounds__(SH_THREADS, 1)
+conv_shift_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmD,
+                        const ShiftWgradParams p) {
+  constexpr int BROWB = (BN >= 64) ? 128 : BN * 2;            // dY row bytes in smem
+  constexpr uint32_t LAYOUT_B = (BROWB == 64) ? 4u : 2u;
+  constexpr int B_BYTES = 64 * BROWB;
+  constexpr int STAGE_BYTES = KH * SH_WABYTES + 8192;         // A halves + B (<= 8 KB), keeps 1024 B alignment
+  constexpr int STAGES = (KH == 1) ? 8 : 6;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
+  uint64_t* full_bar = bars;
+  uint64_t* empty_bar = bars + STAGES;
+  uint64_t* done_bar = bars + 2 * STAGES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int kb0 = blockIdx.x * p.kb_per_cta;
+  const int kb1 = min(kb0 + p.kb_per_cta, p.kb_total);
+  const int nchunks = p.taps * KH;                  // 64-row chunks of the output matrix G
+  const int n_mt = (nchunks + 1) / 2;               // 128-row accumulator tiles
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmX);
+    tma_prefetch_desc(&tmD);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+    mbar_init(done_bar, 1);
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc<512>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int s = 0;
+      uint32_t ph = 0;
+      for (int kb = kb0; kb < kb1; ++kb) {
+        mbar_wait(&empty_bar[s], ph ^ 1);
+        uint8_t* sa = smem + s * STAGE_BYTES;
+        mbar_arrive_expect_tx(&full_bar[s], (uint32_t)(KH * SH_WABYTES + B_BYTES));
+#pragma unroll
+        for (int h = 0; h < KH; ++h) tma_load_2d(sa + h * SH_WABYTES, &tmX, &full_bar[s], h * 64, kb * 64);
+        tma_load_2d(sa + KH * SH_WABYTES, &tmD, &full_bar[s], 0, kb * 64);
+        if (++s == STAGES) { s = 0; ph ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    constexpr uint32_t IDESC = (1u << 4) | (1u << 15) | (1u << 16) | ((uint32_t)(BN >> 3) << 17) |
+                               ((uint32_t)(SH_BM >> 4) << 24);
+    if (lane == 0) {
+      int s = 0;
+      uint32_t ph = 0;
+      for (int kb = kb0; kb < kb1; ++kb) {
+        mbar_wait(&full_bar[s], ph);
+        tc_fence_after();
+        const uint32_t a_addr = smem_u32(smem + s * STAGE_BYTES);
+        const uint32_t b_addr = a_addr + KH * SH_WABYTES;
+        for (int j = 0; j < n_mt; ++j) {
+          const int q0 = 2 * j, q1 = 2 * j + 1;
+          const uint32_t st0 = a_addr + (q0 % KH) * SH_WABYTES + p.shift[q0 / KH] * 128;
+          uint32_t lbo = 128;
+          if (q1 < nchunks) lbo = (a_addr + (q1 % KH) * SH_WABYTES + p.shift[q1 / KH] * 128) - st0;
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const uint64_t adesc = make_sdesc(st0 + k * (16 * 128), lbo, 1024, 2u);
+            const uint64_t bdesc = make_sdesc(b_addr + k * (16 * BROWB), 64 * BROWB, 8 * BROWB, LAYOUT_B);
+            umma_f16(tmem_base + (uint32_t)(j * BN), adesc, bdesc, IDESC, (kb > kb0 || k > 0) ? 1u : 0u);
+          }
+        }
+        umma_commit(&empty_bar[s]);
+        if (++s == STAGES) { s = 0; ph ^= 1; }
+      }
+      umma_commit(done_bar);
+    }
+  } else if (warp >= 4) {
+    const int ew = warp - 4;
+    if (kb1 > kb0) {
+      mbar_wait(done_bar, 0);
+      tc_fence_after();
+      const int mrows = nchunks * 64;
+      for (int j = 0; j < n_mt; ++j) {
+        const int row = j * 128 + ew * 32 + lane;
+#pragma unroll 1
+        for (int c = 0; c < BN; c += 16) {
+          uint32_t r[16];
+          tmem_ld16(tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(j * BN + c), r);
+          tmem_ld_wait();
+          if (row < mrows && c < p.N) {
+            float* out = p.G + (long long)row * p.ldg + c;
+#pragma unroll
+            for (int i = 0; i < 16; ++i)
+              if (c + i < p.N) atomicAdd(out + i, __uint_as_float(r[i]) * p.alpha);
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc<512>(tmem_base);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ host
+template <int BN, int KH>
+static int launch_fwd(const CUtensorMap& tmX, const CUtensorMap& tmW, const ShiftParams& p, cudaStream_t st) {
+  constexpr int STAGES = (KH == 1) ? 6 : 3;
+  constexpr int SMEM = STAGES * KH * SH_ABYTES + 80 * 1024 + 1024 + 256;
+  static bool attr = false;
+  auto kern = conv_shift_fwd_kernel<BN, KH>;
+  if (!attr) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
+    if (e != cudaSuccess) {
+      set_last_error("conv_shift_fwd: smem attr %d: %s", SMEM, cudaGetErrorString(e));
+      return B200RL_ERR_CUDA;
+    }
+    attr = true;
+  }
+  const int grid = p.num_tiles < device_num_sms() ? p.num_tiles : device_num_sms();
+  kern<<<grid, SH_THREADS, SMEM, st>>>(tmX, tmW, p);
+  return check_launch("conv_shift_fwd_kernel");
+}
+
+template <int BN, int KH>
+static int launch_wgrad(const CUtensorMap& tmX, const CUtensorMap& tmD, const ShiftWgradParams& p, int grid,
+                        cudaStream_t st) {
+  constexpr int STAGES = (KH == 1) ? 8 : 6;
+  constexpr int SMEM = STAGES * (KH * SH_WABYTES + 8192) + 1024 + 256;
+  static bool attr = false;
+  auto kern = conv_shift_wgrad_kernel<BN, KH>;
+  if (!attr) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
+    if (e != cudaSuccess) {
+      set_last_error("conv_shift_wgrad: smem attr %d: %s", SMEM, cudaGetErrorString(e));
+      return B200RL_ERR_CUDA;
+    }
+    attr = true;
+  }
+  kern<<<grid, SH_THREADS, SMEM, st>>>(tmX, tmD, p);
+  return check_launch("conv_shift_wgrad_kernel");
+}
+
+static void fill_map(AddrMap& a, const long long* m) {       // {mode, sN, sY, sX, Cq, s}
+  a.mode = (int)m[0]; a.sN = m[1]; a.sY = m[2]; a.sX = m[3]; a.Cq = (int)m[4]; a.s = (int)m[5];
+}
+
+// X: [B*Hg*Wg, C] fp16 (C = 64 or 128, row pitch C); W: [N, taps*C] fp16 (row pitch ldw), K order (tap, channel);
+// shifts[taps]: absolute row shifts (all >= 0 for forward, all <= 0 for the data gradient).
+int conv_shift_fwd_impl(const void* X, long long B, int Hg, int Wg, int C, const void* W, long long ldw, int N,
+                        int taps, const int* shifts, int vy, int vx, void* out, const long long* omap,
+                        const void* saved, const long long* smap, const float* bias, int act, int dact, float alpha,
+                        cudaStream_t stream) {
+  B200RL_REQUIRE(X && W && out && omap && B > 0, "conv_shift_fwd: null operand");
+  B200RL_REQUIRE(C == 64 || C == 128, "conv_shift_fwd: C must be 64 or 128 (got %d)", C);
+  B200RL_REQUIRE(N == 32 || N == 64 || N == 128, "conv_shift_fwd: N must be 32, 64 or 128 (got %d)", N);
+  B200RL_REQUIRE(taps >= 1 && taps <= SH_MAX_TAPS, "conv_shift_fwd: 1..%d taps", SH_MAX_TAPS);
+  B200RL_REQUIRE((long long)taps * (C / 64) * N * 128 <= 80 * 1024, "conv_shift_fwd: weights do not fit in smem");
+  ShiftParams p = {};
+  int lo = shifts[0], hi = shifts[0];
+  for (int t = 1; t < taps; ++t) { lo = shifts[t] < lo ? shifts[t] : lo; hi = shifts[t] > hi ? shifts[t] : hi; }
+  B200RL_REQUIRE(hi - lo <= SH_AROWS - SH_BM, "conv_shift_fwd: shift span %d too large", hi - lo);
+  p.M = B * Hg * Wg; p.Hg = Hg; p.Wg = Wg; p.N = N; p.taps = taps; p.min_shift = lo;
+  for (int t = 0; t < taps; ++t) p.shift[t] = shifts[t] - lo;
+  p.vy = vy; p.vx = vx; p.out = reinterpret_cast<__half*>(out);
+  fill_map(p.omap, omap);
+  p.saved = reinterpret_cast<const __half*>(saved);
+  if (smap) fill_map(p.smap, smap);
+  p.bias = bias; p.act = act; p.dact = dact; p.alpha = alpha;
+  p.num_tiles = (int)((p.M + SH_BM - 1) / SH_BM);
+  CUtensorMap tmX, tmW;
+  int rc;
+  if ((rc = make_tmap_2d_f16(&tmX, X, p.M, C, C, 64, SH_AROWS)) != 0) return rc;
+  if ((rc = make_tmap_2d_f16(&tmW, W, N, (long long)taps * C, ldw, 64, N)) != 0) return rc;
+  const int KH = C / 64;
+#define SHIFT_FWD_CASE(bn)                                                                      \
+  if (N == bn) return KH == 1 ? launch_fwd<bn, 1>(tmX, tmW, p, stream) : launch_fwd<bn, 2>(tmX, tmW, p, stream);
+  SHIFT_FWD_CASE(32)
+  SHIFT_FWD_CASE(64)
+  SHIFT_FWD_CASE(128)
+#undef SHIFT_FWD_CASE
+  return B200RL_ERR_UNSUPPORTED;
+}
+
+// G[taps*C, N] (fp32, row pitch ldg) += alpha * sum_m X[m + shift_t, c] * dY[m, n]
+int conv_shift_wgrad_impl(const void* X, long long rows, int C, const void* dY, int N, int taps, const int* shifts,
+                          float* G, long long ldg, float alpha, int max_ctas, cudaStream_t stream) {
+  B200RL_REQUIRE(X && dY && G && rows > 0, "conv_shift_wgrad: null operand");
+  B200RL_REQUIRE(C == 64 || C == 128, "conv_shift_wgrad: C must be 64 or 128");
+  B200RL_REQUIRE(N == 32 || N == 64, "conv_shift_wgrad: N must be 32 or 64 (got %d)", N);
+  B200RL_REQUIRE(taps >= 1 && taps <= SH_MAX_TAPS, "conv_shift_wgrad: 1..%d taps", SH_MAX_TAPS);
+  const int KH = C / 64;
+  const int n_mt = (taps * KH + 1) / 2;
+  B200RL_REQUIRE(n_mt * N <= 512, "conv_shift_wgrad: accumulators exceed TMEM");
+  ShiftWgradParams p = {};
+  for (int t = 0; t < taps; ++t) {
+    B200RL_REQUIRE(shifts[t] >= 0 && shifts[t] <= SH_WROWS_K - 64, "conv_shift_wgrad: shift %d out of range", shifts[t]);
+    p.shift[t] = shifts[t];
+    if (t > 0 && KH == 1) B200RL_REQUIRE(shifts[t] > shifts[t - 1], "conv_shift_wgrad: shifts must increase");
+  }
+  p.M = rows; p.N = N; p.taps = taps; p.G = G; p.ldg = ldg; p.alpha = alpha;
+  p.kb_total = (int)((rows + 63) / 64);
+  int ctas = device_num_sms();
+  if (max_ctas > 0 && max_ctas < ctas) ctas = max_ctas;
+  if (ctas > p.kb_total) ctas = p.kb_total;
+  p.kb_per_cta = (p.kb_total + ctas - 1) / ctas;
+  const int grid = (p.kb_total + p.kb_per_cta - 1) / p.kb_per_cta;
+  CUtensorMap tmX, tmD;
+  int rc;
+  if ((rc = make_tmap_2d_f16(&tmX, X, rows, C, C, 64, SH_WROWS_K)) != 0) return rc;
+  if ((rc = make_tmap_2d_f16(&tmD, dY, rows, N, N, N < 64 ? N : 64, 64)) != 0) return rc;
+  if (N == 32) return KH == 1 ? launch_wgrad<32, 1>(tmX, tmD, p, grid, stream) : launch_wgrad<32, 2>(tmX, tmD, p, grid, stream);
+  return KH == 1 ? launch_wgrad<64, 1>(tmX, tmD, p, grid, stream) : launch_wgrad<64, 2>(tmX, tmD, p, grid, stream);
+}
+
+}  // namespace b200rl

@@ -20,10 +20,12 @@
 // (tf.gradients via ppo2/model.py:102) of the reference.
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 
 #include <mutex>
 
 #include "common.cuh"
+#include "tc_common.cuh"
 
 namespace b200rl {
 
@@ -32,8 +34,6 @@ static constexpr int BK = 64;          // elements of the reduction dimension pe
 static constexpr int UMMA_K = 16;
 static constexpr int NUM_THREADS = 256;
 
-enum : int { MODE_F16_ACT = 0, MODE_F32_STORE = 1, MODE_F32_ATOMIC = 2, MODE_F16_DACT = 3, MODE_F16_SHUFFLE = 4 };
-enum : int { ACT_NONE = 0, ACT_RELU = 1, ACT_TANH = 2 };
 
 struct ConvCoords {       // im2col traversal of the A operand (all zero for plain GEMMs)
   int OW, OH;             // grid of base pixels per image (GEMM rows = n*OH*OW + p*OW + q)
@@ -58,6 +58,7 @@ struct GemmParams {
   int mode, act;
   ConvCoords cv;
   ShuffleOut sh;
+  int rm_C, rm_OW, rm_Wg;   // rm_C > 0: output column (pix*rm_C + c) is stored at ((pix/rm_OW)*rm_Wg + pix%rm_OW)*rm_C + c
 };
 
 template <int BN>
@@ -70,78 +71,6 @@ struct Cfg {
   static constexpr int TMEM_COLS = (2 * BN <= 32) ? 32 : (2 * BN <= 64) ? 64 : (2 * BN <= 128) ? 128 : (2 * BN <= 256) ? 256 : 512;
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
 };
-
-// smem matrix descriptor; layout: 2 = SWIZZLE_128B, 4 = SWIZZLE_64B, 6 = SWIZZLE_32B
-__device__ __forceinline__ uint64_t make_sdesc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes, uint32_t layout) {
-  uint64_t d = 0;
-  d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);
-  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16;
-  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32;
-  d |= 1ull << 46;  // descriptor version (Blackwell)
-  d |= (uint64_t)layout << 61;
-  return d;
-}
-
-__device__ __forceinline__ void tma_load_im2col_4d(void* smem_dst, const CUtensorMap* tmap, uint64_t* bar, int c, int w,
-                                                   int h, int n, uint16_t off_w, uint16_t off_h) {
-  asm volatile(
-      "cp.async.bulk.tensor.4d.shared::cluster.global.im2col.mbarrier::complete_tx::bytes"
-      " [%0], [%1, {%3, %4, %5, %6}], [%2], {%7, %8};"
-      ::"r"(smem_u32(smem_dst)), "l"(tmap), "r"(smem_u32(bar)), "r"(c), "r"(w), "r"(h), "r"(n), "h"(off_w), "h"(off_h)
-      : "memory");
-}
-
-__device__ __forceinline__ float apply_act(float x, int act) {
-  if (act == ACT_RELU) return fmaxf(x, 0.0f);
-  if (act == ACT_TANH) return tanhf(x);
-  return x;
-}
-__device__ __forceinline__ float act_grad_from_saved(float h, int act) {
-  if (act == ACT_RELU) return h > 0.0f ? 1.0f : 0.0f;
-  if (act == ACT_TANH) return 1.0f - h * h;
-  return 1.0f;
-}
-
-// v[16] *= act'(saved[0..16)) with 16-byte loads when aligned
-__device__ __forceinline__ void mask16(float (&v)[16], const __half* sv, bool vec, int nvalid, int act) {
-  if (vec) {
-    uint4 q0 = *reinterpret_cast<const uint4*>(sv);
-    uint4 q1 = *reinterpret_cast<const uint4*>(sv + 8);
-    const __half2* h0 = reinterpret_cast<const __half2*>(&q0);
-    const __half2* h1 = reinterpret_cast<const __half2*>(&q1);
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      float2 f = __half22float2(h0[i]);
-      v[2 * i] *= act_grad_from_saved(f.x, act);
-      v[2 * i + 1] *= act_grad_from_saved(f.y, act);
-      float2 g = __half22float2(h1[i]);
-      v[8 + 2 * i] *= act_grad_from_saved(g.x, act);
-      v[8 + 2 * i + 1] *= act_grad_from_saved(g.y, act);
-    }
-  } else {
-#pragma unroll
-    for (int i = 0; i < 16; ++i)
-      if (i < nvalid) v[i] *= act_grad_from_saved(__half2float(sv[i]), act);
-  }
-}
-__device__ __forceinline__ void store16_f16(const float (&v)[16], __half* out, bool vec, int nvalid) {
-  if (vec) {
-    uint4 q0, q1;
-    __half2* h0 = reinterpret_cast<__half2*>(&q0);
-    __half2* h1 = reinterpret_cast<__half2*>(&q1);
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      h0[i] = __floats2half2_rn(v[2 * i], v[2 * i + 1]);
-      h1[i] = __floats2half2_rn(v[8 + 2 * i], v[8 + 2 * i + 1]);
-    }
-    *reinterpret_cast<uint4*>(out) = q0;
-    *reinterpret_cast<uint4*>(out + 8) = q1;
-  } else {
-#pragma unroll
-    for (int i = 0; i < 16; ++i)
-      if (i < nvalid) out[i] = __float2half_rn(v[i]);
-  }
-}
 
 // CPT: channels per tap (64 / 32 / 16); MN_MAJOR: wgrad layout; IM2COL: A operand through TMA im2col mode
 // BRES (K-major implicit conv only): the whole weight matrix (taps x [BN x CPT]) is loaded ONCE per CTA and
@@ -396,7 +325,12 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             } else {  // MODE_F16_DACT: dX = (dY W^T) * act'(saved activation)
               mask16(v, p.saved + (long long)row * p.ld_saved + col0, full && ((p.ld_saved & 7) == 0), nvalid, p.act);
             }
-            store16_f16(v, reinterpret_cast<__half*>(p.C) + (long long)row * p.ldc + col0,
+            int ocol = col0;
+            if (p.rm_C > 0) {
+              const int pix = col0 / p.rm_C;
+              ocol = ((pix / p.rm_OW) * p.rm_Wg + pix % p.rm_OW) * p.rm_C + col0 % p.rm_C;
+            }
+            store16_f16(v, reinterpret_cast<__half*>(p.C) + (long long)row * p.ldc + ocol,
                         full && ((p.ldc & 7) == 0), nvalid);
           }
         }
@@ -483,8 +417,15 @@ static int make_tmap_im2col(CUtensorMap* tm, const void* ptr, long long B, int H
   return B200RL_OK;
 }
 
+int make_tmap_2d_f16(CUtensorMap* tm, const void* ptr, long long rows, long long cols, long long ld, int box_cols,
+                     int box_rows) {
+  return make_tmap(tm, ptr, rows, cols, ld, box_cols, box_rows);
+}
+
 static int g_num_sms = 0;
-static int num_sms() {
+int device_num_sms();
+static int num_sms() { return device_num_sms(); }
+int device_num_sms() {
   if (g_num_sms == 0) {
     int dev = 0;
     cudaGetDevice(&dev);
@@ -526,8 +467,10 @@ static void fill_splits(GemmParams& p, int split_k) {
 // C-ABI body (declared in include/b200rl.h)
 int gemm_f16_impl(const void* A, const void* B, void* C, const float* bias, const void* saved, int M, int N, int K,
                   long long lda, long long ldb, long long ldc, long long ld_saved, int mn_major, int mode, int act,
-                  float alpha, int split_k, int max_ctas, cudaStream_t stream) {
+                  float alpha, int split_k, int max_ctas, int rm_C, int rm_OW, int rm_Wg, cudaStream_t stream) {
   B200RL_REQUIRE(A && B && C, "gemm: null operand");
+  B200RL_REQUIRE(rm_C == 0 || (rm_C % 16 == 0 && rm_OW > 0 && rm_Wg >= rm_OW && (mode == MODE_F16_ACT || mode == MODE_F16_DACT)),
+                 "gemm: bad column remap");
   B200RL_REQUIRE(M > 0 && N > 0 && K > 0, "gemm: bad shape M=%d N=%d K=%d", M, N, K);
   B200RL_REQUIRE((lda % 8) == 0 && (ldb % 8) == 0, "gemm: lda/ldb must be multiples of 8 fp16 (16 B): %lld %lld", lda,
                  ldb);
@@ -549,6 +492,7 @@ int gemm_f16_impl(const void* A, const void* B, void* C, const float* bias, cons
   fill_splits(p, split_k);
   p.C = C; p.ldc = ldc; p.bias = bias; p.saved = reinterpret_cast<const __half*>(saved); p.ld_saved = ld_saved;
   p.alpha = alpha; p.mode = mode; p.act = act;
+  p.rm_C = rm_C; p.rm_OW = rm_OW; p.rm_Wg = rm_Wg;
 
   CUtensorMap tmA, tmB;
   int rc;

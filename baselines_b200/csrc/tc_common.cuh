@@ -1,0 +1,88 @@
+// Device helpers shared by the tcgen05 GEMM / convolution kernels.
+#pragma once
+#include "common.cuh"
+
+namespace b200rl {
+
+enum : int { MODE_F16_ACT = 0, MODE_F32_STORE = 1, MODE_F32_ATOMIC = 2, MODE_F16_DACT = 3, MODE_F16_SHUFFLE = 4 };
+enum : int { ACT_NONE = 0, ACT_RELU = 1, ACT_TANH = 2 };
+
+// smem matrix descriptor; layout: 2 = SWIZZLE_128B, 4 = SWIZZLE_64B, 6 = SWIZZLE_32B
+__device__ __forceinline__ uint64_t make_sdesc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes, uint32_t layout) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32;
+  d |= 1ull << 46;  // descriptor version (Blackwell)
+  d |= (uint64_t)layout << 61;
+  return d;
+}
+
+__device__ __forceinline__ void tma_load_im2col_4d(void* smem_dst, const CUtensorMap* tmap, uint64_t* bar, int c, int w,
+                                                   int h, int n, uint16_t off_w, uint16_t off_h) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.im2col.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%3, %4, %5, %6}], [%2], {%7, %8};"
+      ::"r"(smem_u32(smem_dst)), "l"(tmap), "r"(smem_u32(bar)), "r"(c), "r"(w), "r"(h), "r"(n), "h"(off_w), "h"(off_h)
+      : "memory");
+}
+
+__device__ __forceinline__ float apply_act(float x, int act) {
+  if (act == ACT_RELU) return fmaxf(x, 0.0f);
+  if (act == ACT_TANH) return tanhf(x);
+  return x;
+}
+__device__ __forceinline__ float act_grad_from_saved(float h, int act) {
+  if (act == ACT_RELU) return h > 0.0f ? 1.0f : 0.0f;
+  if (act == ACT_TANH) return 1.0f - h * h;
+  return 1.0f;
+}
+
+// v[16] *= act'(saved[0..16)) with 16-byte loads when aligned
+__device__ __forceinline__ void mask16(float (&v)[16], const __half* sv, bool vec, int nvalid, int act) {
+  if (vec) {
+    uint4 q0 = *reinterpret_cast<const uint4*>(sv);
+    uint4 q1 = *reinterpret_cast<const uint4*>(sv + 8);
+    const __half2* h0 = reinterpret_cast<const __half2*>(&q0);
+    const __half2* h1 = reinterpret_cast<const __half2*>(&q1);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      float2 f = __half22float2(h0[i]);
+      v[2 * i] *= act_grad_from_saved(f.x, act);
+      v[2 * i + 1] *= act_grad_from_saved(f.y, act);
+      float2 g = __half22float2(h1[i]);
+      v[8 + 2 * i] *= act_grad_from_saved(g.x, act);
+      v[8 + 2 * i + 1] *= act_grad_from_saved(g.y, act);
+    }
+  } else {
+#pragma unroll
+    for (int i = 0; i < 16; ++i)
+      if (i < nvalid) v[i] *= act_grad_from_saved(__half2float(sv[i]), act);
+  }
+}
+__device__ __forceinline__ void store16_f16(const float (&v)[16], __half* out, bool vec, int nvalid) {
+  if (vec) {
+    uint4 q0, q1;
+    __half2* h0 = reinterpret_cast<__half2*>(&q0);
+    __half2* h1 = reinterpret_cast<__half2*>(&q1);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      h0[i] = __floats2half2_rn(v[2 * i], v[2 * i + 1]);
+      h1[i] = __floats2half2_rn(v[8 + 2 * i], v[8 + 2 * i + 1]);
+    }
+    *reinterpret_cast<uint4*>(out) = q0;
+    *reinterpret_cast<uint4*>(out + 8) = q1;
+  } else {
+#pragma unroll
+    for (int i = 0; i < 16; ++i)
+      if (i < nvalid) out[i] = __float2half_rn(v[i]);
+  }
+}
+
+
+// host helpers implemented in gemm_tcgen05.cu
+int make_tmap_2d_f16(CUtensorMap* tm, const void* ptr, long long rows, long long cols, long long ld, int box_cols,
+                     int box_rows);
+int device_num_sms();
+
+}  // namespace b200rl

@@ -44,14 +44,15 @@ def gae_scan(rewards, values, dones, last_values, last_dones, advs, returns, gam
 
 
 def gemm(A, B, C, *, M, N, K, lda, ldb, ldc, bias=None, saved=None, ld_saved=0, mn_major=False,
-         mode=MODE_F16_ACT, act=ACT_NONE, alpha=1.0, split_k=1, max_ctas=0, tag=None):
+         mode=MODE_F16_ACT, act=ACT_NONE, alpha=1.0, split_k=1, max_ctas=0, tag=None, remap=(0, 0, 0)):
     _chk(A, torch.float16, "A")
     _chk(B, torch.float16, "B")
     _chk(bias, torch.float32, "bias")
     _chk(saved, torch.float16, "saved")
     _lib.call("b200rl_gemm_f16", _ptr(A), _ptr(B), _ptr(C), _ptr(bias), _ptr(saved), int(M), int(N), int(K),
               int(lda), int(ldb), int(ldc), int(ld_saved), int(bool(mn_major)), int(mode), int(act), float(alpha),
-              int(split_k), int(max_ctas), _stream(), label="gemm." + (tag or ("wgrad" if mn_major else "tn")),
+              int(split_k), int(max_ctas), int(remap[0]), int(remap[1]), int(remap[2]), _stream(),
+              label="gemm." + (tag or ("wgrad" if mn_major else "tn")),
               flops=2.0 * M * N * K,
               nbytes=2.0 * (M * K + N * K) + M * N * (2 if mode in (MODE_F16_ACT, MODE_F16_DACT) else 4)
               + (2.0 * M * N if mode == MODE_F16_DACT else 0))
@@ -69,6 +70,40 @@ def conv_gemm(x, B, H, W, C, R, S, stride_h, stride_w, pad_h, pad_w, OH, OW, wt_
               int(mode), int(act), float(alpha), int(split_k), int(sh[0]), int(sh[1]), int(sh[2]), int(sh[3]),
               _stream(), label="conv." + (tag or str(kind)), flops=2.0 * rows * N * R * S * C,
               nbytes=2.0 * B * H * W * C + 2.0 * R * S * C * N + rows * N * (2.0 if kind == 0 else 2.0))
+
+
+import ctypes as _C
+
+
+def _iarr(vals, ctype):
+    return (ctype * len(vals))(*[int(v) for v in vals])
+
+
+def conv_shift_fwd(X, B, Hg, Wg, C, W, ldw, N, shifts, vy, vx, out, omap, *, saved=None, smap=None, bias=None,
+                   act=ACT_NONE, dact=False, alpha=1.0, tag=None):
+    """Shift-GEMM convolution (forward, or data gradient with dact=True).  omap / smap: 6-tuples
+    (mode, sN, sY, sX, Cq, s)."""
+    _chk(X, torch.float16, "X")
+    _chk(W, torch.float16, "W")
+    _chk(out, torch.float16, "out")
+    sh = _iarr(shifts, _C.c_int)
+    om = _iarr(omap, _C.c_longlong)
+    sm = _iarr(smap, _C.c_longlong) if smap is not None else None
+    rows = B * Hg * Wg
+    _lib.call("b200rl_conv_shift_fwd", _ptr(X), int(B), Hg, Wg, C, _ptr(W), int(ldw), int(N), len(shifts), sh, vy, vx,
+              _ptr(out), om, _ptr(saved), sm, _ptr(bias), int(act), int(bool(dact)), float(alpha), _stream(),
+              label="convs." + (tag or "fwd"), flops=2.0 * rows * N * len(shifts) * C,
+              nbytes=2.0 * rows * C + 2.0 * rows * N)
+
+
+def conv_shift_wgrad(X, rows, C, dY, N, shifts, G, ldg, alpha=1.0, max_ctas=0, tag=None):
+    _chk(X, torch.float16, "X")
+    _chk(dY, torch.float16, "dY")
+    _chk(G, torch.float32, "G")
+    sh = _iarr(shifts, _C.c_int)
+    _lib.call("b200rl_conv_shift_wgrad", _ptr(X), int(rows), C, _ptr(dY), int(N), len(shifts), sh, _ptr(G), int(ldg),
+              float(alpha), int(max_ctas), _stream(), label="convs." + (tag or "wgrad"),
+              flops=2.0 * rows * N * len(shifts) * C, nbytes=2.0 * rows * (C + N))
 
 
 def dgrad_weights(w, out, R, S, Cin, Cout, s, ld):

@@ -52,7 +52,23 @@ int b200rl_gae_scan(const float* rewards, const float* values, const uint8_t* do
  * max_ctas <= 0 : one persistent CTA per SM. */
 int b200rl_gemm_f16(const void* A, const void* B, void* C, const float* bias, const void* saved, int M, int N, int K,
                     long long lda, long long ldb, long long ldc, long long ld_saved, int mn_major, int mode, int act,
-                    float alpha, int split_k, int max_ctas, void* stream);
+                    float alpha, int split_k, int max_ctas, int rm_C, int rm_OW, int rm_Wg, void* stream);
+/* rm_C > 0 (fp16 outputs only): output column pix*rm_C + c is stored at ((pix/rm_OW)*rm_Wg + pix%rm_OW)*rm_C + c,
+ * i.e. a [.., OH, OW, C] row is scattered into a zero-bordered [.., Hg, Wg, C] grid (fc1 dgrad -> conv3's dY). */
+
+/* Shift-GEMM convolutions (tf.nn.conv2d a2c/utils.py:56 + gradients): stride-1 conv over X[(n,y,x) rows, C]
+ * (C = 64 or 128; strided convs arrive space-to-depth transformed).  Each X row is loaded into smem once; filter
+ * tap t is the same buffer read through a descriptor shifted by shifts[t] rows.
+ *   fwd  : out[map(n,y,x), :N] = act(sum_t X[m+shift_t] * W[:, t*C:(t+1)*C]^T + bias)   for y < vy, x < vx
+ *          dact = 1: out = (sum_t ...) * act'(saved[smap(n,y,x)])  (data gradient: X = zero-bordered dY, shifts <= 0)
+ *   omap / smap: {mode, sN, sY, sX, Cq, s}: 0 = n*sN+y*sY+x*sX+col; 1 = depth->space; 2 = space->depth
+ *   wgrad: G[t*C + c, n] += alpha * sum_m X[m+shift_t, c] * dY[m, n]  (dY on X's grid, zero at invalid positions) */
+int b200rl_conv_shift_fwd(const void* X, long long B, int Hg, int Wg, int C, const void* W, long long ldw, int N,
+                          int taps, const int* shifts, int vy, int vx, void* out, const long long* omap,
+                          const void* saved, const long long* smap, const float* bias, int act, int dact, float alpha,
+                          void* stream);
+int b200rl_conv_shift_wgrad(const void* X, long long rows, int C, const void* dY, int N, int taps, const int* shifts,
+                            float* G, long long ldg, float alpha, int max_ctas, void* stream);
 
 /* Implicit-GEMM convolution (tf.nn.conv2d a2c/utils.py:56 and its gradients): the A operand is read
  * straight from the NHWC fp16 activation x[B,H,W,C] by TMA im2col mode (C = 16, 32 or 64 channels per tap).

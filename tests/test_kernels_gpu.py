@@ -586,3 +586,113 @@ def test_conv_gemm_dgrad_pixel_shuffle(ops, B, Hin, Cin, Cout, rf, s):
     want = xin.grad.permute(0, 2, 3, 1) * (h_in.float() > 0)
     err = float((dx.float() - want).abs().max())
     assert torch.allclose(dx.float(), want, atol=3e-2, rtol=5e-3), err
+
+
+# ------------------------------------------------------------------------------------------ shift-GEMM convolutions
+SHIFT_CASES = [("c1_s2d", 5, 21, 21, 64, 2, 32), ("c2_s2d", 7, 10, 10, 128, 2, 64), ("c3", 11, 9, 9, 64, 3, 64)]
+
+
+@pytest.mark.parametrize("name,B,Hg,Wg,C,R,N", SHIFT_CASES)
+def test_conv_shift_forward_wgrad_dgrad(ops, name, B, Hg, Wg, C, R, N):
+    """Stride-1 RxR VALID conv over a [B,Hg,Wg,C] grid: forward (compact output), wgrad and dgrad (dY stored
+    zero-bordered on the input grid) against explicit patch matrices."""
+    torch.manual_seed(len(name) + B)
+    OH, OW = Hg - R + 1, Wg - R + 1
+    taps = R * R
+    shifts = [r * Wg + s for r in range(R) for s in range(R)]
+    x = (torch.randn(B, Hg, Wg, C, device="cuda") * 0.5).half()
+    K = taps * C
+    wt = (torch.randn(N, K, device="cuda") * 0.1).half()
+    bias = torch.randn(N, device="cuda")
+    P = _patches(x.float(), R, R, 1, 1, 0, 0, OH, OW)                    # [B*OH*OW, (r,s,c)]
+    # ---- forward -> compact [B,OH,OW,N]
+    out = torch.full((B, OH, OW, N), 7.0, dtype=torch.float16, device="cuda")
+    omap = (0, OH * OW * N, OW * N, N, 0, 0)
+    ops.conv_shift_fwd(x, B, Hg, Wg, C, wt, K, N, shifts, OH, OW, out, omap, bias=bias, act=ops.ACT_RELU)
+    torch.cuda.synchronize()
+    want = torch.relu(P @ wt.float().t() + bias).view(B, OH, OW, N)
+    err = float((out.float() - want).abs().max())
+    assert torch.allclose(out.float(), want, atol=3e-2, rtol=5e-3), (name, "fwd", err)
+    # ---- wgrad: dY lives on the INPUT grid, zero outside the valid OHxOW window
+    dz = torch.zeros(B, Hg, Wg, N, dtype=torch.float16, device="cuda")
+    dzv = (torch.randn(B, OH, OW, N, device="cuda") * 0.5).half()
+    dz[:, :OH, :OW] = dzv
+    G = torch.ones(K, N, dtype=torch.float32, device="cuda")
+    ops.conv_shift_wgrad(x, B * Hg * Wg, C, dz, N, shifts, G, N, alpha=0.5)
+    torch.cuda.synchronize()
+    wantG = 1.0 + 0.5 * (P.t() @ dzv.float().reshape(-1, N))
+    err = float((G - wantG).abs().max())
+    assert torch.allclose(G, wantG, atol=3e-3 * (B * OH * OW) ** 0.5, rtol=3e-3), (name, "wgrad", err)
+    # ---- dgrad: dX[m] = sum_t dY[m - sh_t] W_t, W_t = [C rows (c_in), N cols (c_out)] = rows t*C.. of W_hwio[K, N]
+    if C == 64:
+        w_hwio = (torch.randn(K, N, device="cuda") * 0.1).half()          # [(r,s,c_in), c_out]
+        wd = torch.zeros(C, taps * N, dtype=torch.float16, device="cuda")  # [c_in, (t, c_out)] K-major operand
+        for t in range(taps):
+            wd[:, t * N:(t + 1) * N] = w_hwio[t * C:(t + 1) * C]
+        saved = torch.randn(B, Hg, Wg, C, device="cuda").half()
+        dx = torch.zeros(B, Hg, Wg, C, dtype=torch.float16, device="cuda")
+        gmap = (0, Hg * Wg * C, Wg * C, C, 0, 0)
+        if N in (64, 128):
+            ops.conv_shift_fwd(dz, B, Hg, Wg, N, wd, taps * N, C, [-s for s in shifts], Hg, Wg, dx, gmap, saved=saved,
+                               smap=gmap, act=ops.ACT_RELU, dact=True)
+            torch.cuda.synchronize()
+            # reference: dX = patches-transpose: scatter-add of dz_valid @ W_t^T
+            dcols = dzv.float().reshape(-1, N) @ w_hwio.float().t()        # [B*OH*OW, (r,s,c)]
+            ref = torch.zeros(B, Hg, Wg, C, device="cuda")
+            dc = dcols.view(B, OH, OW, R, R, C)
+            for r in range(R):
+                for s in range(R):
+                    ref[:, r:r + OH, s:s + OW] += dc[:, :, :, r, s]
+            ref = ref * (saved.float() > 0)
+            err = float((dx.float() - ref).abs().max())
+            assert torch.allclose(dx.float(), ref, atol=3e-2, rtol=5e-3), (name, "dgrad", err)
+
+
+def test_conv_shift_address_maps(ops):
+    """space->depth (mode 2) output map of conv1 -> h1 and depth->space (mode 1) map of conv2's dgrad."""
+    torch.manual_seed(3)
+    B, Hg, Wg, C, N = 3, 21, 21, 64, 32
+    shifts = [0, 1, Wg, Wg + 1]
+    x = (torch.randn(B, Hg, Wg, C, device="cuda") * 0.5).half()
+    wt = (torch.randn(N, 4 * C, device="cuda") * 0.1).half()
+    P = _patches(x.float(), 2, 2, 1, 1, 0, 0, 20, 20)
+    want = (P @ wt.float().t()).view(B, 20, 20, N)
+    h1 = torch.zeros(B, 10, 10, 4 * N, dtype=torch.float16, device="cuda")
+    ops.conv_shift_fwd(x, B, Hg, Wg, C, wt, 4 * C, N, shifts, 20, 20, h1, (2, 100 * 4 * N, 10 * 4 * N, 4 * N, N, 2))
+    torch.cuda.synchronize()
+    s2d = want.view(B, 10, 2, 10, 2, N).permute(0, 1, 3, 2, 4, 5).reshape(B, 10, 10, 4 * N)
+    assert torch.allclose(h1.float(), s2d, atol=3e-2, rtol=5e-3)
+    # depth->space: GEMM columns (dy, dx, c) of row (n, Y, X) land at (2Y+dy, 2X+dx, c) of a 21x21x32 grid
+    dz = torch.zeros(B, 10, 10, 64, dtype=torch.float16, device="cuda")
+    dz[:, :9, :9] = (torch.randn(B, 9, 9, 64, device="cuda") * 0.5).half()
+    wd = (torch.randn(128, 4 * 64, device="cuda") * 0.1).half()           # [(dy,dx,c), (t, c_out)]
+    out = torch.zeros(B, 21, 21, 32, dtype=torch.float16, device="cuda")
+    sh = [-(a * 10 + b) for a in range(2) for b in range(2)]
+    ops.conv_shift_fwd(dz, B, 10, 10, 64, wd, 256, 128, sh, 10, 10, out, (1, 21 * 21 * 32, 21 * 32, 32, 32, 2),
+                       dact=True)
+    torch.cuda.synchronize()
+    dzp = torch.zeros(B, 11, 11, 64, device="cuda")
+    dzp[:, 1:, 1:] = dz.float()                                            # dY[m - (a*10+b)] == padded(Y-a, X-b)
+    ref = torch.zeros(B, 10, 10, 128, device="cuda")
+    for t, (a, b) in enumerate([(a, b) for a in range(2) for b in range(2)]):
+        ref += dzp[:, 1 - a:11 - a, 1 - b:11 - b] @ wd.float()[:, t * 64:(t + 1) * 64].t()
+    ref_sp = ref.view(B, 10, 10, 2, 2, 32).permute(0, 1, 3, 2, 4, 5).reshape(B, 20, 20, 32)
+    assert torch.allclose(out[:, :20, :20].float(), ref_sp, atol=3e-2, rtol=5e-3)
+    assert float(out[:, 20:].abs().max()) == 0 and float(out[:, :, 20:].abs().max()) == 0
+
+
+def test_gemm_column_remap(ops):
+    """fc1 dgrad writes its [B, 7*7*64] rows into the zero-bordered [B, 9, 9, 64] grid of conv3's dY."""
+    torch.manual_seed(4)
+    M, N, K = 300, 49 * 64, 128
+    A = (torch.randn(M, K, device="cuda") * 0.3).half()
+    W = (torch.randn(N, K, device="cuda") * 0.3).half()
+    saved = torch.randn(M, N, device="cuda").half()
+    out = torch.zeros(M, 81 * 64, dtype=torch.float16, device="cuda")
+    ops.gemm(A, W, out, M=M, N=N, K=K, lda=K, ldb=K, ldc=81 * 64, saved=saved, ld_saved=N, mode=ops.MODE_F16_DACT,
+             act=ops.ACT_RELU, remap=(64, 7, 9))
+    torch.cuda.synchronize()
+    ref = (A.float() @ W.float().t()) * (saved.float() > 0)
+    grid = out.float().view(M, 9, 9, 64)
+    assert torch.allclose(grid[:, :7, :7].reshape(M, -1), ref, atol=3e-2, rtol=5e-3)
+    assert float(grid[:, 7:].abs().max()) == 0 and float(grid[:, :, 7:].abs().max()) == 0
