@@ -183,14 +183,14 @@ class Linear:
                  mode=ops.MODE_F32_ATOMIC, alpha=alpha * self.in_scale, split_k=split, tag="wgrad." + self.name)
         ops.colsum(dz, self.gb, M, self.N, lddz, alpha=alpha)
 
-    def dgrad(self, dz, lddz, M, out, ldo, saved=None, ld_saved=0, act=ops.ACT_NONE):
+    def dgrad(self, dz, lddz, M, out, ldo, saved=None, ld_saved=0, act=ops.ACT_NONE, remap=(0, 0, 0)):
         """out[M, K] = (dz W^T) * act'(saved)."""
         if saved is None or act == ops.ACT_NONE:
             ops.gemm(dz, self.w_bwd, out, M=M, N=self.K, K=self.N, lda=lddz, ldb=self.Np, ldc=ldo,
-                     mode=ops.MODE_F16_ACT, act=ops.ACT_NONE, tag="dgrad." + self.name)
+                     mode=ops.MODE_F16_ACT, act=ops.ACT_NONE, tag="dgrad." + self.name, remap=remap)
         else:
             ops.gemm(dz, self.w_bwd, out, M=M, N=self.K, K=self.N, lda=lddz, ldb=self.Np, ldc=ldo, saved=saved,
-                     ld_saved=ld_saved, mode=ops.MODE_F16_DACT, act=act, tag="dgrad." + self.name)
+                     ld_saved=ld_saved, mode=ops.MODE_F16_DACT, act=act, tag="dgrad." + self.name, remap=remap)
 
 
 class Conv(Linear):
@@ -207,8 +207,9 @@ class Conv(Linear):
         # space-to-depth view of a uint8 first layer: stride-s conv, filter k*s  ->  stride-1 conv, filter k, over
         # s*s*C channels.  The fp32 master weight is stored with its K rows in (a, b, dy, dx, c) order; row_perm
         # maps them back to the reference's HWIO (ky, kx, c) order for checkpoints.
-        self.s2d = bool(allow_s2d and not same_pad and rf % stride == 0 and H % stride == 0 and W % stride == 0 and
-                        C * stride * stride in (16, 32, 64) and (stride * C) % 8 == 0 and (W * C) % 8 == 0)
+        self.s2d = bool(allow_s2d and stride > 1 and not same_pad and rf % stride == 0 and H % stride == 0 and
+                        W % stride == 0 and C * stride * stride in (16, 32, 64, 128) and (stride * C) % 8 == 0 and
+                        (W * C) % 8 == 0)
         row_perm = None
         if self.s2d:
             s_, k = stride, rf // stride
@@ -299,6 +300,33 @@ class Conv(Linear):
                       shuffle=(self.H, self.W, self.C, s), tag="dgrad." + self.name)
 
 
+def _shift_plan_ok(ob_shape, convs, same_pad):
+    """Shift-GEMM path (csrc/conv_shift.cu): every conv must be VALID with rf = k*stride on an input whose
+    space-to-depth view has 64 or 128 channels, with 32 / 64 output channels (NatureCNN qualifies)."""
+    if same_pad:
+        return False
+    H, W, C = ob_shape
+    for i, (_nm, nf, rf, st) in enumerate(convs):
+        if rf % st or H % st or W % st or C * st * st not in (64, 128) or nf not in (32, 64):
+            return False
+        if i > 0 and nf != 64:          # its data gradient reads dY with C = nf channels (64-wide TMA rows)
+            return False
+        k = rf // st
+        if (k - 1) * (W // st) + (k - 1) > 32 or k * k > 16 or k * k * (C * st * st // 64) * nf * 128 > 80 * 1024:
+            return False
+        OH, OW = (H - rf) // st + 1, (W - rf) // st + 1
+        if i + 1 < len(convs):
+            nst = convs[i + 1][3]
+            if OH % nst or OW % nst:
+                return False
+            # the data gradient of layer i+1 is a GEMM with N = s^2*C_in outputs and resident [N, taps*nf] weights
+            kn = convs[i + 1][2] // nst
+            if nf * nst * nst not in (64, 128) or kn * kn * nf * nst * nst * 128 > 80 * 1024:
+                return False
+        H, W, C = OH, OW, nf
+    return True
+
+
 class Tower:
     """A latent network (conv stack + fc, or mlp) with its activation workspace for `cap` samples."""
 
@@ -312,6 +340,10 @@ class Tower:
             H, W, C = ob_shape
             self.in_u8 = True
             scale_in = 1.0 / 255.0                                           # models.py:19 folded into c1 weights
+            import os
+            self.shift_mode = (os.environ.get("B200RL_EXPLICIT_CONV", "0") != "1" and
+                               os.environ.get("B200RL_NO_SHIFT", "0") != "1" and
+                               _shift_plan_ok(ob_shape, convs, same_pad))
             for i, (nm, nf, rf, stride) in enumerate(convs):
                 if tf_style == "a2c":
                     tfw, tfb, bshape = f"{tf_prefix}/{nm}/w:0", f"{tf_prefix}/{nm}/b:0", (1, nf, 1, 1)
@@ -322,8 +354,9 @@ class Tower:
                 conv = Conv(store, f"{prefix}/{nm}", H, W, C, nf, rf, stride, "relu",
                             winit((rf, rf, C, nf), math.sqrt(2)), same_pad=same_pad,
                             in_scale=scale_in if i == 0 else 1.0, tf_w=tfw, tf_b=tfb, b_shape=bshape,
-                            allow_s2d=(i == 0 and os.environ.get("B200RL_EXPLICIT_CONV", "0") != "1"
-                                       and os.environ.get("B200RL_NO_S2D", "0") != "1"))
+                            allow_s2d=(self.shift_mode or
+                                       (i == 0 and os.environ.get("B200RL_EXPLICIT_CONV", "0") != "1"
+                                        and os.environ.get("B200RL_NO_S2D", "0") != "1")))
                 self.convs.append(conv)
                 H, W, C = conv.OH, conv.OW, nf
             self.flat = H * W * C
@@ -337,6 +370,7 @@ class Tower:
             self.in_dim = None
         elif kind == "mlp":
             self.in_u8 = False
+            self.shift_mode = False
             nin = int(np.prod(ob_shape))
             self.in_dim, self.in_pad = nin, _pad8(nin)
             for i in range(num_layers):                                       # models.py:94-99 (tanh)
@@ -354,6 +388,15 @@ class Tower:
         f16 = dict(dtype=torch.float16, device=dev)
         for l in self.layers:
             l.materialize()
+        if self.convs and self.shift_mode:
+            self._materialize_shift(f16)
+            self.hfc = [torch.empty(cap, l.Np, **f16) for l in self.fcs]
+            self.dzfc = [torch.empty(cap, l.Np, **f16) for l in self.fcs]
+            if self.fcs:
+                self.dlatent, self.ld_dlatent = self.dzfc[-1], self.fcs[-1].Np
+            else:
+                raise NotImplementedError("shift-mode conv_only towers")
+            return
         import os
         allow = os.environ.get("B200RL_EXPLICIT_CONV", "0") != "1"
         # implicit dgrad needs VALID padding, the dz tensor's channels in {16,32,64} and a zero-initialised dx
@@ -380,14 +423,81 @@ class Tower:
         else:
             self.dlatent, self.ld_dlatent = self.dzconv[-1], self.flat
 
+    # ---- shift-GEMM conv stack ---------------------------------------------------------------------------------
+    def _materialize_shift(self, f16):
+        cap, cv = self.cap, self.convs
+        self.sg = []                                   # per layer: dict(Hg, Wg, Cg, k, shifts, s)
+        for c in cv:
+            s_, k = c.stride, c.rf // c.stride
+            Hg, Wg, Cg = c.H // s_, c.W // s_, c.C * s_ * s_
+            self.sg.append(dict(Hg=Hg, Wg=Wg, Cg=Cg, k=k, s=s_, shifts=[a * Wg + b for a in range(k) for b in range(k)]))
+        c0, g0 = cv[0], self.sg[0]
+        self.x16 = torch.empty(cap, g0["Hg"] * g0["Wg"] * g0["Cg"], **f16)
+        # activations: layer i's output is stored space-to-depth'ed for layer i+1 (compact after the last conv)
+        self.hconv = [torch.empty(cap, c.OH * c.OW * c.nf, **f16) for c in cv]
+        # gradients w.r.t. conv outputs live zero-bordered on the conv's INPUT grid
+        self.dY = [torch.zeros(cap, g["Hg"] * g["Wg"] * c.nf, **f16) for c, g in zip(cv, self.sg)]
+        # data-gradient weight operands [N' = Cg, taps * nf] (tap blocks of the master weight side by side)
+        self.wd = [None] + [torch.zeros(g["Cg"], g["k"] * g["k"] * c.nf, **f16) for c, g in zip(cv[1:], self.sg[1:])]
+        self.flat = cv[-1].OH * cv[-1].OW * cv[-1].nf
+
+    def _refresh_shift(self):
+        for i, (c, g) in enumerate(zip(self.convs, self.sg)):
+            if i == 0:
+                continue
+            taps, Cg, nf = g["k"] * g["k"], g["Cg"], c.nf
+            for t in range(taps):                      # wd[:, t*nf:(t+1)*nf] = fp16(W[t*Cg:(t+1)*Cg, :])
+                ops.cast_transpose(c.w[t * Cg:(t + 1) * Cg], Cg, nf, self.wd[i][:, t * nf:], taps * nf, None, 0)
+
+    def _forward_shift(self, x, B, src_idx):
+        cv, sg = self.convs, self.sg
+        c0 = cv[0]
+        ops.s2d_gather(x, self.x16, B, c0.H, c0.W, c0.C, c0.stride, src_idx=src_idx)
+        cur = self.x16
+        for i, (c, g) in enumerate(zip(cv, sg)):
+            if i + 1 < len(cv) and cv[i + 1].stride > 1:
+                sn = cv[i + 1].stride
+                Hn, Wn, Cn = c.OH // sn, c.OW // sn, c.nf * sn * sn
+                omap = (2, Hn * Wn * Cn, Wn * Cn, Cn, c.nf, sn)
+            else:
+                omap = (0, c.OH * c.OW * c.nf, c.OW * c.nf, c.nf, 0, 0)
+            ops.conv_shift_fwd(cur, B, g["Hg"], g["Wg"], g["Cg"], c.w_fwd, c.Kp, c.nf, g["shifts"], c.OH, c.OW,
+                               self.hconv[i], omap, bias=c.b, act=c.act, tag="fwd." + c.name)
+            cur = self.hconv[i]
+        return cur, self.flat
+
+    def _backward_shift(self, B, alpha):
+        """self.dY[-1] holds d loss / d (last conv pre-activation) on its grid (written by the fc dgrad)."""
+        cv, sg = self.convs, self.sg
+        for i in reversed(range(len(cv))):
+            c, g = cv[i], sg[i]
+            rows = B * g["Hg"] * g["Wg"]
+            xin = self.x16 if i == 0 else self.hconv[i - 1]
+            ops.conv_shift_wgrad(xin, rows, g["Cg"], self.dY[i], c.nf, g["shifts"], c.gw, c.nf,
+                                 alpha=alpha * c.in_scale, tag="wgrad." + c.name)
+            ops.colsum(self.dY[i], c.gb, rows, c.nf, c.nf, alpha=alpha)
+            if i == 0:
+                break
+            # dX_i (= dY_{i-1} after the ReLU mask) as a shift-GEMM over dY_i with negative shifts
+            cp, gp = cv[i - 1], sg[i - 1]
+            omap = (1, gp["Hg"] * gp["Wg"] * cp.nf, gp["Wg"] * cp.nf, cp.nf, cp.nf, g["s"])
+            smap = (0, g["Hg"] * g["Wg"] * g["Cg"], g["Wg"] * g["Cg"], g["Cg"], 0, 0)
+            ops.conv_shift_fwd(self.dY[i], B, g["Hg"], g["Wg"], c.nf, self.wd[i], g["k"] * g["k"] * c.nf, g["Cg"],
+                               [-sft for sft in g["shifts"]], g["Hg"], g["Wg"], self.dY[i - 1], omap,
+                               saved=self.hconv[i - 1], smap=smap, act=ops.ACT_RELU, dact=True, tag="dgrad." + c.name)
+
     def refresh(self):
         for l in self.layers:
             l.refresh()
+        if self.convs and self.shift_mode:
+            self._refresh_shift()
 
     # x: uint8 [*,H,W,C] images (cnn) or fp16 [*, in_pad] rows (mlp); src_idx gathers samples from it
     def forward(self, x, B, src_idx=None):
         assert B <= self.cap
-        if self.convs:
+        if self.convs and self.shift_mode:
+            h, ldh = self._forward_shift(x, B, src_idx)
+        elif self.convs:
             cur = x
             for i, c in enumerate(self.convs):
                 if c.implicit:
@@ -438,10 +548,18 @@ class Tower:
                 return
             if i > 0:
                 out, ldo = self.dzfc[i - 1], self.fcs[i - 1].Np
+                l.dgrad(dz, lddz, B, out, ldo, saved=xin, ld_saved=ldx, act=act_in)
+            elif self.shift_mode:
+                cL, gL = self.convs[-1], self.sg[-1]
+                out, ldo = self.dY[-1], gL["Hg"] * gL["Wg"] * cL.nf      # scatter into the zero-bordered grid
+                l.dgrad(dz, lddz, B, out, ldo, saved=xin, ld_saved=ldx, act=act_in, remap=(cL.nf, cL.OW, gL["Wg"]))
             else:
                 out, ldo = self.dzconv[-1], self.flat
-            l.dgrad(dz, lddz, B, out, ldo, saved=xin, ld_saved=ldx, act=act_in)
+                l.dgrad(dz, lddz, B, out, ldo, saved=xin, ld_saved=ldx, act=act_in)
             dz, lddz = out, ldo
+        if self.convs and self.shift_mode:
+            self._backward_shift(B, alpha)
+            return
         for i in reversed(range(len(self.convs))):
             c = self.convs[i]
             dzc = self.dzconv[i]
