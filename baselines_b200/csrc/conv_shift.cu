@@ -36,19 +36,27 @@ struct AddrMap {
                          // 1: depth->space: cls = col/Cq: (s*y + cls/s, s*x + cls%s, col%Cq)
                          // 2: space->depth: (y/s, x/s, ((y%s)*s + x%s)*Cq + col)
   long long sN, sY, sX;
-  int Cq, s;
+  int Cq, s;             // powers of two for modes 1 / 2
+  int Cq_log2, s_log2;
 };
 
-__device__ __forceinline__ long long map_addr(const AddrMap& a, int n, int y, int x, int col) {
-  if (a.mode == 1) {
-    const int cls = col / a.Cq;
-    return (long long)n * a.sN + (long long)(a.s * y + cls / a.s) * a.sY + (long long)(a.s * x + cls % a.s) * a.sX +
-           (col % a.Cq);
+// part of the address that does not depend on the column
+__device__ __forceinline__ long long map_rowbase(const AddrMap& a, int n, int y, int x) {
+  if (a.mode == 2) {
+    const int sm = a.s - 1;
+    return (long long)n * a.sN + (long long)(y >> a.s_log2) * a.sY + (long long)(x >> a.s_log2) * a.sX +
+           ((((y & sm) << a.s_log2) + (x & sm)) << a.Cq_log2);
   }
-  if (a.mode == 2)
-    return (long long)n * a.sN + (long long)(y / a.s) * a.sY + (long long)(x / a.s) * a.sX +
-           ((y % a.s) * a.s + (x % a.s)) * a.Cq + col;
-  return (long long)n * a.sN + (long long)y * a.sY + (long long)x * a.sX + col;
+  if (a.mode == 1) return (long long)n * a.sN + ((long long)y << a.s_log2) * a.sY + ((long long)x << a.s_log2) * a.sX;
+  return (long long)n * a.sN + (long long)y * a.sY + (long long)x * a.sX;
+}
+// column-dependent part (col is a multiple of 16, so a 16-column chunk never straddles a class)
+__device__ __forceinline__ long long map_coloff(const AddrMap& a, int col) {
+  if (a.mode == 1) {
+    const int cls = col >> a.Cq_log2;
+    return (long long)(cls >> a.s_log2) * a.sY + (long long)(cls & (a.s - 1)) * a.sX + (col & (a.Cq - 1));
+  }
+  return col;
 }
 
 struct ShiftParams {
@@ -73,7 +81,7 @@ struct ShiftParams {
 template <int BN, int KH>
 __global__ void __launch_bounds__(SH_THREADS, 1)
 conv_shift_fwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW,
-                      const ShiftParams p) {
+                      const __grid_constant__ ShiftParams p) {
   constexpr int STAGE_BYTES = KH * SH_ABYTES;
   constexpr int STAGES = (KH == 1) ? 6 : 3;
   constexpr int W_SUB = BN * 128;                    // one (tap, half) weight sub-tile
@@ -89,7 +97,9 @@ conv_shift_fwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_cons
   uint64_t* w_bar = bars + 2 * STAGES + 4;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 5);
 
+  __shared__ float s_bias[BN];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x < BN) s_bias[threadIdx.x] = (p.bias && (int)threadIdx.x < p.N) ? p.bias[threadIdx.x] : 0.0f;
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmX);
     tma_prefetch_desc(&tmW);
@@ -128,22 +138,26 @@ conv_shift_fwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_cons
       int s = 0, as = 0;
       uint32_t ph = 0, aph = 0;
       mbar_wait(w_bar, 0);
+      // descriptors differ only in their 14-bit start-address field: build the constant part once and add
+      // (byte offset >> 4) per MMA -- the single issuing thread is otherwise instruction bound for small N
+      const uint64_t desc_hi = make_sdesc(0, 16, 1024, 2u);
+      const uint32_t w_lo = (smem_u32(wres) & 0x3FFFFu) >> 4;
       for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
         mbar_wait(&tempty_bar[as], aph ^ 1);
         mbar_wait(&full_bar[s], ph);
         tc_fence_after();
-        const uint32_t a_addr = smem_u32(smem + s * STAGE_BYTES);
-        const uint32_t w_addr = smem_u32(wres);
+        const uint32_t a_lo = (smem_u32(smem + s * STAGE_BYTES) & 0x3FFFFu) >> 4;
         const uint32_t tmem_d = tmem_base + (uint32_t)(as * BN);
         uint32_t acc = 0;
         for (int t = 0; t < p.taps; ++t) {
+          const uint32_t at = a_lo + (uint32_t)p.shift[t] * 8u;          // 128 B per row = 8 x 16 B
+          const uint32_t wt = w_lo + (uint32_t)(t * KH) * (W_SUB >> 4);
 #pragma unroll
           for (int h = 0; h < KH; ++h) {
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
-              const uint64_t adesc = make_sdesc(a_addr + h * SH_ABYTES + p.shift[t] * 128 + k * 32, 16, 1024, 2u);
-              const uint64_t bdesc = make_sdesc(w_addr + (t * KH + h) * W_SUB + k * 32, 16, 1024, 2u);
-              umma_f16(tmem_d, adesc, bdesc, IDESC, acc);
+              umma_f16(tmem_d, desc_hi | (uint64_t)(at + h * (SH_ABYTES >> 4) + 2 * k),
+                       desc_hi | (uint64_t)(wt + h * (W_SUB >> 4) + 2 * k), IDESC, acc);
               acc = 1;
             }
           }
@@ -158,32 +172,58 @@ conv_shift_fwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_cons
     const int ew = warp - 4;
     int as = 0;
     uint32_t aph = 0;
+    constexpr int G = (BN >= 64) ? 4 : BN / 16;       // 16-column chunks handled together (loads in flight)
     for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
-      mbar_wait(&tfull_bar[as], aph);
-      tc_fence_after();
       const long long m = (long long)tile * SH_BM + ew * 32 + lane;
       const int x = (int)(m % p.Wg);
       const long long t2 = m / p.Wg;
       const int y = (int)(t2 % p.Hg);
       const int n = (int)(t2 / p.Hg);
       const bool ok = (m < p.M) && (y < p.vy) && (x < p.vx);
+      const long long obase = map_rowbase(p.omap, n, y, x);
+      const long long sbase = p.saved ? map_rowbase(p.smap, n, y, x) : 0;
+      const bool masked = p.dact && p.saved != nullptr;
+      mbar_wait(&tfull_bar[as], aph);
+      tc_fence_after();
       const uint32_t taddr0 = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(as * BN);
 #pragma unroll 1
-      for (int c = 0; c < BN; c += 16) {
-        uint32_t r[16];
-        tmem_ld16(taddr0 + c, r);
-        tmem_ld_wait();
-        if (ok && c < p.N) {
-          float v[16];
+      for (int c0 = 0; c0 < BN; c0 += 16 * G) {
+        uint4 sv[G][2];
+        if (masked && ok) {
 #pragma unroll
-          for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]) * p.alpha;
-          if (p.dact) {
-            if (p.saved) mask16(v, p.saved + map_addr(p.smap, n, y, x, c), true, 16, p.act);
-          } else {
-#pragma unroll
-            for (int i = 0; i < 16; ++i) v[i] = apply_act(v[i] + (p.bias ? __ldg(p.bias + c + i) : 0.0f), p.act);
+          for (int j = 0; j < G; ++j) {
+            const __half* sp = p.saved + sbase + map_coloff(p.smap, c0 + 16 * j);
+            sv[j][0] = __ldg(reinterpret_cast<const uint4*>(sp));
+            sv[j][1] = __ldg(reinterpret_cast<const uint4*>(sp) + 1);
           }
-          store16_f16(v, p.out + map_addr(p.omap, n, y, x, c), true, 16);
+        }
+        uint32_t r[G][16];
+#pragma unroll
+        for (int j = 0; j < G; ++j) tmem_ld16(taddr0 + c0 + 16 * j, r[j]);
+        tmem_ld_wait();
+        if (ok) {
+#pragma unroll
+          for (int j = 0; j < G; ++j) {
+            const int c = c0 + 16 * j;
+            float v[16];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[j][i]) * p.alpha;
+            if (p.dact) {
+              if (masked) {
+                const uint32_t w[8] = {sv[j][0].x, sv[j][0].y, sv[j][0].z, sv[j][0].w,
+                                       sv[j][1].x, sv[j][1].y, sv[j][1].z, sv[j][1].w};
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                  v[2 * i] *= act_grad_from_saved(__half2float(__ushort_as_half((unsigned short)(w[i] & 0xffffu))), p.act);
+                  v[2 * i + 1] *= act_grad_from_saved(__half2float(__ushort_as_half((unsigned short)(w[i] >> 16))), p.act);
+                }
+              }
+            } else {
+#pragma unroll
+              for (int i = 0; i < 16; ++i) v[i] = apply_act(v[i] + s_bias[c + i], p.act);
+            }
+            store16_f16(v, p.out + obase + map_coloff(p.omap, c), true, 16);
+          }
         }
       }
       tc_fence_before();
@@ -214,7 +254,7 @@ struct ShiftWgradParams {
 template <int BN, int KH>
 __global__ void __launch_bounds__(SH_THREADS, 1)
 conv_shift_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmD,
-                        const ShiftWgradParams p) {
+                        const __grid_constant__ ShiftWgradParams p) {
   constexpr int BROWB = (BN >= 64) ? 128 : BN * 2;            // dY row bytes in smem
   constexpr uint32_t LAYOUT_B = (BROWB == 64) ? 4u : 2u;
   constexpr int B_BYTES = 64 * BROWB;
@@ -274,17 +314,18 @@ conv_shift_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_co
         tc_fence_after();
         const uint32_t a_addr = smem_u32(smem + s * STAGE_BYTES);
         const uint32_t b_addr = a_addr + KH * SH_WABYTES;
+        const uint64_t bdesc0 = make_sdesc(b_addr, 64 * BROWB, 8 * BROWB, LAYOUT_B);
         for (int j = 0; j < n_mt; ++j) {
           const int q0 = 2 * j, q1 = 2 * j + 1;
           const uint32_t st0 = a_addr + (q0 % KH) * SH_WABYTES + p.shift[q0 / KH] * 128;
           uint32_t lbo = 128;
           if (q1 < nchunks) lbo = (a_addr + (q1 % KH) * SH_WABYTES + p.shift[q1 / KH] * 128) - st0;
+          const uint64_t adesc0 = make_sdesc(st0, lbo, 1024, 2u);
+          const uint32_t td = tmem_base + (uint32_t)(j * BN);
 #pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            const uint64_t adesc = make_sdesc(st0 + k * (16 * 128), lbo, 1024, 2u);
-            const uint64_t bdesc = make_sdesc(b_addr + k * (16 * BROWB), 64 * BROWB, 8 * BROWB, LAYOUT_B);
-            umma_f16(tmem_base + (uint32_t)(j * BN), adesc, bdesc, IDESC, (kb > kb0 || k > 0) ? 1u : 0u);
-          }
+          for (int k = 0; k < 4; ++k)
+            umma_f16(td, adesc0 + (uint64_t)(k * (16 * 128 / 16)), bdesc0 + (uint64_t)(k * (16 * BROWB / 16)), IDESC,
+                     (kb > kb0 || k > 0) ? 1u : 0u);
         }
         umma_commit(&empty_bar[s]);
         if (++s == STAGES) { s = 0; ph ^= 1; }
@@ -361,8 +402,14 @@ static int launch_wgrad(const CUtensorMap& tmX, const CUtensorMap& tmD, const Sh
   return check_launch("conv_shift_wgrad_kernel");
 }
 
-static void fill_map(AddrMap& a, const long long* m) {       // {mode, sN, sY, sX, Cq, s}
+static int ilog2(int v) { int l = 0; while ((1 << l) < v) ++l; return l; }
+static bool fill_map(AddrMap& a, const long long* m) {       // {mode, sN, sY, sX, Cq, s}
   a.mode = (int)m[0]; a.sN = m[1]; a.sY = m[2]; a.sX = m[3]; a.Cq = (int)m[4]; a.s = (int)m[5];
+  a.Cq_log2 = a.s_log2 = 0;
+  if (a.mode == 0) return true;
+  if (a.Cq < 16 || (a.Cq & (a.Cq - 1)) || a.s < 1 || (a.s & (a.s - 1))) return false;
+  a.Cq_log2 = ilog2(a.Cq); a.s_log2 = ilog2(a.s);
+  return true;
 }
 
 // X: [B*Hg*Wg, C] fp16 (C = 64 or 128, row pitch C); W: [N, taps*C] fp16 (row pitch ldw), K order (tap, channel);
@@ -383,9 +430,10 @@ int conv_shift_fwd_impl(const void* X, long long B, int Hg, int Wg, int C, const
   p.M = B * Hg * Wg; p.Hg = Hg; p.Wg = Wg; p.N = N; p.taps = taps; p.min_shift = lo;
   for (int t = 0; t < taps; ++t) p.shift[t] = shifts[t] - lo;
   p.vy = vy; p.vx = vx; p.out = reinterpret_cast<__half*>(out);
-  fill_map(p.omap, omap);
+  B200RL_REQUIRE(fill_map(p.omap, omap), "conv_shift_fwd: output map needs power-of-two Cq >= 16 and s");
   p.saved = reinterpret_cast<const __half*>(saved);
-  if (smap) fill_map(p.smap, smap);
+  if (smap) B200RL_REQUIRE(fill_map(p.smap, smap), "conv_shift_fwd: saved map needs power-of-two Cq >= 16 and s");
+  B200RL_REQUIRE(!(saved && !smap), "conv_shift_fwd: saved needs smap");
   p.bias = bias; p.act = act; p.dact = dact; p.alpha = alpha;
   p.num_tiles = (int)((p.M + SH_BM - 1) / SH_BM);
   CUtensorMap tmX, tmW;
