@@ -21,8 +21,8 @@ int gemm_f16_impl(const void*, const void*, void*, const float*, const void*, in
 int conv_shift_fwd_impl(const void*, long long, int, int, int, const void*, long long, int, int, const int*, int, int,
                         void*, const long long*, const void*, const long long*, const float*, int, int, float,
                         cudaStream_t);
-int conv_shift_wgrad_impl(const void*, long long, int, const void*, int, int, const int*, float*, long long, float, int,
-                          cudaStream_t);
+int conv_shift_wgrad_impl(const void*, long long, int, const void*, int, int, const int*, float*, long long, float,
+                          float*, float, int, cudaStream_t);
 int conv_gemm_impl(const void*, long long, int, int, int, int, int, int, int, int, int, int, int, const void*,
                    long long, void*, long long, const float*, const void*, long long, int, int, int, int, float, int,
                    int, int, int, int, cudaStream_t);
@@ -94,8 +94,9 @@ int b200rl_conv_shift_fwd(const void* X, long long B, int Hg, int Wg, int C, con
                              alpha, S(stream));
 }
 int b200rl_conv_shift_wgrad(const void* X, long long rows, int C, const void* dY, int N, int taps, const int* shifts,
-                            float* G, long long ldg, float alpha, int max_ctas, void* stream) {
-  return conv_shift_wgrad_impl(X, rows, C, dY, N, taps, shifts, G, ldg, alpha, max_ctas, S(stream));
+                            float* G, long long ldg, float alpha, float* gbias, float alpha_b, int max_ctas,
+                            void* stream) {
+  return conv_shift_wgrad_impl(X, rows, C, dY, N, taps, shifts, G, ldg, alpha, gbias, alpha_b, max_ctas, S(stream));
 }
 
 int b200rl_conv_gemm(const void* x, long long B, int H, int W, int C, int R, int S, int stride_h, int stride_w,

@@ -131,32 +131,55 @@ col2im_kernel(const __half* __restrict__ dcols, const __half* __restrict__ saved
 //   out[b, Y, X, (dy*s + dx)*C + c] = x[src_idx[b], s*Y + dy, s*X + dx, c]
 // A stride-s conv with filter rf = k*s over x becomes a stride-1 conv with filter k over `out`, whose
 // s*s*C channels give TMA im2col full 128-byte rows.  One thread = 8 consecutive elements of one (dy) segment.
+template <int EPT>   // elements per thread: 16 (one 16 B load, two 16 B stores) or 8
 __global__ void __launch_bounds__(256)
 s2d_gather_kernel(const uint8_t* __restrict__ x, const long long* __restrict__ src_idx, __half* __restrict__ out,
                   long long B, int H, int W, int C, int s) {
   const int seg = s * C;                   // contiguous elements per (Y, X, dy)
-  const int cps = seg / 8;                 // 8-element chunks per segment
+  const int cps = seg / EPT;
   const int HY = H / s, WX = W / s;
   const long long total = B * HY * WX * s * cps;
-  for (long long id = (long long)blockIdx.x * blockDim.x + threadIdx.x; id < total;
-       id += (long long)gridDim.x * blockDim.x) {
-    const int j = (int)(id % cps);
-    long long t = id / cps;
-    const int dy = (int)(t % s);
-    t /= s;
-    const int X = (int)(t % WX);
-    t /= WX;
-    const int Y = (int)(t % HY);
-    const long long b = t / HY;
-    const long long sb = src_idx ? src_idx[b] : b;
-    const uint8_t* src = x + ((sb * H + (long long)s * Y + dy) * W + (long long)s * X) * C + j * 8;
-    const uint2 q = *reinterpret_cast<const uint2*>(src);
-    const uint8_t* bp = reinterpret_cast<const uint8_t*>(&q);
-    __half o[8];
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long id0 = (long long)blockIdx.x * blockDim.x + threadIdx.x; id0 < total; id0 += 4 * stride) {
+    uint4 q[4];
+    __half* dst[4];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) o[i] = __ushort2half_rn((unsigned short)bp[i]);
-    __half* dst = out + (((b * HY + Y) * WX + X) * (long long)s + dy) * seg + j * 8;
-    *reinterpret_cast<uint4*>(dst) = *reinterpret_cast<const uint4*>(o);
+    for (int u = 0; u < 4; ++u) {          // 4 independent loads in flight per thread
+      const long long id = id0 + u * stride;
+      dst[u] = nullptr;
+      if (id < total) {
+        const int j = (int)(id % cps);
+        long long t = id / cps;
+        const int dy = (int)(t % s);
+        t /= s;
+        const int X = (int)(t % WX);
+        t /= WX;
+        const int Y = (int)(t % HY);
+        const long long b = t / HY;
+        const long long sb = src_idx ? src_idx[b] : b;
+        const uint8_t* src = x + ((sb * H + (long long)s * Y + dy) * W + (long long)s * X) * C + j * EPT;
+        if (EPT == 16) q[u] = __ldg(reinterpret_cast<const uint4*>(src));
+        else { const uint2 h = __ldg(reinterpret_cast<const uint2*>(src)); q[u] = make_uint4(h.x, h.y, 0, 0); }
+        dst[u] = out + (((b * HY + Y) * WX + X) * (long long)s + dy) * seg + j * EPT;
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      if (dst[u]) {
+        const uint32_t w[4] = {q[u].x, q[u].y, q[u].z, q[u].w};
+        uint4 o[2];
+        uint32_t* ow = reinterpret_cast<uint32_t*>(o);
+#pragma unroll
+        for (int i = 0; i < EPT / 4; ++i) {
+          const __half2 lo = __floats2half2_rn((float)(w[i] & 0xffu), (float)((w[i] >> 8) & 0xffu));
+          const __half2 hi = __floats2half2_rn((float)((w[i] >> 16) & 0xffu), (float)(w[i] >> 24));
+          ow[2 * i] = *reinterpret_cast<const uint32_t*>(&lo);
+          ow[2 * i + 1] = *reinterpret_cast<const uint32_t*>(&hi);
+        }
+        __stcs(reinterpret_cast<uint4*>(dst[u]), o[0]);
+        if (EPT == 16) __stcs(reinterpret_cast<uint4*>(dst[u]) + 1, o[1]);
+      }
+    }
   }
 }
 
@@ -239,9 +262,15 @@ int s2d_gather_impl(const void* x, const long long* src_idx, void* out, long lon
   B200RL_REQUIRE(H % s == 0 && W % s == 0 && (s * C) % 8 == 0 && (reinterpret_cast<uintptr_t>(x) & 7) == 0 &&
                      (W * C) % 8 == 0,
                  "s2d_gather: need H,W multiples of s and s*C, W*C multiples of 8");
-  const long long total = B * (H / s) * (W / s) * s * ((s * C) / 8);
-  s2d_gather_kernel<<<grid_for(total, 256), 256, 0, stream>>>(reinterpret_cast<const uint8_t*>(x), src_idx,
-                                                             reinterpret_cast<__half*>(out), B, H, W, C, s);
+  const bool wide = ((s * C) % 16 == 0) && ((W * C) % 16 == 0) && ((reinterpret_cast<uintptr_t>(x) & 15) == 0);
+  const long long total = B * (H / s) * (W / s) * s * ((s * C) / (wide ? 16 : 8));
+  const int grid = grid_for((total + 3) / 4, 256);
+  if (wide)
+    s2d_gather_kernel<16><<<grid, 256, 0, stream>>>(reinterpret_cast<const uint8_t*>(x), src_idx,
+                                                    reinterpret_cast<__half*>(out), B, H, W, C, s);
+  else
+    s2d_gather_kernel<8><<<grid, 256, 0, stream>>>(reinterpret_cast<const uint8_t*>(x), src_idx,
+                                                   reinterpret_cast<__half*>(out), B, H, W, C, s);
   return check_launch("s2d_gather_kernel");
 }
 

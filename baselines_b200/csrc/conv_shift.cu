@@ -174,12 +174,12 @@ conv_shift_fwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_cons
     uint32_t aph = 0;
     constexpr int G = (BN >= 64) ? 4 : BN / 16;       // 16-column chunks handled together (loads in flight)
     for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
-      const long long m = (long long)tile * SH_BM + ew * 32 + lane;
-      const int x = (int)(m % p.Wg);
-      const long long t2 = m / p.Wg;
-      const int y = (int)(t2 % p.Hg);
-      const int n = (int)(t2 / p.Hg);
-      const bool ok = (m < p.M) && (y < p.vy) && (x < p.vx);
+      const uint32_t m = (uint32_t)tile * SH_BM + ew * 32 + lane;       // M < 2^31 (checked on the host)
+      const uint32_t t2 = m / (uint32_t)p.Wg;
+      const int x = (int)(m - t2 * (uint32_t)p.Wg);
+      const int n = (int)(t2 / (uint32_t)p.Hg);
+      const int y = (int)(t2 - (uint32_t)n * (uint32_t)p.Hg);
+      const bool ok = ((long long)m < p.M) && (y < p.vy) && (x < p.vx);
       const long long obase = map_rowbase(p.omap, n, y, x);
       const long long sbase = p.saved ? map_rowbase(p.smap, n, y, x) : 0;
       const bool masked = p.dact && p.saved != nullptr;
@@ -241,6 +241,8 @@ conv_shift_fwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_cons
 
 // ------------------------------------------------------------------------------------------------ wgrad
 struct ShiftWgradParams {
+  float* gbias;            // optional: gbias[n] += alpha_b * sum_m dY[m, n]  (fused bias gradient)
+  float alpha_b;
   long long M;             // reduction rows = B*Hg*Wg
   int N;                   // dY channels
   int taps;
@@ -279,7 +281,7 @@ conv_shift_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_co
     tma_prefetch_desc(&tmD);
   }
   if (warp == 1 && lane == 0) {
-    for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+    for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], p.gbias ? 2 : 1); }
     mbar_init(done_bar, 1);
     fence_barrier_init();
   }
@@ -331,6 +333,36 @@ conv_shift_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_co
         if (++s == STAGES) { s = 0; ph ^= 1; }
       }
       umma_commit(done_bar);
+    }
+  } else if (warp == 3) {
+    // fused bias gradient: column sums of the dY tile while it sits in shared memory (swizzle undone by hand)
+    if (p.gbias != nullptr) {
+      float a0 = 0.0f, a1 = 0.0f;
+      const int cpair = lane;                                  // columns 2*lane, 2*lane+1 of this 64-wide chunk
+      const bool act = (2 * cpair) < (BN < 64 ? BN : 64);
+      int s = 0;
+      uint32_t ph = 0;
+      for (int kb = kb0; kb < kb1; ++kb) {
+        mbar_wait(&full_bar[s], ph);
+        const uint8_t* sb = smem + s * STAGE_BYTES + KH * SH_WABYTES;
+        if (act) {
+          const int chunk = (cpair * 4) >> 4, within = (cpair * 4) & 15;
+#pragma unroll 8
+          for (int r = 0; r < 64; ++r) {
+            const int sw = (BROWB == 128) ? (r & 7) : ((r >> 1) & 3);
+            const uint32_t w = *reinterpret_cast<const uint32_t*>(sb + r * BROWB + ((chunk ^ sw) << 4) + within);
+            a0 += __half2float(__ushort_as_half((unsigned short)(w & 0xffffu)));
+            a1 += __half2float(__ushort_as_half((unsigned short)(w >> 16)));
+          }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&empty_bar[s]);
+        if (++s == STAGES) { s = 0; ph ^= 1; }
+      }
+      if (act && kb1 > kb0) {
+        if (2 * cpair < p.N) atomicAdd(p.gbias + 2 * cpair, a0 * p.alpha_b);
+        if (2 * cpair + 1 < p.N) atomicAdd(p.gbias + 2 * cpair + 1, a1 * p.alpha_b);
+      }
     }
   } else if (warp >= 4) {
     const int ew = warp - 4;
@@ -427,6 +459,7 @@ int conv_shift_fwd_impl(const void* X, long long B, int Hg, int Wg, int C, const
   int lo = shifts[0], hi = shifts[0];
   for (int t = 1; t < taps; ++t) { lo = shifts[t] < lo ? shifts[t] : lo; hi = shifts[t] > hi ? shifts[t] : hi; }
   B200RL_REQUIRE(hi - lo <= SH_AROWS - SH_BM, "conv_shift_fwd: shift span %d too large", hi - lo);
+  B200RL_REQUIRE(B * Hg * Wg < (1LL << 31) - 4096, "conv_shift_fwd: too many rows");
   p.M = B * Hg * Wg; p.Hg = Hg; p.Wg = Wg; p.N = N; p.taps = taps; p.min_shift = lo;
   for (int t = 0; t < taps; ++t) p.shift[t] = shifts[t] - lo;
   p.vy = vy; p.vx = vx; p.out = reinterpret_cast<__half*>(out);
@@ -452,7 +485,8 @@ int conv_shift_fwd_impl(const void* X, long long B, int Hg, int Wg, int C, const
 
 // G[taps*C, N] (fp32, row pitch ldg) += alpha * sum_m X[m + shift_t, c] * dY[m, n]
 int conv_shift_wgrad_impl(const void* X, long long rows, int C, const void* dY, int N, int taps, const int* shifts,
-                          float* G, long long ldg, float alpha, int max_ctas, cudaStream_t stream) {
+                          float* G, long long ldg, float alpha, float* gbias, float alpha_b, int max_ctas,
+                          cudaStream_t stream) {
   B200RL_REQUIRE(X && dY && G && rows > 0, "conv_shift_wgrad: null operand");
   B200RL_REQUIRE(C == 64 || C == 128, "conv_shift_wgrad: C must be 64 or 128");
   B200RL_REQUIRE(N == 32 || N == 64, "conv_shift_wgrad: N must be 32 or 64 (got %d)", N);
@@ -467,6 +501,7 @@ int conv_shift_wgrad_impl(const void* X, long long rows, int C, const void* dY, 
     if (t > 0 && KH == 1) B200RL_REQUIRE(shifts[t] > shifts[t - 1], "conv_shift_wgrad: shifts must increase");
   }
   p.M = rows; p.N = N; p.taps = taps; p.G = G; p.ldg = ldg; p.alpha = alpha;
+  p.gbias = gbias; p.alpha_b = alpha_b;
   p.kb_total = (int)((rows + 63) / 64);
   int ctas = device_num_sms();
   if (max_ctas > 0 && max_ctas < ctas) ctas = max_ctas;

@@ -474,8 +474,7 @@ class Tower:
             rows = B * g["Hg"] * g["Wg"]
             xin = self.x16 if i == 0 else self.hconv[i - 1]
             ops.conv_shift_wgrad(xin, rows, g["Cg"], self.dY[i], c.nf, g["shifts"], c.gw, c.nf,
-                                 alpha=alpha * c.in_scale, tag="wgrad." + c.name)
-            ops.colsum(self.dY[i], c.gb, rows, c.nf, c.nf, alpha=alpha)
+                                 alpha=alpha * c.in_scale, tag="wgrad." + c.name, gbias=c.gb, alpha_b=alpha)
             if i == 0:
                 break
             # dX_i (= dY_{i-1} after the ReLU mask) as a shift-GEMM over dY_i with negative shifts

@@ -96,13 +96,14 @@ def conv_shift_fwd(X, B, Hg, Wg, C, W, ldw, N, shifts, vy, vx, out, omap, *, sav
               nbytes=2.0 * rows * C + 2.0 * rows * N)
 
 
-def conv_shift_wgrad(X, rows, C, dY, N, shifts, G, ldg, alpha=1.0, max_ctas=0, tag=None):
+def conv_shift_wgrad(X, rows, C, dY, N, shifts, G, ldg, alpha=1.0, max_ctas=0, tag=None, gbias=None, alpha_b=1.0):
     _chk(X, torch.float16, "X")
     _chk(dY, torch.float16, "dY")
     _chk(G, torch.float32, "G")
     sh = _iarr(shifts, _C.c_int)
+    _chk(gbias, torch.float32, "gbias")
     _lib.call("b200rl_conv_shift_wgrad", _ptr(X), int(rows), C, _ptr(dY), int(N), len(shifts), sh, _ptr(G), int(ldg),
-              float(alpha), int(max_ctas), _stream(), label="convs." + (tag or "wgrad"),
+              float(alpha), _ptr(gbias), float(alpha_b), int(max_ctas), _stream(), label="convs." + (tag or "wgrad"),
               flops=2.0 * rows * N * len(shifts) * C, nbytes=2.0 * rows * (C + N))
 
 

@@ -68,7 +68,8 @@ int b200rl_conv_shift_fwd(const void* X, long long B, int Hg, int Wg, int C, con
                           const void* saved, const long long* smap, const float* bias, int act, int dact, float alpha,
                           void* stream);
 int b200rl_conv_shift_wgrad(const void* X, long long rows, int C, const void* dY, int N, int taps, const int* shifts,
-                            float* G, long long ldg, float alpha, int max_ctas, void* stream);
+                            float* G, long long ldg, float alpha, float* gbias, float alpha_b, int max_ctas,
+                            void* stream);   /* gbias != NULL: gbias[n] += alpha_b * sum_m dY[m, n] (fused) */
 
 /* Implicit-GEMM convolution (tf.nn.conv2d a2c/utils.py:56 and its gradients): the A operand is read
  * straight from the NHWC fp16 activation x[B,H,W,C] by TMA im2col mode (C = 16, 32 or 64 channels per tap).

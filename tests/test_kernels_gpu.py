@@ -618,8 +618,11 @@ def test_conv_shift_forward_wgrad_dgrad(ops, name, B, Hg, Wg, C, R, N):
     dzv = (torch.randn(B, OH, OW, N, device="cuda") * 0.5).half()
     dz[:, :OH, :OW] = dzv
     G = torch.ones(K, N, dtype=torch.float32, device="cuda")
-    ops.conv_shift_wgrad(x, B * Hg * Wg, C, dz, N, shifts, G, N, alpha=0.5)
+    gb = torch.ones(N, dtype=torch.float32, device="cuda")
+    ops.conv_shift_wgrad(x, B * Hg * Wg, C, dz, N, shifts, G, N, alpha=0.5, gbias=gb, alpha_b=0.25)
     torch.cuda.synchronize()
+    want_gb = 1.0 + 0.25 * dzv.float().reshape(-1, N).sum(0)           # fused bias gradient
+    assert torch.allclose(gb, want_gb, atol=1e-2, rtol=1e-3), (name, "gbias", float((gb - want_gb).abs().max()))
     wantG = 1.0 + 0.5 * (P.t() @ dzv.float().reshape(-1, N))
     err = float((G - wantG).abs().max())
     assert torch.allclose(G, wantG, atol=3e-3 * (B * OH * OW) ** 0.5, rtol=3e-3), (name, "wgrad", err)
