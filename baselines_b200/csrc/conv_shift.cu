@@ -116,36 +116,43 @@ conv_shift_fwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_cons
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
+  // Role loops are warp-uniform; only the issue of the uniform-datapath instructions (TMA, tcgen05.mma,
+  // tcgen05.commit) is gated by elect.sync -- a data-dependent `if (lane == 0)` makes the compiler wrap every
+  // such instruction in an ELECT / BRA.U.ANY loop (~300 instructions per tile on the issuing thread).
   if (warp == 0) {
-    if (lane == 0) {
+    if (elect_one()) {
       mbar_arrive_expect_tx(w_bar, (uint32_t)(p.taps * KH) * W_SUB);
       for (int q = 0; q < p.taps * KH; ++q) tma_load_2d(wres + q * W_SUB, &tmW, w_bar, q * 64, 0);
-      int s = 0;
-      uint32_t ph = 0;
-      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
-        mbar_wait(&empty_bar[s], ph ^ 1);
+    }
+    __syncwarp();
+    int s = 0;
+    uint32_t ph = 0;
+    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+      mbar_wait(&empty_bar[s], ph ^ 1);
+      if (elect_one()) {
         uint8_t* sa = smem + s * STAGE_BYTES;
         mbar_arrive_expect_tx(&full_bar[s], (uint32_t)STAGE_BYTES);
         const int row0 = tile * SH_BM + p.min_shift;                  // may be negative: TMA zero-fills
 #pragma unroll
         for (int h = 0; h < KH; ++h) tma_load_2d(sa + h * SH_ABYTES, &tmX, &full_bar[s], h * 64, row0);
-        if (++s == STAGES) { s = 0; ph ^= 1; }
       }
+      __syncwarp();
+      if (++s == STAGES) { s = 0; ph ^= 1; }
     }
   } else if (warp == 1) {
     constexpr uint32_t IDESC = (1u << 4) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(SH_BM >> 4) << 24);
-    if (lane == 0) {
-      int s = 0, as = 0;
-      uint32_t ph = 0, aph = 0;
-      mbar_wait(w_bar, 0);
-      // descriptors differ only in their 14-bit start-address field: build the constant part once and add
-      // (byte offset >> 4) per MMA -- the single issuing thread is otherwise instruction bound for small N
-      const uint64_t desc_hi = make_sdesc(0, 16, 1024, 2u);
-      const uint32_t w_lo = (smem_u32(wres) & 0x3FFFFu) >> 4;
-      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
-        mbar_wait(&tempty_bar[as], aph ^ 1);
-        mbar_wait(&full_bar[s], ph);
-        tc_fence_after();
+    int s = 0, as = 0;
+    uint32_t ph = 0, aph = 0;
+    mbar_wait(w_bar, 0);
+    // descriptors differ only in their 14-bit start-address field: build the constant part once and add
+    // (byte offset >> 4) per MMA
+    const uint64_t desc_hi = make_sdesc(0, 16, 1024, 2u);
+    const uint32_t w_lo = (smem_u32(wres) & 0x3FFFFu) >> 4;
+    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+      mbar_wait(&tempty_bar[as], aph ^ 1);
+      mbar_wait(&full_bar[s], ph);
+      tc_fence_after();
+      if (elect_one()) {
         const uint32_t a_lo = (smem_u32(smem + s * STAGE_BYTES) & 0x3FFFFu) >> 4;
         const uint32_t tmem_d = tmem_base + (uint32_t)(as * BN);
         uint32_t acc = 0;
@@ -164,9 +171,10 @@ conv_shift_fwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_cons
         }
         umma_commit(&empty_bar[s]);
         umma_commit(&tfull_bar[as]);
-        if (++s == STAGES) { s = 0; ph ^= 1; }
-        if (++as == 2) { as = 0; aph ^= 1; }
       }
+      __syncwarp();
+      if (++s == STAGES) { s = 0; ph ^= 1; }
+      if (++as == 2) { as = 0; aph ^= 1; }
     }
   } else if (warp >= 4) {
     const int ew = warp - 4;
@@ -292,28 +300,30 @@ conv_shift_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_co
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
-    if (lane == 0) {
-      int s = 0;
-      uint32_t ph = 0;
-      for (int kb = kb0; kb < kb1; ++kb) {
-        mbar_wait(&empty_bar[s], ph ^ 1);
+    int s = 0;
+    uint32_t ph = 0;
+    for (int kb = kb0; kb < kb1; ++kb) {
+      mbar_wait(&empty_bar[s], ph ^ 1);
+      if (elect_one()) {
         uint8_t* sa = smem + s * STAGE_BYTES;
         mbar_arrive_expect_tx(&full_bar[s], (uint32_t)(KH * SH_WABYTES + B_BYTES));
 #pragma unroll
         for (int h = 0; h < KH; ++h) tma_load_2d(sa + h * SH_WABYTES, &tmX, &full_bar[s], h * 64, kb * 64);
         tma_load_2d(sa + KH * SH_WABYTES, &tmD, &full_bar[s], 0, kb * 64);
-        if (++s == STAGES) { s = 0; ph ^= 1; }
       }
+      __syncwarp();
+      if (++s == STAGES) { s = 0; ph ^= 1; }
     }
   } else if (warp == 1) {
     constexpr uint32_t IDESC = (1u << 4) | (1u << 15) | (1u << 16) | ((uint32_t)(BN >> 3) << 17) |
                                ((uint32_t)(SH_BM >> 4) << 24);
-    if (lane == 0) {
+    {
       int s = 0;
       uint32_t ph = 0;
       for (int kb = kb0; kb < kb1; ++kb) {
         mbar_wait(&full_bar[s], ph);
         tc_fence_after();
+        if (elect_one()) {
         const uint32_t a_addr = smem_u32(smem + s * STAGE_BYTES);
         const uint32_t b_addr = a_addr + KH * SH_WABYTES;
         const uint64_t bdesc0 = make_sdesc(b_addr, 64 * BROWB, 8 * BROWB, LAYOUT_B);
@@ -330,9 +340,11 @@ conv_shift_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_co
                      (kb > kb0 || k > 0) ? 1u : 0u);
         }
         umma_commit(&empty_bar[s]);
+        if (kb == kb1 - 1) umma_commit(done_bar);
+        }
+        __syncwarp();
         if (++s == STAGES) { s = 0; ph ^= 1; }
       }
-      umma_commit(done_bar);
     }
   } else if (warp == 3) {
     // fused bias gradient: column sums of the dY tile while it sits in shared memory (swizzle undone by hand)

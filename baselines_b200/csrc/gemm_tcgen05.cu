@@ -135,11 +135,12 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
-    if (lane == 0) {
-      if (BRES) {
+    {
+      if (BRES && elect_one()) {
         mbar_arrive_expect_tx(bres_bar, (uint32_t)p.cv.taps * B_SUB);
         for (int g = 0; g < p.cv.taps; ++g) tma_load_2d(bres + g * B_SUB, &tmB, bres_bar, g * CPT, 0);
       }
+      __syncwarp();
       int s = 0;
       uint32_t ph = 0;
       for (int work = blockIdx.x; work < total_work; work += gridDim.x) {
@@ -159,6 +160,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         }
         for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(&empty_bar[s], ph ^ 1);
+          if (elect_one()) {
           uint8_t* sa = smem + s * STAGE_BYTES;
           uint8_t* sb = sa + C_::A_BYTES;
           if (!MN_MAJOR) {
@@ -203,6 +205,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             for (int j = 0; j < BCHUNKS; ++j)
               tma_load_2d(sb + j * (BK * BROWB), &tmB, &full_bar[s], n_tile * BN + j * 64, kb * BK);
           }
+          }
+          __syncwarp();
           if (++s == STAGES) { s = 0; ph ^= 1; }
         }
       }
@@ -213,7 +217,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                                | (0u << 7) | (0u << 10)       // A, B = f16
                                | ((MN_MAJOR ? 1u : 0u) << 15) | ((MN_MAJOR ? 1u : 0u) << 16)
                                | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
-    if (lane == 0) {
+    {
       int s = 0;
       uint32_t ph = 0;
       int as = 0;
@@ -231,6 +235,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(&full_bar[s], ph);
           tc_fence_after();
+          if (elect_one()) {
           const uint32_t a_addr = smem_u32(smem + s * STAGE_BYTES);
           const uint32_t b_addr = BRES ? smem_u32(bres) + (uint32_t)(kb * TPS) * B_SUB : a_addr + C_::A_BYTES;
           if (!MN_MAJOR) {
@@ -257,9 +262,11 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             }
           }
           umma_commit(&empty_bar[s]);   // smem slot reusable once these MMAs retire
+          if (kb == kb1 - 1) umma_commit(&tfull_bar[as]);    // accumulator ready for the epilogue
+          }
+          __syncwarp();
           if (++s == STAGES) { s = 0; ph ^= 1; }
         }
-        umma_commit(&tfull_bar[as]);    // accumulator ready for the epilogue
         if (++as == 2) { as = 0; aph ^= 1; }
       }
     }
