@@ -349,31 +349,38 @@ conv_shift_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_co
   } else if (warp == 3) {
     // fused bias gradient: column sums of the dY tile while it sits in shared memory (swizzle undone by hand)
     if (p.gbias != nullptr) {
-      float a0 = 0.0f, a1 = 0.0f;
-      const int cpair = lane;                                  // columns 2*lane, 2*lane+1 of this 64-wide chunk
-      const bool act = (2 * cpair) < (BN < 64 ? BN : 64);
+      // lanes cover one 64-wide row with 8-byte loads (4 columns per lane); the remaining lanes take other rows
+      constexpr int LPR = BROWB / 8;                           // lanes per row: 16 (128 B rows) or 8 (64 B rows)
+      constexpr int RG = 32 / LPR;                             // row groups handled in parallel
+      const int cq = lane % LPR, rg = lane / LPR;              // column quad, row group
+      const int chunk = (cq * 8) >> 4, within = (cq * 8) & 15;
+      float a[4] = {0.f, 0.f, 0.f, 0.f};
       int s = 0;
       uint32_t ph = 0;
       for (int kb = kb0; kb < kb1; ++kb) {
         mbar_wait(&full_bar[s], ph);
         const uint8_t* sb = smem + s * STAGE_BYTES + KH * SH_WABYTES;
-        if (act) {
-          const int chunk = (cpair * 4) >> 4, within = (cpair * 4) & 15;
 #pragma unroll 8
-          for (int r = 0; r < 64; ++r) {
-            const int sw = (BROWB == 128) ? (r & 7) : ((r >> 1) & 3);
-            const uint32_t w = *reinterpret_cast<const uint32_t*>(sb + r * BROWB + ((chunk ^ sw) << 4) + within);
-            a0 += __half2float(__ushort_as_half((unsigned short)(w & 0xffffu)));
-            a1 += __half2float(__ushort_as_half((unsigned short)(w >> 16)));
-          }
+        for (int r = rg; r < 64; r += RG) {
+          const int sw = (BROWB == 128) ? (r & 7) : ((r >> 1) & 3);
+          const uint2 w = *reinterpret_cast<const uint2*>(sb + r * BROWB + ((chunk ^ sw) << 4) + within);
+          a[0] += __half2float(__ushort_as_half((unsigned short)(w.x & 0xffffu)));
+          a[1] += __half2float(__ushort_as_half((unsigned short)(w.x >> 16)));
+          a[2] += __half2float(__ushort_as_half((unsigned short)(w.y & 0xffffu)));
+          a[3] += __half2float(__ushort_as_half((unsigned short)(w.y >> 16)));
         }
         __syncwarp();
         if (lane == 0) mbar_arrive(&empty_bar[s]);
         if (++s == STAGES) { s = 0; ph ^= 1; }
       }
-      if (act && kb1 > kb0) {
-        if (2 * cpair < p.N) atomicAdd(p.gbias + 2 * cpair, a0 * p.alpha_b);
-        if (2 * cpair + 1 < p.N) atomicAdd(p.gbias + 2 * cpair + 1, a1 * p.alpha_b);
+#pragma unroll
+      for (int o = LPR; o < 32; o <<= 1)                       // fold the row groups together
+#pragma unroll
+        for (int i = 0; i < 4; ++i) a[i] += __shfl_xor_sync(0xffffffffu, a[i], o);
+      if (rg == 0 && kb1 > kb0) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+          if (4 * cq + i < p.N) atomicAdd(p.gbias + 4 * cq + i, a[i] * p.alpha_b);
       }
     }
   } else if (warp >= 4) {
