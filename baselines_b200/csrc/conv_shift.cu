@@ -78,7 +78,7 @@ struct ShiftParams {
 };
 
 // ------------------------------------------------------------------------------------------------ forward / dgrad
-template <int BN, int KH>
+template <int BN, int KH, bool DACT>
 __global__ void __launch_bounds__(SH_THREADS, 1)
 conv_shift_fwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW,
                       const __grid_constant__ ShiftParams p) {
@@ -190,19 +190,28 @@ conv_shift_fwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_cons
       const bool ok = ((long long)m < p.M) && (y < p.vy) && (x < p.vx);
       const long long obase = map_rowbase(p.omap, n, y, x);
       const long long sbase = p.saved ? map_rowbase(p.smap, n, y, x) : 0;
-      const bool masked = p.dact && p.saved != nullptr;
+      const bool masked = DACT && p.saved != nullptr;
+      // branch-free activation: relu(x) = max(x, 0), identity = max(x, -inf); relu'(h) = (h > 0), 1 = (h > -inf).
+      // (The epilogue is instruction-FETCH bound when its unrolled body outgrows the L0 / L1.5 I-caches, so it is
+      // kept small: no tanh here, no per-element mode switches.)
+      const float lo = (p.act == ACT_RELU) ? 0.0f : -INFINITY;
       mbar_wait(&tfull_bar[as], aph);
       tc_fence_after();
       const uint32_t taddr0 = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(as * BN);
 #pragma unroll 1
       for (int c0 = 0; c0 < BN; c0 += 16 * G) {
         uint4 sv[G][2];
-        if (masked && ok) {
+        if (DACT) {
+          if (masked && ok) {
 #pragma unroll
-          for (int j = 0; j < G; ++j) {
-            const __half* sp = p.saved + sbase + map_coloff(p.smap, c0 + 16 * j);
-            sv[j][0] = __ldg(reinterpret_cast<const uint4*>(sp));
-            sv[j][1] = __ldg(reinterpret_cast<const uint4*>(sp) + 1);
+            for (int j = 0; j < G; ++j) {
+              const __half* sp = p.saved + sbase + map_coloff(p.smap, c0 + 16 * j);
+              sv[j][0] = __ldg(reinterpret_cast<const uint4*>(sp));
+              sv[j][1] = __ldg(reinterpret_cast<const uint4*>(sp) + 1);
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < G; ++j) sv[j][0] = sv[j][1] = make_uint4(0x3c003c00u, 0x3c003c00u, 0x3c003c00u, 0x3c003c00u);
           }
         }
         uint32_t r[G][16];
@@ -213,24 +222,30 @@ conv_shift_fwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_cons
 #pragma unroll
           for (int j = 0; j < G; ++j) {
             const int c = c0 + 16 * j;
-            float v[16];
+            uint32_t packed[8];
+            if (DACT) {
+              const uint32_t w[8] = {sv[j][0].x, sv[j][0].y, sv[j][0].z, sv[j][0].w,
+                                     sv[j][1].x, sv[j][1].y, sv[j][1].z, sv[j][1].w};
 #pragma unroll
-            for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[j][i]) * p.alpha;
-            if (p.dact) {
-              if (masked) {
-                const uint32_t w[8] = {sv[j][0].x, sv[j][0].y, sv[j][0].z, sv[j][0].w,
-                                       sv[j][1].x, sv[j][1].y, sv[j][1].z, sv[j][1].w};
-#pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                  v[2 * i] *= act_grad_from_saved(__half2float(__ushort_as_half((unsigned short)(w[i] & 0xffffu))), p.act);
-                  v[2 * i + 1] *= act_grad_from_saved(__half2float(__ushort_as_half((unsigned short)(w[i] >> 16))), p.act);
-                }
+              for (int i = 0; i < 8; ++i) {
+                const float2 h = __half22float2(*reinterpret_cast<const __half2*>(&w[i]));
+                const float a = (h.x > lo) ? __uint_as_float(r[j][2 * i]) * p.alpha : 0.0f;
+                const float b = (h.y > lo) ? __uint_as_float(r[j][2 * i + 1]) * p.alpha : 0.0f;
+                const __half2 o = __floats2half2_rn(a, b);
+                packed[i] = *reinterpret_cast<const uint32_t*>(&o);
               }
             } else {
 #pragma unroll
-              for (int i = 0; i < 16; ++i) v[i] = apply_act(v[i] + s_bias[c + i], p.act);
+              for (int i = 0; i < 8; ++i) {
+                const float a = fmaxf(fmaf(__uint_as_float(r[j][2 * i]), p.alpha, s_bias[c + 2 * i]), lo);
+                const float b = fmaxf(fmaf(__uint_as_float(r[j][2 * i + 1]), p.alpha, s_bias[c + 2 * i + 1]), lo);
+                const __half2 o = __floats2half2_rn(a, b);
+                packed[i] = *reinterpret_cast<const uint32_t*>(&o);
+              }
             }
-            store16_f16(v, p.out + obase + map_coloff(p.omap, c), true, 16);
+            uint4* dst = reinterpret_cast<uint4*>(p.out + obase + map_coloff(p.omap, c));
+            dst[0] = make_uint4(packed[0], packed[1], packed[2], packed[3]);
+            dst[1] = make_uint4(packed[4], packed[5], packed[6], packed[7]);
           }
         }
       }
@@ -415,12 +430,12 @@ conv_shift_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_co
 }
 
 // ------------------------------------------------------------------------------------------------ host
-template <int BN, int KH>
+template <int BN, int KH, bool DACT>
 static int launch_fwd(const CUtensorMap& tmX, const CUtensorMap& tmW, const ShiftParams& p, cudaStream_t st) {
   constexpr int STAGES = (KH == 1) ? 6 : 3;
   constexpr int SMEM = STAGES * KH * SH_ABYTES + 80 * 1024 + 1024 + 256;
   static bool attr = false;
-  auto kern = conv_shift_fwd_kernel<BN, KH>;
+  auto kern = conv_shift_fwd_kernel<BN, KH, DACT>;
   if (!attr) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
     if (e != cudaSuccess) {
@@ -493,8 +508,12 @@ int conv_shift_fwd_impl(const void* X, long long B, int Hg, int Wg, int C, const
   if ((rc = make_tmap_2d_f16(&tmX, X, p.M, C, C, 64, SH_AROWS)) != 0) return rc;
   if ((rc = make_tmap_2d_f16(&tmW, W, N, (long long)taps * C, ldw, 64, N)) != 0) return rc;
   const int KH = C / 64;
-#define SHIFT_FWD_CASE(bn)                                                                      \
-  if (N == bn) return KH == 1 ? launch_fwd<bn, 1>(tmX, tmW, p, stream) : launch_fwd<bn, 2>(tmX, tmW, p, stream);
+  B200RL_REQUIRE(act == ACT_NONE || act == ACT_RELU, "conv_shift_fwd: activation must be none or relu");
+#define SHIFT_FWD_CASE(bn)                                                                                    \
+  if (N == bn) {                                                                                              \
+    if (dact) return KH == 1 ? launch_fwd<bn, 1, true>(tmX, tmW, p, stream) : launch_fwd<bn, 2, true>(tmX, tmW, p, stream); \
+    return KH == 1 ? launch_fwd<bn, 1, false>(tmX, tmW, p, stream) : launch_fwd<bn, 2, false>(tmX, tmW, p, stream);        \
+  }
   SHIFT_FWD_CASE(32)
   SHIFT_FWD_CASE(64)
   SHIFT_FWD_CASE(128)
