@@ -87,5 +87,6 @@ def run(only=None, quick=False):
 if __name__ == "__main__":
     ap = argparse.ArgumentParser()
     ap.add_argument("--only", default=None)
+    ap.add_argument("--quick", action="store_true", help="fc1 at M=131072 only")
     a = ap.parse_args()
-    print(json.dumps(run(a.only)))
+    print(json.dumps(run(a.only, a.quick)))
