@@ -40,15 +40,43 @@ tree_set_kernel(double* __restrict__ sum_tree, double* __restrict__ min_tree, lo
   }
 }
 
-// same top-down decomposition (hence the same association of additions) as segment_tree.py:36-49
+// Range sum with the SAME association of additions as the reference's recursive top-down decomposition
+// (segment_tree.py:36-49), evaluated iteratively (device recursion overflowed the stack at capacity 2^20):
+//   * descend to the node where the range splits;
+//   * the left part is a right-aligned range  -> ((innermost + v) + v) ...   (complete right siblings outward)
+//   * the right part is a left-aligned range  -> v + (v + (... innermost))   (complete left siblings outward)
+__device__ double fold_left_aligned(const double* v, long long hi, long long node, long long nlo, long long nhi) {
+  double st[48];
+  int n = 0;
+  while (hi != nhi) {
+    const long long mid = (nlo + nhi) / 2;
+    if (hi <= mid) { node = 2 * node; nhi = mid; }
+    else { st[n++] = v[2 * node]; node = 2 * node + 1; nlo = mid + 1; }
+  }
+  double acc = v[node];
+  while (n > 0) acc = __dadd_rn(st[--n], acc);
+  return acc;
+}
+__device__ double fold_right_aligned(const double* v, long long lo, long long node, long long nlo, long long nhi) {
+  double st[48];
+  int n = 0;
+  while (lo != nlo) {
+    const long long mid = (nlo + nhi) / 2;
+    if (mid + 1 <= lo) { node = 2 * node + 1; nlo = mid + 1; }
+    else { st[n++] = v[2 * node + 1]; node = 2 * node; nhi = mid; }
+  }
+  double acc = v[node];
+  while (n > 0) acc = __dadd_rn(acc, st[--n]);
+  return acc;
+}
 __device__ double fold_sum(const double* v, long long lo, long long hi, long long node, long long nlo, long long nhi) {
   while (true) {
     if (lo == nlo && hi == nhi) return v[node];
     const long long mid = (nlo + nhi) / 2;
     if (hi <= mid) { node = 2 * node; nhi = mid; continue; }
     if (mid + 1 <= lo) { node = 2 * node + 1; nlo = mid + 1; continue; }
-    const double l = fold_sum(v, lo, mid, 2 * node, nlo, mid);
-    const double r = fold_sum(v, mid + 1, hi, 2 * node + 1, mid + 1, nhi);
+    const double l = fold_right_aligned(v, lo, 2 * node, nlo, mid);
+    const double r = fold_left_aligned(v, hi, 2 * node + 1, mid + 1, nhi);
     return __dadd_rn(l, r);
   }
 }
