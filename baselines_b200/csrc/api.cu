@@ -20,9 +20,9 @@ int gemm_f16_impl(const void*, const void*, void*, const float*, const void*, in
                   long long, long long, int, int, int, float, int, int, int, int, int, cudaStream_t);
 int conv_shift_fwd_impl(const void*, long long, int, int, int, const void*, long long, int, int, const int*, int, int,
                         void*, const long long*, const void*, const long long*, const float*, int, int, float,
-                        cudaStream_t);
+                        const void*, const long long*, int, int, int, int, cudaStream_t);
 int conv_shift_wgrad_impl(const void*, long long, int, const void*, int, int, const int*, float*, long long, float,
-                          float*, float, int, cudaStream_t);
+                          float*, float, int, const void*, const long long*, int, int, int, int, cudaStream_t);
 int conv_gemm_impl(const void*, long long, int, int, int, int, int, int, int, int, int, int, int, const void*,
                    long long, void*, long long, const float*, const void*, long long, int, int, int, int, float, int,
                    int, int, int, int, cudaStream_t);
@@ -89,14 +89,17 @@ int b200rl_gemm_f16(const void* A, const void* B, void* C, const float* bias, co
 int b200rl_conv_shift_fwd(const void* X, long long B, int Hg, int Wg, int C, const void* W, long long ldw, int N,
                           int taps, const int* shifts, int vy, int vx, void* out, const long long* omap,
                           const void* saved, const long long* smap, const float* bias, int act, int dact, float alpha,
+                          const void* u8_x, const long long* u8_idx, int u8_H, int u8_W, int u8_C, int u8_s,
                           void* stream) {
   return conv_shift_fwd_impl(X, B, Hg, Wg, C, W, ldw, N, taps, shifts, vy, vx, out, omap, saved, smap, bias, act, dact,
-                             alpha, S(stream));
+                             alpha, u8_x, u8_idx, u8_H, u8_W, u8_C, u8_s, S(stream));
 }
 int b200rl_conv_shift_wgrad(const void* X, long long rows, int C, const void* dY, int N, int taps, const int* shifts,
                             float* G, long long ldg, float alpha, float* gbias, float alpha_b, int max_ctas,
+                            const void* u8_x, const long long* u8_idx, int u8_H, int u8_W, int u8_C, int u8_s,
                             void* stream) {
-  return conv_shift_wgrad_impl(X, rows, C, dY, N, taps, shifts, G, ldg, alpha, gbias, alpha_b, max_ctas, S(stream));
+  return conv_shift_wgrad_impl(X, rows, C, dY, N, taps, shifts, G, ldg, alpha, gbias, alpha_b, max_ctas, u8_x, u8_idx,
+                               u8_H, u8_W, u8_C, u8_s, S(stream));
 }
 
 int b200rl_conv_gemm(const void* x, long long B, int H, int W, int C, int R, int S, int stride_h, int stride_w,

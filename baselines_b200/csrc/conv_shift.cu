@@ -59,7 +59,135 @@ __device__ __forceinline__ long long map_coloff(const AddrMap& a, int col) {
   return col;
 }
 
+// Optional fused source for the FIRST conv layer: uint8 NHWC images gathered through src_idx.  Producer warps
+// build the space-to-depth fp16 A tile directly in shared memory (tf.cast of models.py:19 and arr[mbinds] of
+// ppo2.py:165 fused into the first load): grid row (n, Y, X) = 64 channels (dy, dx, c) = s segments of s*C bytes.
+struct U8Src {
+  const uint8_t* x;        // nullptr: A tiles come from the fp16 matrix through TMA
+  const long long* idx;    // sample gather (may be null)
+  int H, W, C, s;          // image geometry and space-to-depth factor (s*C == 16, s*s*C == 64)
+  int Hg, Wg;
+};
+
+static constexpr int U8_WARPS = 8;
+static constexpr int U8_THREADS = U8_WARPS * 32;
+
+// 16 uint8 -> 16 fp16 (exact): bytes are spliced into 0x64xx (= 1024 + b) and 1024 is subtracted
+__device__ __forceinline__ void u8x16_to_f16(const uint4& q, uint4& lo, uint4& hi) {
+  const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+  uint32_t o[8];
+  const __half2 k1024 = __floats2half2_rn(1024.0f, 1024.0f);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const uint32_t a = __byte_perm(w[i], 0x64646464u, 0x5140);
+    const uint32_t b = __byte_perm(w[i], 0x64646464u, 0x5342);
+    const __half2 ha = __hsub2(*reinterpret_cast<const __half2*>(&a), k1024);
+    const __half2 hb = __hsub2(*reinterpret_cast<const __half2*>(&b), k1024);
+    o[2 * i] = *reinterpret_cast<const uint32_t*>(&ha);
+    o[2 * i + 1] = *reinterpret_cast<const uint32_t*>(&hb);
+  }
+  lo = make_uint4(o[0], o[1], o[2], o[3]);
+  hi = make_uint4(o[4], o[5], o[6], o[7]);
+}
+
+// cp.async (LDGSTS) with zero fill: src_bytes = 0 writes 16 zero bytes
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc, int src_bytes) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_u32(smem_dst)), "l"(gsrc), "r"(src_bytes)
+               : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+// Producer work unit = 32 consecutive grid rows of one tile (one warp, lane = row): the raw 4 x 16 uint8 segments of
+// a row are staged with cp.async into a per-warp ring (U8_DEPTH units in flight, no registers held; the lane that
+// staged bytes reads them back, so the ring needs no cross-thread synchronisation), then cast and written into the
+// 128B-swizzled fp16 tile.  Units are dealt round-robin to the U8_WARPS producer warps across tiles.
+static constexpr int U8_DEPTH = 4;
+static constexpr int U8_UNIT_BYTES = 32 * 64;
+static constexpr int U8_RING_BYTES = U8_WARPS * U8_DEPTH * U8_UNIT_BYTES;     // 64 KB
+
+struct U8Unit {
+  long long sb;            // sample index of this lane's row in the NEXT unit to issue (-1: out of range -> zeros)
+  __device__ __forceinline__ void lookup(const U8Src& u, long long m, long long M) {
+    sb = -1;
+    if (m >= 0 && m < M) {
+      const uint32_t n = (uint32_t)m / (uint32_t)(u.Hg * u.Wg);
+      sb = u.idx ? __ldg(u.idx + n) : (long long)n;
+    }
+  }
+  __device__ __forceinline__ void issue(const U8Src& u, long long m, uint8_t* slot, int lane) const {
+    const uint8_t* src = u.x;
+    int sz = 0;
+    long long rowstride = 0;
+    if (sb >= 0) {
+      const uint32_t mm = (uint32_t)m, per = (uint32_t)(u.Hg * u.Wg);
+      const uint32_t rem = mm - (mm / per) * per;
+      const uint32_t Y = rem / (uint32_t)u.Wg, X = rem - Y * (uint32_t)u.Wg;
+      rowstride = (long long)u.W * u.C;
+      src += ((sb * u.H + (long long)(u.s * Y)) * u.W + (long long)u.s * X) * u.C;
+      sz = 16;
+    }
+#pragma unroll
+    for (int dy = 0; dy < 4; ++dy) cp_async16(slot + dy * 512 + lane * 16, src + dy * rowstride, sz);
+  }
+  // rows32 = first of the unit's 32 tile rows (a multiple of 8 rows, so the swizzle phase is lane & 7)
+  __device__ __forceinline__ void convert(const uint8_t* slot, uint8_t* rows32, int lane) const {
+    uint8_t* rowp = rows32 + lane * 128;
+    const int sw = lane & 7;
+#pragma unroll
+    for (int dy = 0; dy < 4; ++dy) {
+      uint4 lo, hi;
+      u8x16_to_f16(*reinterpret_cast<const uint4*>(slot + dy * 512 + lane * 16), lo, hi);
+      *reinterpret_cast<uint4*>(rowp + (((2 * dy) ^ sw) << 4)) = lo;
+      *reinterpret_cast<uint4*>(rowp + (((2 * dy + 1) ^ sw) << 4)) = hi;
+    }
+  }
+};
+
+// The producer-warp loop shared by forward and wgrad.  Tile `seq` (0-based, local to this CTA) starts at grid row
+// row0(seq) and occupies pipeline stage seq % STAGES; it has RB = NROWS/32 units.
+template <int NROWS, int STAGES, typename Row0>
+__device__ __forceinline__ void u8_producer_loop(const U8Src& u, long long M, int ntiles, Row0 row0, uint8_t* stages,
+                                                 int stage_bytes, uint64_t* full_bar, uint64_t* empty_bar,
+                                                 uint8_t* ring_base, int pw, int lane) {
+  constexpr int RB = NROWS / 32;
+  static_assert(NROWS % 32 == 0, "unit = 32 rows");
+  uint8_t* ring = ring_base + pw * (U8_DEPTH * U8_UNIT_BYTES);
+  const int total = ntiles * RB;
+  U8Unit t;
+  auto row_of = [&](int unit) { return row0(unit / RB) + (unit % RB) * 32 + lane; };
+  int ui = pw;
+  t.lookup(u, row_of(ui), ui < total ? M : 0);
+#pragma unroll
+  for (int d = 0; d < U8_DEPTH; ++d) {
+    if (ui < total) t.issue(u, row_of(ui), ring + d * U8_UNIT_BYTES, lane);
+    cp_async_commit();
+    ui += U8_WARPS;
+    t.lookup(u, row_of(ui), ui < total ? M : 0);
+  }
+  int d = 0;
+  for (int uc = pw; uc < total; uc += U8_WARPS) {
+    const int seq = uc / RB, rb = uc - seq * RB;
+    const int s = seq % STAGES;
+    const uint32_t ph = (uint32_t)(seq / STAGES) & 1u;
+    cp_async_wait<U8_DEPTH - 1>();
+    mbar_wait(&empty_bar[s], ph ^ 1);
+    t.convert(ring + d * U8_UNIT_BYTES, stages + s * stage_bytes + rb * (32 * 128), lane);
+    fence_proxy_async_smem();                           // generic-proxy writes -> visible to the tensor core
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&full_bar[s]);
+    if (ui < total) t.issue(u, row_of(ui), ring + d * U8_UNIT_BYTES, lane);
+    cp_async_commit();
+    ui += U8_WARPS;
+    t.lookup(u, row_of(ui), ui < total ? M : 0);
+    if (++d == U8_DEPTH) d = 0;
+  }
+  cp_async_wait<0>();
+}
+
 struct ShiftParams {
+  U8Src u8;
   long long M;             // grid rows = B*Hg*Wg
   int Hg, Wg;              // grid
   int N;                   // output channels of the GEMM
@@ -78,8 +206,8 @@ struct ShiftParams {
 };
 
 // ------------------------------------------------------------------------------------------------ forward / dgrad
-template <int BN, int KH, bool DACT>
-__global__ void __launch_bounds__(SH_THREADS, 1)
+template <int BN, int KH, bool DACT, bool U8>
+__global__ void __launch_bounds__(SH_THREADS + (U8 ? U8_THREADS : 0), 1)
 conv_shift_fwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW,
                       const __grid_constant__ ShiftParams p) {
   constexpr int STAGE_BYTES = KH * SH_ABYTES;
@@ -105,7 +233,7 @@ conv_shift_fwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_cons
     tma_prefetch_desc(&tmW);
   }
   if (warp == 1 && lane == 0) {
-    for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+    for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], U8 ? SH_AROWS / 32 : 1); mbar_init(&empty_bar[s], 1); }
     for (int s = 0; s < 2; ++s) { mbar_init(&tfull_bar[s], 1); mbar_init(&tempty_bar[s], 128); }
     mbar_init(w_bar, 1);
     fence_barrier_init();
@@ -127,18 +255,28 @@ conv_shift_fwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_cons
     __syncwarp();
     int s = 0;
     uint32_t ph = 0;
-    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
-      mbar_wait(&empty_bar[s], ph ^ 1);
-      if (elect_one()) {
-        uint8_t* sa = smem + s * STAGE_BYTES;
-        mbar_arrive_expect_tx(&full_bar[s], (uint32_t)STAGE_BYTES);
-        const int row0 = tile * SH_BM + p.min_shift;                  // may be negative: TMA zero-fills
+    if (!U8) {
+      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+        mbar_wait(&empty_bar[s], ph ^ 1);
+        if (elect_one()) {
+          uint8_t* sa = smem + s * STAGE_BYTES;
+          mbar_arrive_expect_tx(&full_bar[s], (uint32_t)STAGE_BYTES);
+          const int row0 = tile * SH_BM + p.min_shift;                  // may be negative: TMA zero-fills
 #pragma unroll
-        for (int h = 0; h < KH; ++h) tma_load_2d(sa + h * SH_ABYTES, &tmX, &full_bar[s], h * 64, row0);
+          for (int h = 0; h < KH; ++h) tma_load_2d(sa + h * SH_ABYTES, &tmX, &full_bar[s], h * 64, row0);
+        }
+        __syncwarp();
+        if (++s == STAGES) { s = 0; ph ^= 1; }
       }
-      __syncwarp();
-      if (++s == STAGES) { s = 0; ph ^= 1; }
     }
+  } else if (U8 && warp >= 8) {
+    // uint8 producer warps (the cp.async ring lives in the unused 64 KB of the weight area)
+    const int step = gridDim.x, first = blockIdx.x;
+    const int ntiles = first < p.num_tiles ? (p.num_tiles - first + step - 1) / step : 0;
+    const int min_shift = p.min_shift;
+    u8_producer_loop<SH_AROWS, STAGES>(
+        p.u8, p.M, ntiles, [=](int seq) { return (long long)(first + seq * step) * SH_BM + min_shift; }, smem,
+        STAGE_BYTES, full_bar, empty_bar, wres + 16384, warp - 8, lane);
   } else if (warp == 1) {
     constexpr uint32_t IDESC = (1u << 4) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(SH_BM >> 4) << 24);
     int s = 0, as = 0;
@@ -176,7 +314,7 @@ conv_shift_fwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_cons
       if (++s == STAGES) { s = 0; ph ^= 1; }
       if (++as == 2) { as = 0; aph ^= 1; }
     }
-  } else if (warp >= 4) {
+  } else if (warp >= 4 && warp < 8) {
     const int ew = warp - 4;
     int as = 0;
     uint32_t aph = 0;
@@ -264,6 +402,7 @@ conv_shift_fwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_cons
 
 // ------------------------------------------------------------------------------------------------ wgrad
 struct ShiftWgradParams {
+  U8Src u8;
   float* gbias;            // optional: gbias[n] += alpha_b * sum_m dY[m, n]  (fused bias gradient)
   float alpha_b;
   long long M;             // reduction rows = B*Hg*Wg
@@ -276,8 +415,8 @@ struct ShiftWgradParams {
   int kb_total, kb_per_cta;
 };
 
-template <int BN, int KH>
-__global__ void __launch_bounds__(SH_THREADS, 1)
+template <int BN, int KH, bool U8>
+__global__ void __launch_bounds__(SH_THREADS + (U8 ? U8_THREADS : 0), 1)
 conv_shift_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmD,
                         const __grid_constant__ ShiftWgradParams p) {
   constexpr int BROWB = (BN >= 64) ? 128 : BN * 2;            // dY row bytes in smem
@@ -304,7 +443,10 @@ conv_shift_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_co
     tma_prefetch_desc(&tmD);
   }
   if (warp == 1 && lane == 0) {
-    for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], p.gbias ? 2 : 1); }
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full_bar[s], U8 ? 1 + SH_WROWS_K / 32 : 1);
+      mbar_init(&empty_bar[s], p.gbias ? 2 : 1);
+    }
     mbar_init(done_bar, 1);
     fence_barrier_init();
   }
@@ -321,14 +463,20 @@ conv_shift_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_co
       mbar_wait(&empty_bar[s], ph ^ 1);
       if (elect_one()) {
         uint8_t* sa = smem + s * STAGE_BYTES;
-        mbar_arrive_expect_tx(&full_bar[s], (uint32_t)(KH * SH_WABYTES + B_BYTES));
+        mbar_arrive_expect_tx(&full_bar[s], (uint32_t)((U8 ? 0 : KH * SH_WABYTES) + B_BYTES));
+        if (!U8) {
 #pragma unroll
-        for (int h = 0; h < KH; ++h) tma_load_2d(sa + h * SH_WABYTES, &tmX, &full_bar[s], h * 64, kb * 64);
+          for (int h = 0; h < KH; ++h) tma_load_2d(sa + h * SH_WABYTES, &tmX, &full_bar[s], h * 64, kb * 64);
+        }
         tma_load_2d(sa + KH * SH_WABYTES, &tmD, &full_bar[s], 0, kb * 64);
       }
       __syncwarp();
       if (++s == STAGES) { s = 0; ph ^= 1; }
     }
+  } else if (U8 && warp >= 8) {
+    u8_producer_loop<SH_WROWS_K, STAGES>(
+        p.u8, p.M, kb1 - kb0, [=](int seq) { return (long long)(kb0 + seq) * 64; }, smem, STAGE_BYTES, full_bar,
+        empty_bar, smem + STAGES * STAGE_BYTES + 256, warp - 8, lane);
   } else if (warp == 1) {
     constexpr uint32_t IDESC = (1u << 4) | (1u << 15) | (1u << 16) | ((uint32_t)(BN >> 3) << 17) |
                                ((uint32_t)(SH_BM >> 4) << 24);
@@ -398,7 +546,7 @@ conv_shift_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_co
           if (4 * cq + i < p.N) atomicAdd(p.gbias + 4 * cq + i, a[i] * p.alpha_b);
       }
     }
-  } else if (warp >= 4) {
+  } else if (warp >= 4 && warp < 8) {
     const int ew = warp - 4;
     if (kb1 > kb0) {
       mbar_wait(done_bar, 0);
@@ -430,12 +578,12 @@ conv_shift_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_co
 }
 
 // ------------------------------------------------------------------------------------------------ host
-template <int BN, int KH, bool DACT>
+template <int BN, int KH, bool DACT, bool U8 = false>
 static int launch_fwd(const CUtensorMap& tmX, const CUtensorMap& tmW, const ShiftParams& p, cudaStream_t st) {
   constexpr int STAGES = (KH == 1) ? 6 : 3;
   constexpr int SMEM = STAGES * KH * SH_ABYTES + 80 * 1024 + 1024 + 256;
   static bool attr = false;
-  auto kern = conv_shift_fwd_kernel<BN, KH, DACT>;
+  auto kern = conv_shift_fwd_kernel<BN, KH, DACT, U8>;
   if (!attr) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
     if (e != cudaSuccess) {
@@ -445,17 +593,18 @@ static int launch_fwd(const CUtensorMap& tmX, const CUtensorMap& tmW, const Shif
     attr = true;
   }
   const int grid = p.num_tiles < device_num_sms() ? p.num_tiles : device_num_sms();
-  kern<<<grid, SH_THREADS, SMEM, st>>>(tmX, tmW, p);
+  kern<<<grid, SH_THREADS + (U8 ? U8_THREADS : 0), SMEM, st>>>(tmX, tmW, p);
   return check_launch("conv_shift_fwd_kernel");
 }
 
-template <int BN, int KH>
+template <int BN, int KH, bool U8 = false>
 static int launch_wgrad(const CUtensorMap& tmX, const CUtensorMap& tmD, const ShiftWgradParams& p, int grid,
                         cudaStream_t st) {
   constexpr int STAGES = (KH == 1) ? 8 : 6;
-  constexpr int SMEM = STAGES * (KH * SH_WABYTES + 8192) + 1024 + 256;
+  constexpr int SMEM = STAGES * (KH * SH_WABYTES + 8192) + 1024 + 256 +
+                       (U8 ? U8_RING_BYTES : 0);
   static bool attr = false;
-  auto kern = conv_shift_wgrad_kernel<BN, KH>;
+  auto kern = conv_shift_wgrad_kernel<BN, KH, U8>;
   if (!attr) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
     if (e != cudaSuccess) {
@@ -464,7 +613,7 @@ static int launch_wgrad(const CUtensorMap& tmX, const CUtensorMap& tmD, const Sh
     }
     attr = true;
   }
-  kern<<<grid, SH_THREADS, SMEM, st>>>(tmX, tmD, p);
+  kern<<<grid, SH_THREADS + (U8 ? U8_THREADS : 0), SMEM, st>>>(tmX, tmD, p);
   return check_launch("conv_shift_wgrad_kernel");
 }
 
@@ -483,8 +632,14 @@ static bool fill_map(AddrMap& a, const long long* m) {       // {mode, sN, sY, s
 int conv_shift_fwd_impl(const void* X, long long B, int Hg, int Wg, int C, const void* W, long long ldw, int N,
                         int taps, const int* shifts, int vy, int vx, void* out, const long long* omap,
                         const void* saved, const long long* smap, const float* bias, int act, int dact, float alpha,
+                        const void* u8_x, const long long* u8_idx, int u8_H, int u8_W, int u8_C, int u8_s,
                         cudaStream_t stream) {
-  B200RL_REQUIRE(X && W && out && omap && B > 0, "conv_shift_fwd: null operand");
+  B200RL_REQUIRE((X || u8_x) && W && out && omap && B > 0, "conv_shift_fwd: null operand");
+  if (u8_x) {
+    B200RL_REQUIRE(C == 64 && u8_s * u8_C == 16 && u8_s == 4 && u8_H == Hg * u8_s && u8_W == Wg * u8_s && !dact &&
+                       N == 32 && (reinterpret_cast<uintptr_t>(u8_x) & 15) == 0 && (u8_W * u8_C) % 16 == 0,
+                   "conv_shift_fwd: fused uint8 source needs s=4, s*C=16, N=32, 16 B aligned rows");
+  }
   B200RL_REQUIRE(C == 64 || C == 128, "conv_shift_fwd: C must be 64 or 128 (got %d)", C);
   B200RL_REQUIRE(N == 32 || N == 64 || N == 128, "conv_shift_fwd: N must be 32, 64 or 128 (got %d)", N);
   B200RL_REQUIRE(taps >= 1 && taps <= SH_MAX_TAPS, "conv_shift_fwd: 1..%d taps", SH_MAX_TAPS);
@@ -503,8 +658,14 @@ int conv_shift_fwd_impl(const void* X, long long B, int Hg, int Wg, int C, const
   B200RL_REQUIRE(!(saved && !smap), "conv_shift_fwd: saved needs smap");
   p.bias = bias; p.act = act; p.dact = dact; p.alpha = alpha;
   p.num_tiles = (int)((p.M + SH_BM - 1) / SH_BM);
+  p.u8.x = reinterpret_cast<const uint8_t*>(u8_x); p.u8.idx = u8_idx; p.u8.H = u8_H; p.u8.W = u8_W; p.u8.C = u8_C;
+  p.u8.s = u8_s; p.u8.Hg = Hg; p.u8.Wg = Wg;
   CUtensorMap tmX, tmW;
   int rc;
+  if (u8_x) {
+    if ((rc = make_tmap_2d_f16(&tmW, W, N, (long long)taps * C, ldw, 64, N)) != 0) return rc;
+    return launch_fwd<32, 1, false, true>(tmW, tmW, p, stream);      // tmX unused: A tiles come from the producers
+  }
   if ((rc = make_tmap_2d_f16(&tmX, X, p.M, C, C, 64, SH_AROWS)) != 0) return rc;
   if ((rc = make_tmap_2d_f16(&tmW, W, N, (long long)taps * C, ldw, 64, N)) != 0) return rc;
   const int KH = C / 64;
@@ -524,8 +685,13 @@ int conv_shift_fwd_impl(const void* X, long long B, int Hg, int Wg, int C, const
 // G[taps*C, N] (fp32, row pitch ldg) += alpha * sum_m X[m + shift_t, c] * dY[m, n]
 int conv_shift_wgrad_impl(const void* X, long long rows, int C, const void* dY, int N, int taps, const int* shifts,
                           float* G, long long ldg, float alpha, float* gbias, float alpha_b, int max_ctas,
+                          const void* u8_x, const long long* u8_idx, int u8_H, int u8_W, int u8_C, int u8_s,
                           cudaStream_t stream) {
-  B200RL_REQUIRE(X && dY && G && rows > 0, "conv_shift_wgrad: null operand");
+  B200RL_REQUIRE((X || u8_x) && dY && G && rows > 0, "conv_shift_wgrad: null operand");
+  if (u8_x)
+    B200RL_REQUIRE(C == 64 && u8_s == 4 && u8_s * u8_C == 16 && N == 32 && u8_H % 4 == 0 && u8_W % 4 == 0 &&
+                       (reinterpret_cast<uintptr_t>(u8_x) & 15) == 0,
+                   "conv_shift_wgrad: fused uint8 source needs s=4, s*C=16, N=32");
   B200RL_REQUIRE(C == 64 || C == 128, "conv_shift_wgrad: C must be 64 or 128");
   B200RL_REQUIRE(N == 32 || N == 64, "conv_shift_wgrad: N must be 32 or 64 (got %d)", N);
   B200RL_REQUIRE(taps >= 1 && taps <= SH_MAX_TAPS, "conv_shift_wgrad: 1..%d taps", SH_MAX_TAPS);
@@ -546,10 +712,13 @@ int conv_shift_wgrad_impl(const void* X, long long rows, int C, const void* dY, 
   if (ctas > p.kb_total) ctas = p.kb_total;
   p.kb_per_cta = (p.kb_total + ctas - 1) / ctas;
   const int grid = (p.kb_total + p.kb_per_cta - 1) / p.kb_per_cta;
+  p.u8.x = reinterpret_cast<const uint8_t*>(u8_x); p.u8.idx = u8_idx; p.u8.H = u8_H; p.u8.W = u8_W; p.u8.C = u8_C;
+  p.u8.s = u8_s; p.u8.Hg = u8_s ? u8_H / u8_s : 0; p.u8.Wg = u8_s ? u8_W / u8_s : 0;
   CUtensorMap tmX, tmD;
   int rc;
-  if ((rc = make_tmap_2d_f16(&tmX, X, rows, C, C, 64, SH_WROWS_K)) != 0) return rc;
   if ((rc = make_tmap_2d_f16(&tmD, dY, rows, N, N, N < 64 ? N : 64, 64)) != 0) return rc;
+  if (u8_x) return launch_wgrad<32, 1, true>(tmD, tmD, p, grid, stream);
+  if ((rc = make_tmap_2d_f16(&tmX, X, rows, C, C, 64, SH_WROWS_K)) != 0) return rc;
   if (N == 32) return KH == 1 ? launch_wgrad<32, 1>(tmX, tmD, p, grid, stream) : launch_wgrad<32, 2>(tmX, tmD, p, grid, stream);
   return KH == 1 ? launch_wgrad<64, 1>(tmX, tmD, p, grid, stream) : launch_wgrad<64, 2>(tmX, tmD, p, grid, stream);
 }

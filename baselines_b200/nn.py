@@ -432,7 +432,11 @@ class Tower:
             Hg, Wg, Cg = c.H // s_, c.W // s_, c.C * s_ * s_
             self.sg.append(dict(Hg=Hg, Wg=Wg, Cg=Cg, k=k, s=s_, shifts=[a * Wg + b for a in range(k) for b in range(k)]))
         c0, g0 = cv[0], self.sg[0]
-        self.x16 = torch.empty(cap, g0["Hg"] * g0["Wg"] * g0["Cg"], **f16)
+        import os
+        # first layer straight from the uint8 images (producer warps gather + cast + space-to-depth in smem)
+        self.fused_u8 = (os.environ.get("B200RL_NO_FUSED_U8", "0") != "1" and c0.stride == 4 and c0.C == 4 and
+                         c0.nf == 32 and g0["Cg"] == 64)
+        self.x16 = None if self.fused_u8 else torch.empty(cap, g0["Hg"] * g0["Wg"] * g0["Cg"], **f16)
         # activations: layer i's output is stored space-to-depth'ed for layer i+1 (compact after the last conv)
         self.hconv = [torch.empty(cap, c.OH * c.OW * c.nf, **f16) for c in cv]
         # gradients w.r.t. conv outputs live zero-bordered on the conv's INPUT grid
@@ -452,8 +456,13 @@ class Tower:
     def _forward_shift(self, x, B, src_idx):
         cv, sg = self.convs, self.sg
         c0 = cv[0]
-        ops.s2d_gather(x, self.x16, B, c0.H, c0.W, c0.C, c0.stride, src_idx=src_idx)
-        cur = self.x16
+        if self.fused_u8:
+            self._u8 = (x, src_idx, c0.H, c0.W, c0.C, c0.stride)
+            cur = None
+        else:
+            self._u8 = None
+            ops.s2d_gather(x, self.x16, B, c0.H, c0.W, c0.C, c0.stride, src_idx=src_idx)
+            cur = self.x16
         for i, (c, g) in enumerate(zip(cv, sg)):
             if i + 1 < len(cv) and cv[i + 1].stride > 1:
                 sn = cv[i + 1].stride
@@ -462,7 +471,8 @@ class Tower:
             else:
                 omap = (0, c.OH * c.OW * c.nf, c.OW * c.nf, c.nf, 0, 0)
             ops.conv_shift_fwd(cur, B, g["Hg"], g["Wg"], g["Cg"], c.w_fwd, c.Kp, c.nf, g["shifts"], c.OH, c.OW,
-                               self.hconv[i], omap, bias=c.b, act=c.act, tag="fwd." + c.name)
+                               self.hconv[i], omap, bias=c.b, act=c.act, tag="fwd." + c.name,
+                               u8=self._u8 if i == 0 else None)
             cur = self.hconv[i]
         return cur, self.flat
 
@@ -474,7 +484,8 @@ class Tower:
             rows = B * g["Hg"] * g["Wg"]
             xin = self.x16 if i == 0 else self.hconv[i - 1]
             ops.conv_shift_wgrad(xin, rows, g["Cg"], self.dY[i], c.nf, g["shifts"], c.gw, c.nf,
-                                 alpha=alpha * c.in_scale, tag="wgrad." + c.name, gbias=c.gb, alpha_b=alpha)
+                                 alpha=alpha * c.in_scale, tag="wgrad." + c.name, gbias=c.gb, alpha_b=alpha,
+                                 u8=self._u8 if i == 0 else None)
             if i == 0:
                 break
             # dX_i (= dY_{i-1} after the ReLU mask) as a shift-GEMM over dY_i with negative shifts

@@ -79,32 +79,46 @@ def _iarr(vals, ctype):
     return (ctype * len(vals))(*[int(v) for v in vals])
 
 
+def _u8_args(u8):
+    """u8 = (images uint8 [.., H, W, C], src_idx or None, H, W, C, s) or None."""
+    if u8 is None:
+        return None, None, 0, 0, 0, 0
+    x, idx, H, W, C, s = u8
+    _chk(x, torch.uint8, "u8 images")
+    _chk(idx, torch.int64, "u8 src_idx")
+    return _ptr(x), _ptr(idx), int(H), int(W), int(C), int(s)
+
+
 def conv_shift_fwd(X, B, Hg, Wg, C, W, ldw, N, shifts, vy, vx, out, omap, *, saved=None, smap=None, bias=None,
-                   act=ACT_NONE, dact=False, alpha=1.0, tag=None):
+                   act=ACT_NONE, dact=False, alpha=1.0, tag=None, u8=None):
     """Shift-GEMM convolution (forward, or data gradient with dact=True).  omap / smap: 6-tuples
     (mode, sN, sY, sX, Cq, s)."""
     _chk(X, torch.float16, "X")
     _chk(W, torch.float16, "W")
     _chk(out, torch.float16, "out")
+    u8a = _u8_args(u8)
     sh = _iarr(shifts, _C.c_int)
     om = _iarr(omap, _C.c_longlong)
     sm = _iarr(smap, _C.c_longlong) if smap is not None else None
     rows = B * Hg * Wg
     _lib.call("b200rl_conv_shift_fwd", _ptr(X), int(B), Hg, Wg, C, _ptr(W), int(ldw), int(N), len(shifts), sh, vy, vx,
-              _ptr(out), om, _ptr(saved), sm, _ptr(bias), int(act), int(bool(dact)), float(alpha), _stream(),
+              _ptr(out), om, _ptr(saved), sm, _ptr(bias), int(act), int(bool(dact)), float(alpha), *u8a, _stream(),
               label="convs." + (tag or "fwd"), flops=2.0 * rows * N * len(shifts) * C,
-              nbytes=2.0 * rows * C + 2.0 * rows * N)
+              nbytes=(1.0 if u8 is not None else 2.0) * rows * C + 2.0 * rows * N)
 
 
-def conv_shift_wgrad(X, rows, C, dY, N, shifts, G, ldg, alpha=1.0, max_ctas=0, tag=None, gbias=None, alpha_b=1.0):
+def conv_shift_wgrad(X, rows, C, dY, N, shifts, G, ldg, alpha=1.0, max_ctas=0, tag=None, gbias=None, alpha_b=1.0,
+                     u8=None):
     _chk(X, torch.float16, "X")
     _chk(dY, torch.float16, "dY")
     _chk(G, torch.float32, "G")
     sh = _iarr(shifts, _C.c_int)
     _chk(gbias, torch.float32, "gbias")
+    u8a = _u8_args(u8)
     _lib.call("b200rl_conv_shift_wgrad", _ptr(X), int(rows), C, _ptr(dY), int(N), len(shifts), sh, _ptr(G), int(ldg),
-              float(alpha), _ptr(gbias), float(alpha_b), int(max_ctas), _stream(), label="convs." + (tag or "wgrad"),
-              flops=2.0 * rows * N * len(shifts) * C, nbytes=2.0 * rows * (C + N))
+              float(alpha), _ptr(gbias), float(alpha_b), int(max_ctas), *u8a, _stream(),
+              label="convs." + (tag or "wgrad"), flops=2.0 * rows * N * len(shifts) * C,
+              nbytes=rows * ((1.0 if u8 is not None else 2.0) * C + 2.0 * N))
 
 
 def dgrad_weights(w, out, R, S, Cin, Cout, s, ld):

@@ -66,9 +66,13 @@ int b200rl_gemm_f16(const void* A, const void* B, void* C, const float* bias, co
 int b200rl_conv_shift_fwd(const void* X, long long B, int Hg, int Wg, int C, const void* W, long long ldw, int N,
                           int taps, const int* shifts, int vy, int vx, void* out, const long long* omap,
                           const void* saved, const long long* smap, const float* bias, int act, int dact, float alpha,
+                          const void* u8_x, const long long* u8_idx, int u8_H, int u8_W, int u8_C, int u8_s,
                           void* stream);
+/* u8_x != NULL (first layer): X is ignored; producer warps gather uint8 images u8_x[u8_idx[n], H, W, C], cast them
+ * to fp16 and build the space-to-depth (factor u8_s) tile directly in shared memory (models.py:19, ppo2.py:165). */
 int b200rl_conv_shift_wgrad(const void* X, long long rows, int C, const void* dY, int N, int taps, const int* shifts,
                             float* G, long long ldg, float alpha, float* gbias, float alpha_b, int max_ctas,
+                            const void* u8_x, const long long* u8_idx, int u8_H, int u8_W, int u8_C, int u8_s,
                             void* stream);   /* gbias != NULL: gbias[n] += alpha_b * sum_m dY[m, n] (fused) */
 
 /* Implicit-GEMM convolution (tf.nn.conv2d a2c/utils.py:56 and its gradients): the A operand is read

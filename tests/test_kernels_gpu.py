@@ -699,3 +699,44 @@ def test_gemm_column_remap(ops):
     grid = out.float().view(M, 9, 9, 64)
     assert torch.allclose(grid[:, :7, :7].reshape(M, -1), ref, atol=3e-2, rtol=5e-3)
     assert float(grid[:, 7:].abs().max()) == 0 and float(grid[:, :, 7:].abs().max()) == 0
+
+
+@pytest.mark.parametrize("B,gather", [(3, False), (37, True), (700, True)])
+def test_conv_shift_fused_uint8_source(ops, B, gather):
+    """First conv layer straight from uint8 frames: the producer warps' gather + cast + space-to-depth tile must
+    give the same forward (bit-exact: same fp16 operands, same MMA order) and the same wgrad (split-K float
+    atomics -> tolerance) as s2d_gather followed by the fp16 TMA path."""
+    torch.manual_seed(B)
+    H = W = 84
+    C, s, Hg, Wg, N = 4, 4, 21, 21, 32
+    pool = 2 * B + 5
+    frames = torch.randint(0, 256, (pool, H, W, C), dtype=torch.uint8, device="cuda")
+    idx = torch.randperm(pool, device="cuda")[:B].contiguous() if gather else None
+    x16 = torch.empty(B, Hg * Wg * 64, dtype=torch.float16, device="cuda")
+    ops.s2d_gather(frames, x16, B, H, W, C, s, src_idx=idx)
+    shifts = [0, 1, Wg, Wg + 1]
+    wt = (torch.randn(N, 256, device="cuda") * 0.01).half()
+    bias = torch.randn(N, device="cuda")
+    omap = (2, 100 * 4 * N, 10 * 4 * N, 4 * N, N, 2)
+    h_ref = torch.zeros(B, 10, 10, 4 * N, dtype=torch.float16, device="cuda")
+    h_u8 = torch.zeros_like(h_ref)
+    ops.conv_shift_fwd(x16, B, Hg, Wg, 64, wt, 256, N, shifts, 20, 20, h_ref, omap, bias=bias, act=ops.ACT_RELU)
+    u8 = (frames, idx, H, W, C, s)
+    ops.conv_shift_fwd(None, B, Hg, Wg, 64, wt, 256, N, shifts, 20, 20, h_u8, omap, bias=bias, act=ops.ACT_RELU, u8=u8)
+    torch.cuda.synchronize()
+    assert float(h_ref.float().abs().max()) > 0
+    assert torch.equal(h_ref, h_u8)
+    dz = torch.zeros(B, Hg, Wg, N, dtype=torch.float16, device="cuda")
+    dz[:, :20, :20] = (torch.randn(B, 20, 20, N, device="cuda") * 0.5).half()
+    G_ref = torch.zeros(256, N, dtype=torch.float32, device="cuda")
+    G_u8 = torch.zeros_like(G_ref)
+    gb_ref = torch.zeros(N, dtype=torch.float32, device="cuda")
+    gb_u8 = torch.zeros_like(gb_ref)
+    rows = B * Hg * Wg
+    ops.conv_shift_wgrad(x16, rows, 64, dz, N, shifts, G_ref, N, alpha=1.0 / 255, gbias=gb_ref, alpha_b=1.0)
+    ops.conv_shift_wgrad(None, rows, 64, dz, N, shifts, G_u8, N, alpha=1.0 / 255, gbias=gb_u8, alpha_b=1.0, u8=u8)
+    torch.cuda.synchronize()
+    scale = float(G_ref.abs().max())
+    assert scale > 0
+    assert float((G_ref - G_u8).abs().max()) <= 1e-5 * scale + 1e-3, float((G_ref - G_u8).abs().max())
+    assert torch.allclose(gb_ref, gb_u8, atol=1e-3, rtol=1e-5)
