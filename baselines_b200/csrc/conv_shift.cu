@@ -23,7 +23,8 @@
 namespace b200rl {
 
 static constexpr int SH_BM = 128;
-static constexpr int SH_THREADS = 256;
+static constexpr int SH_THREADS = 256;             // wgrad: TMA, MMA, TMEM alloc, spare, 4 epilogue warps
+static constexpr int SH_FWD_THREADS = 384;         // forward: two epilogue warp sets (one per accumulator stage)
 static constexpr int SH_MAX_TAPS = 16;
 static constexpr int SH_AROWS = 160;                 // 128 + max shift span (<= 32)
 static constexpr int SH_ABYTES = SH_AROWS * 128;     // one 64-channel half of an A stage
@@ -62,11 +63,30 @@ __device__ __forceinline__ long long map_coloff(const AddrMap& a, int col) {
 // Optional fused source for the FIRST conv layer: uint8 NHWC images gathered through src_idx.  Producer warps
 // build the space-to-depth fp16 A tile directly in shared memory (tf.cast of models.py:19 and arr[mbinds] of
 // ppo2.py:165 fused into the first load): grid row (n, Y, X) = 64 channels (dy, dx, c) = s segments of s*C bytes.
+// n / d for n < 2^31, d >= 2 without the ~25-instruction runtime division: q = umulhi(n, mul) >> sh with
+// mul = floor(2^(31+s) / d) + 1, s = ceil(log2 d), sh = s - 1 (error term n*e / (d*2^(31+s)) < 1/d since e <= d <= 2^s).
+struct FastDiv {
+  uint32_t mul, sh, d;
+  __device__ __forceinline__ uint32_t div(uint32_t n) const { return __umulhi(n, mul) >> sh; }
+};
+static FastDiv make_fastdiv(uint32_t d) {
+  FastDiv f;
+  f.d = d;
+  uint32_t s = 0;
+  while ((1ull << s) < d) ++s;
+  if (s == 0) s = 1;                                   // d == 1: mul = 2^31 + 1 does not fit; callers require d >= 2
+  f.mul = (uint32_t)(((1ull << (31 + s)) / d) + 1);
+  f.sh = s - 1;
+  return f;
+}
+
 struct U8Src {
   const uint8_t* x;        // nullptr: A tiles come from the fp16 matrix through TMA
   const long long* idx;    // sample gather (may be null)
-  int H, W, C, s;          // image geometry and space-to-depth factor (s*C == 16, s*s*C == 64)
-  int Hg, Wg;
+  long long sample_bytes;  // H*W*C
+  int row_bytes;           // W*C: distance between the s segments (dy) of one grid row
+  int y_bytes, x_bytes;    // s*W*C, s*C
+  FastDiv per, wg;         // grid rows per sample (Hg*Wg), Wg
 };
 
 static constexpr int U8_WARPS = 8;
@@ -107,40 +127,49 @@ static constexpr int U8_DEPTH = 4;
 static constexpr int U8_UNIT_BYTES = 32 * 64;
 static constexpr int U8_RING_BYTES = U8_WARPS * U8_DEPTH * U8_UNIT_BYTES;     // 64 KB
 
+__device__ __forceinline__ uint4 ld_shared_v4(uint32_t addr) {
+  uint4 v;
+  asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ void st_shared_v4(uint32_t addr, const uint4& v) {
+  asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+
 struct U8Unit {
   long long sb;            // sample index of this lane's row in the NEXT unit to issue (-1: out of range -> zeros)
   __device__ __forceinline__ void lookup(const U8Src& u, long long m, long long M) {
     sb = -1;
     if (m >= 0 && m < M) {
-      const uint32_t n = (uint32_t)m / (uint32_t)(u.Hg * u.Wg);
+      const uint32_t n = u.per.div((uint32_t)m);
       sb = u.idx ? __ldg(u.idx + n) : (long long)n;
     }
   }
-  __device__ __forceinline__ void issue(const U8Src& u, long long m, uint8_t* slot, int lane) const {
+  __device__ __forceinline__ void issue(const U8Src& u, long long m, uint32_t slot_lane) const {
     const uint8_t* src = u.x;
-    int sz = 0;
-    long long rowstride = 0;
+    int sz = 0, rowstride = 0;
     if (sb >= 0) {
-      const uint32_t mm = (uint32_t)m, per = (uint32_t)(u.Hg * u.Wg);
-      const uint32_t rem = mm - (mm / per) * per;
-      const uint32_t Y = rem / (uint32_t)u.Wg, X = rem - Y * (uint32_t)u.Wg;
-      rowstride = (long long)u.W * u.C;
-      src += ((sb * u.H + (long long)(u.s * Y)) * u.W + (long long)u.s * X) * u.C;
+      const uint32_t mm = (uint32_t)m;
+      const uint32_t rem = mm - u.per.div(mm) * u.per.d;
+      const uint32_t Y = u.wg.div(rem), X = rem - Y * u.wg.d;
+      rowstride = u.row_bytes;
+      src += sb * u.sample_bytes + (long long)(Y * (uint32_t)u.y_bytes + X * (uint32_t)u.x_bytes);
       sz = 16;
     }
 #pragma unroll
-    for (int dy = 0; dy < 4; ++dy) cp_async16(slot + dy * 512 + lane * 16, src + dy * rowstride, sz);
+    for (int dy = 0; dy < 4; ++dy)
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(slot_lane + dy * 512), "l"(src + dy * rowstride),
+                   "r"(sz)
+                   : "memory");
   }
-  // rows32 = first of the unit's 32 tile rows (a multiple of 8 rows, so the swizzle phase is lane & 7)
-  __device__ __forceinline__ void convert(const uint8_t* slot, uint8_t* rows32, int lane) const {
-    uint8_t* rowp = rows32 + lane * 128;
-    const int sw = lane & 7;
+  // row_sw = smem address of this lane's tile row + ((lane & 7) << 4): chunk c of the row lives at row_sw ^ (c << 4)
+  __device__ __forceinline__ void convert(uint32_t slot_lane, uint32_t row_sw) const {
 #pragma unroll
     for (int dy = 0; dy < 4; ++dy) {
       uint4 lo, hi;
-      u8x16_to_f16(*reinterpret_cast<const uint4*>(slot + dy * 512 + lane * 16), lo, hi);
-      *reinterpret_cast<uint4*>(rowp + (((2 * dy) ^ sw) << 4)) = lo;
-      *reinterpret_cast<uint4*>(rowp + (((2 * dy + 1) ^ sw) << 4)) = hi;
+      u8x16_to_f16(ld_shared_v4(slot_lane + dy * 512), lo, hi);
+      st_shared_v4(row_sw ^ (uint32_t)((2 * dy) << 4), lo);
+      st_shared_v4(row_sw ^ (uint32_t)((2 * dy + 1) << 4), hi);
     }
   }
 };
@@ -153,7 +182,8 @@ __device__ __forceinline__ void u8_producer_loop(const U8Src& u, long long M, in
                                                  uint8_t* ring_base, int pw, int lane) {
   constexpr int RB = NROWS / 32;
   static_assert(NROWS % 32 == 0, "unit = 32 rows");
-  uint8_t* ring = ring_base + pw * (U8_DEPTH * U8_UNIT_BYTES);
+  const uint32_t ring = smem_u32(ring_base) + pw * (U8_DEPTH * U8_UNIT_BYTES) + lane * 16;
+  const uint32_t tile0 = smem_u32(stages) + lane * 128 + ((lane & 7) << 4);
   const int total = ntiles * RB;
   U8Unit t;
   auto row_of = [&](int unit) { return row0(unit / RB) + (unit % RB) * 32 + lane; };
@@ -161,7 +191,7 @@ __device__ __forceinline__ void u8_producer_loop(const U8Src& u, long long M, in
   t.lookup(u, row_of(ui), ui < total ? M : 0);
 #pragma unroll
   for (int d = 0; d < U8_DEPTH; ++d) {
-    if (ui < total) t.issue(u, row_of(ui), ring + d * U8_UNIT_BYTES, lane);
+    if (ui < total) t.issue(u, row_of(ui), ring + d * U8_UNIT_BYTES);
     cp_async_commit();
     ui += U8_WARPS;
     t.lookup(u, row_of(ui), ui < total ? M : 0);
@@ -173,11 +203,11 @@ __device__ __forceinline__ void u8_producer_loop(const U8Src& u, long long M, in
     const uint32_t ph = (uint32_t)(seq / STAGES) & 1u;
     cp_async_wait<U8_DEPTH - 1>();
     mbar_wait(&empty_bar[s], ph ^ 1);
-    t.convert(ring + d * U8_UNIT_BYTES, stages + s * stage_bytes + rb * (32 * 128), lane);
+    t.convert(ring + d * U8_UNIT_BYTES, tile0 + s * stage_bytes + rb * (32 * 128));
     fence_proxy_async_smem();                           // generic-proxy writes -> visible to the tensor core
     __syncwarp();
     if (lane == 0) mbar_arrive(&full_bar[s]);
-    if (ui < total) t.issue(u, row_of(ui), ring + d * U8_UNIT_BYTES, lane);
+    if (ui < total) t.issue(u, row_of(ui), ring + d * U8_UNIT_BYTES);
     cp_async_commit();
     ui += U8_WARPS;
     t.lookup(u, row_of(ui), ui < total ? M : 0);
@@ -188,6 +218,7 @@ __device__ __forceinline__ void u8_producer_loop(const U8Src& u, long long M, in
 
 struct ShiftParams {
   U8Src u8;
+  FastDiv fwg, fhg;        // epilogue row -> (n, y, x)
   long long M;             // grid rows = B*Hg*Wg
   int Hg, Wg;              // grid
   int N;                   // output channels of the GEMM
@@ -207,7 +238,7 @@ struct ShiftParams {
 
 // ------------------------------------------------------------------------------------------------ forward / dgrad
 template <int BN, int KH, bool DACT, bool U8>
-__global__ void __launch_bounds__(SH_THREADS + (U8 ? U8_THREADS : 0), 1)
+__global__ void __launch_bounds__(SH_FWD_THREADS + (U8 ? U8_THREADS : 0), 1)
 conv_shift_fwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW,
                       const __grid_constant__ ShiftParams p) {
   constexpr int STAGE_BYTES = KH * SH_ABYTES;
@@ -269,14 +300,14 @@ conv_shift_fwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_cons
         if (++s == STAGES) { s = 0; ph ^= 1; }
       }
     }
-  } else if (U8 && warp >= 8) {
+  } else if (U8 && warp >= 12) {
     // uint8 producer warps (the cp.async ring lives in the unused 64 KB of the weight area)
     const int step = gridDim.x, first = blockIdx.x;
     const int ntiles = first < p.num_tiles ? (p.num_tiles - first + step - 1) / step : 0;
     const int min_shift = p.min_shift;
     u8_producer_loop<SH_AROWS, STAGES>(
         p.u8, p.M, ntiles, [=](int seq) { return (long long)(first + seq * step) * SH_BM + min_shift; }, smem,
-        STAGE_BYTES, full_bar, empty_bar, wres + 16384, warp - 8, lane);
+        STAGE_BYTES, full_bar, empty_bar, wres + 16384, warp - 12, lane);
   } else if (warp == 1) {
     constexpr uint32_t IDESC = (1u << 4) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(SH_BM >> 4) << 24);
     int s = 0, as = 0;
@@ -314,16 +345,18 @@ conv_shift_fwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_cons
       if (++s == STAGES) { s = 0; ph ^= 1; }
       if (++as == 2) { as = 0; aph ^= 1; }
     }
-  } else if (warp >= 4 && warp < 8) {
-    const int ew = warp - 4;
-    int as = 0;
+  } else if (warp >= 4 && warp < 12) {
+    // warps 4-7 drain accumulator stage 0 (even tiles), warps 8-11 stage 1 (odd tiles): a warp reaches TMEM lane
+    // quadrant warp % 4 only, and one set per stage gives every tile two tile-times of epilogue
+    const int ew = warp & 3;
+    const int as = (warp - 4) >> 2;
     uint32_t aph = 0;
     constexpr int G = (BN >= 64) ? 4 : BN / 16;       // 16-column chunks handled together (loads in flight)
-    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+    for (int tile = blockIdx.x + as * (int)gridDim.x; tile < p.num_tiles; tile += 2 * (int)gridDim.x) {
       const uint32_t m = (uint32_t)tile * SH_BM + ew * 32 + lane;       // M < 2^31 (checked on the host)
-      const uint32_t t2 = m / (uint32_t)p.Wg;
+      const uint32_t t2 = p.fwg.div(m);
       const int x = (int)(m - t2 * (uint32_t)p.Wg);
-      const int n = (int)(t2 / (uint32_t)p.Hg);
+      const int n = (int)p.fhg.div(t2);
       const int y = (int)(t2 - (uint32_t)n * (uint32_t)p.Hg);
       const bool ok = ((long long)m < p.M) && (y < p.vy) && (x < p.vx);
       const long long obase = map_rowbase(p.omap, n, y, x);
@@ -389,7 +422,7 @@ conv_shift_fwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_cons
       }
       tc_fence_before();
       mbar_arrive(&tempty_bar[as]);
-      if (++as == 2) { as = 0; aph ^= 1; }
+      aph ^= 1;
     }
   }
   tc_fence_before();
@@ -509,7 +542,8 @@ conv_shift_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_co
         if (++s == STAGES) { s = 0; ph ^= 1; }
       }
     }
-  } else if (warp == 3) {
+  } else if (warp >= 4 && warp < 8) {
+    const int ew = warp - 4;
     // fused bias gradient: column sums of the dY tile while it sits in shared memory (swizzle undone by hand)
     if (p.gbias != nullptr) {
       // lanes cover one 64-wide row with 8-byte loads (4 columns per lane); the remaining lanes take other rows
@@ -518,9 +552,12 @@ conv_shift_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_co
       const int cq = lane % LPR, rg = lane / LPR;              // column quad, row group
       const int chunk = (cq * 8) >> 4, within = (cq * 8) & 15;
       float a[4] = {0.f, 0.f, 0.f, 0.f};
+      // pipeline stage s is always summed by warp s % 4: a warp then sees every fill of its stages in order, so the
+      // parity wait cannot alias (a k-block round-robin would let a warp run a whole phase ahead of a stage)
       int s = 0;
       uint32_t ph = 0;
-      for (int kb = kb0; kb < kb1; ++kb) {
+      for (int kb = kb0; kb < kb1; ++kb, s = (s + 1 == STAGES) ? 0 : s + 1, ph ^= (s == 0)) {
+        if ((s & 3) != ew) continue;
         mbar_wait(&full_bar[s], ph);
         const uint8_t* sb = smem + s * STAGE_BYTES + KH * SH_WABYTES;
 #pragma unroll 8
@@ -534,7 +571,6 @@ conv_shift_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_co
         }
         __syncwarp();
         if (lane == 0) mbar_arrive(&empty_bar[s]);
-        if (++s == STAGES) { s = 0; ph ^= 1; }
       }
 #pragma unroll
       for (int o = LPR; o < 32; o <<= 1)                       // fold the row groups together
@@ -546,8 +582,6 @@ conv_shift_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_co
           if (4 * cq + i < p.N) atomicAdd(p.gbias + 4 * cq + i, a[i] * p.alpha_b);
       }
     }
-  } else if (warp >= 4 && warp < 8) {
-    const int ew = warp - 4;
     if (kb1 > kb0) {
       mbar_wait(done_bar, 0);
       tc_fence_after();
@@ -578,6 +612,20 @@ conv_shift_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_co
 }
 
 // ------------------------------------------------------------------------------------------------ host
+static U8Src make_u8src(const void* x, const long long* idx, int H, int W, int C, int s) {
+  U8Src u{};
+  u.x = reinterpret_cast<const uint8_t*>(x);
+  if (!x) return u;
+  u.idx = idx;
+  u.sample_bytes = (long long)H * W * C;
+  u.row_bytes = W * C;
+  u.y_bytes = s * W * C;
+  u.x_bytes = s * C;
+  u.per = make_fastdiv((uint32_t)((H / s) * (W / s)));
+  u.wg = make_fastdiv((uint32_t)(W / s));
+  return u;
+}
+
 template <int BN, int KH, bool DACT, bool U8 = false>
 static int launch_fwd(const CUtensorMap& tmX, const CUtensorMap& tmW, const ShiftParams& p, cudaStream_t st) {
   constexpr int STAGES = (KH == 1) ? 6 : 3;
@@ -593,7 +641,7 @@ static int launch_fwd(const CUtensorMap& tmX, const CUtensorMap& tmW, const Shif
     attr = true;
   }
   const int grid = p.num_tiles < device_num_sms() ? p.num_tiles : device_num_sms();
-  kern<<<grid, SH_THREADS + (U8 ? U8_THREADS : 0), SMEM, st>>>(tmX, tmW, p);
+  kern<<<grid, SH_FWD_THREADS + (U8 ? U8_THREADS : 0), SMEM, st>>>(tmX, tmW, p);
   return check_launch("conv_shift_fwd_kernel");
 }
 
@@ -658,8 +706,10 @@ int conv_shift_fwd_impl(const void* X, long long B, int Hg, int Wg, int C, const
   B200RL_REQUIRE(!(saved && !smap), "conv_shift_fwd: saved needs smap");
   p.bias = bias; p.act = act; p.dact = dact; p.alpha = alpha;
   p.num_tiles = (int)((p.M + SH_BM - 1) / SH_BM);
-  p.u8.x = reinterpret_cast<const uint8_t*>(u8_x); p.u8.idx = u8_idx; p.u8.H = u8_H; p.u8.W = u8_W; p.u8.C = u8_C;
-  p.u8.s = u8_s; p.u8.Hg = Hg; p.u8.Wg = Wg;
+  p.u8 = make_u8src(u8_x, u8_idx, u8_H, u8_W, u8_C, u8_s);
+  B200RL_REQUIRE(Hg >= 2 && Wg >= 2, "conv_shift_fwd: grid must be at least 2x2");
+  p.fwg = make_fastdiv((uint32_t)Wg);
+  p.fhg = make_fastdiv((uint32_t)Hg);
   CUtensorMap tmX, tmW;
   int rc;
   if (u8_x) {
@@ -712,8 +762,7 @@ int conv_shift_wgrad_impl(const void* X, long long rows, int C, const void* dY, 
   if (ctas > p.kb_total) ctas = p.kb_total;
   p.kb_per_cta = (p.kb_total + ctas - 1) / ctas;
   const int grid = (p.kb_total + p.kb_per_cta - 1) / p.kb_per_cta;
-  p.u8.x = reinterpret_cast<const uint8_t*>(u8_x); p.u8.idx = u8_idx; p.u8.H = u8_H; p.u8.W = u8_W; p.u8.C = u8_C;
-  p.u8.s = u8_s; p.u8.Hg = u8_s ? u8_H / u8_s : 0; p.u8.Wg = u8_s ? u8_W / u8_s : 0;
+  p.u8 = make_u8src(u8_x, u8_idx, u8_H, u8_W, u8_C, u8_s);
   CUtensorMap tmX, tmD;
   int rc;
   if ((rc = make_tmap_2d_f16(&tmD, dY, rows, N, N, N < 64 ? N : 64, 64)) != 0) return rc;

@@ -22,6 +22,6 @@ v = torch.randn(B, device=dev)
 r = v + torch.randn(B, device=dev)
 n = torch.full((B,), 1.79, device=dev)
 for _ in range(int(os.environ.get("PROF_ITERS", 2))):
-    m.train_rollout(2.5e-4, 0.1, obs, a, r, v, n, None)
+    m.train_rollout(2.5e-4, 0.1, obs, a, r, v, n, torch.randperm(B, device=dev) if os.environ.get("PROF_GATHER", "1") == "1" else None)
 torch.cuda.synchronize()
 print("done")
