@@ -23,6 +23,7 @@ SIGNATURES = {
     "b200rl_dgrad_weights": [_p, _p, _i, _i, _i, _i, _i, _ll, _p],
     "b200rl_im2col": [_p, _i, _p, _p, _ll, _i, _i, _i, _i, _i, _i, _p],
     "b200rl_s2d_gather": [_p, _p, _p, _ll, _i, _i, _i, _i, _p],
+    "b200rl_frame_stack": [_p, _p, _p, _p, _ll, _ll, _i, _i, _p],
     "b200rl_col2im": [_p, _p, _p, _ll, _i, _i, _i, _i, _i, _i, _i, _p],
     "b200rl_colsum": [_p, _p, _ll, _i, _ll, _f, _p],
     "b200rl_cat_step": [_p, _ll, _i, _p, _ll, _p, _ull, _ull, _p, _p, _p, _ll, _p],

@@ -74,6 +74,69 @@ class DummyVecEnv(VecEnv):
         return self.buf_obs.copy()
 
 
+class VecEnvWrapper(VecEnv):
+    """vec_env.py:140-175: a wrapper over a whole batch of envs; unknown public attributes fall through to venv."""
+
+    def __init__(self, venv, observation_space=None, action_space=None):
+        self.venv = venv
+        super().__init__(venv.num_envs, observation_space or venv.observation_space,
+                         action_space or venv.action_space)
+
+    def step_async(self, actions):
+        self.venv.step_async(actions)
+
+    def close(self):
+        return self.venv.close()
+
+    def __getattr__(self, name):
+        if name.startswith('_'):
+            raise AttributeError("attempted to get missing private attribute '{}'".format(name))
+        return getattr(self.venv, name)
+
+
+class VecFrameStack(VecEnvWrapper):
+    """vec_frame_stack.py:6-31: stack the last `nstack` observations along the channel axis; the stack of an env is
+    cleared when its episode ends.
+
+    reset()/step_wait() are the reference's host implementation (np.roll on a [N, H, W, nstack*c] array).  The
+    B200 Runner does not call them: it sees `frame_stack_device`, pulls the UNSTACKED frames with step_frames()
+    (1/nstack of the bytes over PCIe) and applies the same update to the HBM-resident rollout buffer with
+    b200rl_frame_stack -- the previous stacked observation is already there as rollout.obs[t-1]."""
+    frame_stack_device = True
+
+    def __init__(self, venv, nstack):
+        self.nstack = nstack
+        wos = venv.observation_space
+        low = np.repeat(wos.low, nstack, axis=-1)
+        high = np.repeat(wos.high, nstack, axis=-1)
+        self.frame_channels = int(wos.shape[-1])
+        self.stackedobs = np.zeros((venv.num_envs,) + low.shape, low.dtype)
+        ob_space = spaces.Box(low=low, high=high, dtype=wos.dtype)
+        super().__init__(venv, observation_space=ob_space)
+
+    def step_wait(self):
+        obs, rews, news, infos = self.venv.step_wait()
+        self.stackedobs = np.roll(self.stackedobs, shift=-1, axis=-1)
+        self.stackedobs[np.asarray(news, dtype=np.bool_)] = 0
+        self.stackedobs[..., -obs.shape[-1]:] = obs
+        return self.stackedobs, rews, news, infos
+
+    def reset(self):
+        obs = self.venv.reset()
+        self.stackedobs[...] = 0
+        self.stackedobs[..., -obs.shape[-1]:] = obs
+        return self.stackedobs
+
+    # ---- unstacked access for the device-side stack
+    def reset_frames(self):
+        return self.venv.reset()
+
+    def step_frames(self, actions):
+        """(new frames [N, ..., c], rews, news, infos): the wrapped env's step; stacking is left to the caller."""
+        self.venv.step_async(actions)
+        return self.venv.step_wait()
+
+
 class EpisodeStats:
     """What bench.Monitor contributes to the learner (bench/monitor.py:58-75): info['episode'] = {r, l, t}."""
 

@@ -31,6 +31,7 @@ int gae_scan_impl(const float*, const float*, const uint8_t*, const float*, cons
                   double, double, int, cudaStream_t);
 int im2col_impl(const void*, int, const long long*, void*, long long, int, int, int, int, int, int, cudaStream_t);
 int s2d_gather_impl(const void*, const long long*, void*, long long, int, int, int, int, cudaStream_t);
+int frame_stack_impl(const void*, const void*, const void*, void*, long long, long long, int, int, cudaStream_t);
 int col2im_impl(const void*, const void*, void*, long long, int, int, int, int, int, int, int, cudaStream_t);
 int colsum_impl(const void*, float*, long long, int, long long, float, cudaStream_t);
 int cat_step_impl(const float*, long long, int, const float*, long long, const float*, unsigned long long,
@@ -119,6 +120,11 @@ int b200rl_im2col(const void* x, int src_is_u8, const long long* src_idx, void* 
                   int C, int rf, int stride, int same_pad, void* stream) {
   return im2col_impl(x, src_is_u8, src_idx, cols, B, H, W, C, rf, stride, same_pad, S(stream));
 }
+int b200rl_frame_stack(const void* prev, const void* frame, const void* news, void* out, long long N, long long pixels,
+                       int nstack, int c, void* stream) {
+  return frame_stack_impl(prev, frame, news, out, N, pixels, nstack, c, S(stream));
+}
+
 int b200rl_s2d_gather(const void* x, const long long* src_idx, void* out, long long B, int H, int W, int C, int s,
                       void* stream) {
   return s2d_gather_impl(x, src_idx, out, B, H, W, C, s, S(stream));

@@ -7,6 +7,7 @@
 //             the activation derivative of the layer below
 //   colsum  : bias gradients
 // All HBM-bound: 16-byte vector accesses, consecutive lanes on consecutive 16 B chunks.
+#include <algorithm>
 #include "common.cuh"
 
 namespace b200rl {
@@ -254,6 +255,81 @@ int im2col_impl(const void* x, int src_is_u8, const long long* src_idx, void* co
     im2col_kernel<__half><<<grid, 256, 0, stream>>>(reinterpret_cast<const __half*>(x), src_idx,
                                                     reinterpret_cast<__half*>(cols), B, g);
   return check_launch("im2col_kernel");
+}
+
+// ------------------------------------------------------------------------------------------------ frame stack
+// Device half of VecFrameStack (reference common/vec_env/vec_frame_stack.py:17-25): out = roll(prev, -1, axis=-1)
+// (ONE channel, the reference's literal shift: a whole frame only when c == 1); out[news] = 0; out[..., -c:] = frame.
+// Pixel p of env n holds K = nstack*c bytes.
+template <int VEC>
+__global__ void __launch_bounds__(256)
+frame_stack_k4_kernel(const uint32_t* __restrict__ prev, const uint8_t* __restrict__ frame,
+                      const uint8_t* __restrict__ news, uint32_t* __restrict__ out, long long pixels_per_env,
+                      long long total_pixels) {
+  // K = 4, c = 1: one 32-bit word per pixel; out = (prev >> 8) | frame << 24 (little endian: byte 3 = newest frame)
+  const long long stride = (long long)gridDim.x * blockDim.x * VEC;
+  for (long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * VEC; i < total_pixels; i += stride) {
+    const bool fresh = news[i / pixels_per_env] != 0;       // VEC divides pixels_per_env: one env per vector
+    if (VEC == 4) {
+      const uint4 pv = fresh ? make_uint4(0, 0, 0, 0) : *reinterpret_cast<const uint4*>(prev + i);
+      const uint32_t f = *reinterpret_cast<const uint32_t*>(frame + i);
+      uint4 o;
+      o.x = (pv.x >> 8) | ((f & 0xffu) << 24);
+      o.y = (pv.y >> 8) | (((f >> 8) & 0xffu) << 24);
+      o.z = (pv.z >> 8) | (((f >> 16) & 0xffu) << 24);
+      o.w = (pv.w >> 8) | ((f >> 24) << 24);
+      *reinterpret_cast<uint4*>(out + i) = o;
+    } else {
+      const uint32_t pv = fresh ? 0u : prev[i];
+      out[i] = (pv >> 8) | ((uint32_t)frame[i] << 24);
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256)
+frame_stack_generic_kernel(const uint8_t* __restrict__ prev, const uint8_t* __restrict__ frame,
+                           const uint8_t* __restrict__ news, uint8_t* __restrict__ out, long long pixels_per_env,
+                           long long total_pixels, int K, int c) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total_pixels; i += stride) {
+    const bool fresh = news[i / pixels_per_env] != 0;
+    for (int k = 0; k < K - c; ++k) out[i * K + k] = fresh ? (uint8_t)0 : prev[i * K + k + 1];   // np.roll(.., -1)
+    for (int k = 0; k < c; ++k) out[i * K + K - c + k] = frame[i * c + k];
+  }
+}
+
+int frame_stack_impl(const void* prev, const void* frame, const void* news, void* out, long long N, long long pixels,
+                     int nstack, int c, cudaStream_t stream) {
+  B200RL_REQUIRE(prev && frame && news && out && N > 0 && pixels > 0 && nstack >= 1 && c >= 1, "frame_stack: bad args");
+  B200RL_REQUIRE(prev != out, "frame_stack: in-place update is not supported (pixels are shifted across threads' words)");
+  const long long total = N * pixels;
+  const int K = nstack * c;
+  const bool al16 = ((reinterpret_cast<uintptr_t>(prev) | reinterpret_cast<uintptr_t>(out)) & 15) == 0 &&
+                    (reinterpret_cast<uintptr_t>(frame) & 3) == 0;
+  if (K == 4 && c == 1) {
+    if (al16 && pixels % 4 == 0) {
+      const int grid = (int)std::min<long long>((total / 4 + 255) / 256, 148LL * 16);
+      frame_stack_k4_kernel<4><<<grid, 256, 0, stream>>>(reinterpret_cast<const uint32_t*>(prev),
+                                                        reinterpret_cast<const uint8_t*>(frame),
+                                                        reinterpret_cast<const uint8_t*>(news),
+                                                        reinterpret_cast<uint32_t*>(out), pixels, total);
+    } else {
+      B200RL_REQUIRE(((reinterpret_cast<uintptr_t>(prev) | reinterpret_cast<uintptr_t>(out)) & 3) == 0,
+                     "frame_stack: stacked buffers must be 4-byte aligned");
+      const int grid = (int)std::min<long long>((total + 255) / 256, 148LL * 16);
+      frame_stack_k4_kernel<1><<<grid, 256, 0, stream>>>(reinterpret_cast<const uint32_t*>(prev),
+                                                        reinterpret_cast<const uint8_t*>(frame),
+                                                        reinterpret_cast<const uint8_t*>(news),
+                                                        reinterpret_cast<uint32_t*>(out), pixels, total);
+    }
+  } else {
+    const int grid = (int)std::min<long long>((total + 255) / 256, 148LL * 16);
+    frame_stack_generic_kernel<<<grid, 256, 0, stream>>>(reinterpret_cast<const uint8_t*>(prev),
+                                                        reinterpret_cast<const uint8_t*>(frame),
+                                                        reinterpret_cast<const uint8_t*>(news),
+                                                        reinterpret_cast<uint8_t*>(out), pixels, total, K, c);
+  }
+  return check_launch("frame_stack_kernel");
 }
 
 int s2d_gather_impl(const void* x, const long long* src_idx, void* out, long long B, int H, int W, int C, int s,

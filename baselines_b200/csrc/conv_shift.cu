@@ -371,18 +371,18 @@ conv_shift_fwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_cons
       const uint32_t taddr0 = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(as * BN);
 #pragma unroll 1
       for (int c0 = 0; c0 < BN; c0 += 16 * G) {
-        uint4 sv[G][2];
+        uint32_t sv[G][8];
         if (DACT) {
           if (masked && ok) {
 #pragma unroll
             for (int j = 0; j < G; ++j) {
-              const __half* sp = p.saved + sbase + map_coloff(p.smap, c0 + 16 * j);
-              sv[j][0] = __ldg(reinterpret_cast<const uint4*>(sp));
-              sv[j][1] = __ldg(reinterpret_cast<const uint4*>(sp) + 1);
+              ldg256(p.saved + sbase + map_coloff(p.smap, c0 + 16 * j), sv[j]);
             }
           } else {
 #pragma unroll
-            for (int j = 0; j < G; ++j) sv[j][0] = sv[j][1] = make_uint4(0x3c003c00u, 0x3c003c00u, 0x3c003c00u, 0x3c003c00u);
+            for (int j = 0; j < G; ++j)
+#pragma unroll
+              for (int i = 0; i < 8; ++i) sv[j][i] = 0x3c003c00u;
           }
         }
         uint32_t r[G][16];
@@ -395,11 +395,9 @@ conv_shift_fwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_cons
             const int c = c0 + 16 * j;
             uint32_t packed[8];
             if (DACT) {
-              const uint32_t w[8] = {sv[j][0].x, sv[j][0].y, sv[j][0].z, sv[j][0].w,
-                                     sv[j][1].x, sv[j][1].y, sv[j][1].z, sv[j][1].w};
 #pragma unroll
               for (int i = 0; i < 8; ++i) {
-                const float2 h = __half22float2(*reinterpret_cast<const __half2*>(&w[i]));
+                const float2 h = __half22float2(*reinterpret_cast<const __half2*>(&sv[j][i]));
                 const float a = (h.x > lo) ? __uint_as_float(r[j][2 * i]) * p.alpha : 0.0f;
                 const float b = (h.y > lo) ? __uint_as_float(r[j][2 * i + 1]) * p.alpha : 0.0f;
                 const __half2 o = __floats2half2_rn(a, b);
@@ -414,9 +412,7 @@ conv_shift_fwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_cons
                 packed[i] = *reinterpret_cast<const uint32_t*>(&o);
               }
             }
-            uint4* dst = reinterpret_cast<uint4*>(p.out + obase + map_coloff(p.omap, c));
-            dst[0] = make_uint4(packed[0], packed[1], packed[2], packed[3]);
-            dst[1] = make_uint4(packed[4], packed[5], packed[6], packed[7]);
+            stg256(p.out + obase + map_coloff(p.omap, c), packed);
           }
         }
       }
@@ -704,6 +700,12 @@ int conv_shift_fwd_impl(const void* X, long long B, int Hg, int Wg, int C, const
   p.saved = reinterpret_cast<const __half*>(saved);
   if (smap) B200RL_REQUIRE(fill_map(p.smap, smap), "conv_shift_fwd: saved map needs power-of-two Cq >= 16 and s");
   B200RL_REQUIRE(!(saved && !smap), "conv_shift_fwd: saved needs smap");
+  // the epilogue moves 16 fp16 columns per lane with one 256-bit access
+  B200RL_REQUIRE(((omap[1] | omap[2] | omap[3]) & 15) == 0 && (reinterpret_cast<uintptr_t>(out) & 31) == 0,
+                 "conv_shift_fwd: output strides must be multiples of 16 elements, base 32-byte aligned");
+  if (saved)
+    B200RL_REQUIRE(((smap[1] | smap[2] | smap[3]) & 15) == 0 && (reinterpret_cast<uintptr_t>(saved) & 31) == 0,
+                   "conv_shift_fwd: saved strides must be multiples of 16 elements, base 32-byte aligned");
   p.bias = bias; p.act = act; p.dact = dact; p.alpha = alpha;
   p.num_tiles = (int)((p.M + SH_BM - 1) / SH_BM);
   p.u8 = make_u8src(u8_x, u8_idx, u8_H, u8_W, u8_C, u8_s);

@@ -58,6 +58,7 @@ struct GemmParams {
   int mode, act;
   ConvCoords cv;
   ShuffleOut sh;
+  bool vec32;               // f16 epilogue rows/columns are 32-byte aligned: 256-bit loads / stores
   int rm_C, rm_OW, rm_Wg;   // rm_C > 0: output column (pix*rm_C + c) is stored at ((pix/rm_OW)*rm_Wg + pix%rm_OW)*rm_C + c
 };
 
@@ -340,7 +341,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                 for (int i = 0; i < 16; ++i) v[i] = fmaxf(v[i], lo);
               }
             } else {  // MODE_F16_DACT: dX = (dY W^T) * act'(saved activation)
-              mask16(v, p.saved + (long long)row * p.ld_saved + col0, full && ((p.ld_saved & 7) == 0), nvalid, p.act);
+              mask16(v, p.saved + (long long)row * p.ld_saved + col0, full && p.vec32, nvalid, p.act);
             }
             int ocol = col0;
             if (p.rm_C > 0) {
@@ -348,7 +349,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
               ocol = ((pix / p.rm_OW) * p.rm_Wg + pix % p.rm_OW) * p.rm_C + col0 % p.rm_C;
             }
             store16_f16(v, reinterpret_cast<__half*>(p.C) + (long long)row * p.ldc + ocol,
-                        full && ((p.ldc & 7) == 0), nvalid);
+                        full && p.vec32, nvalid);
           }
         }
       }
@@ -510,6 +511,8 @@ int gemm_f16_impl(const void* A, const void* B, void* C, const float* bias, cons
   p.C = C; p.ldc = ldc; p.bias = bias; p.saved = reinterpret_cast<const __half*>(saved); p.ld_saved = ld_saved;
   p.alpha = alpha; p.mode = mode; p.act = act;
   p.rm_C = rm_C; p.rm_OW = rm_OW; p.rm_Wg = rm_Wg;
+  p.vec32 = ((ldc & 15) == 0) && ((reinterpret_cast<uintptr_t>(C) & 31) == 0) && (rm_C == 0 || (rm_C & 15) == 0) &&
+            (!saved || (((ld_saved & 15) == 0) && ((reinterpret_cast<uintptr_t>(saved) & 31) == 0)));
 
   CUtensorMap tmA, tmB;
   int rc;
@@ -596,6 +599,12 @@ int conv_gemm_impl(const void* x, long long B, int H, int W, int C, int R, int S
   p.cv.OW = OW; p.cv.OH = OH; p.cv.stride_w = stride_w; p.cv.stride_h = stride_h;
   p.cv.lower_w = lower_w; p.cv.lower_h = lower_h; p.cv.S = S; p.cv.taps = taps;
   p.sh.H = sh_H; p.sh.W = sh_W; p.sh.C = sh_C; p.sh.s = sh_s;
+  p.vec32 = ((ldc & 15) == 0) && ((reinterpret_cast<uintptr_t>(out) & 31) == 0) &&
+            (!saved || (((ld_saved & 15) == 0) && ((reinterpret_cast<uintptr_t>(saved) & 31) == 0)));
+  if (mode == MODE_F16_SHUFFLE)
+    B200RL_REQUIRE((sh_C & 15) == 0 && (reinterpret_cast<uintptr_t>(out) & 31) == 0 &&
+                       (!saved || (reinterpret_cast<uintptr_t>(saved) & 31) == 0),
+                   "conv_gemm: shuffle epilogue needs C %% 16 == 0 and 32-byte aligned tensors");
   CUtensorMap tmA, tmB;
   int rc;
   if (kind == 0) {

@@ -38,21 +38,29 @@ __device__ __forceinline__ float act_grad_from_saved(float h, int act) {
   return 1.0f;
 }
 
-// v[16] *= act'(saved[0..16)) with 16-byte loads when aligned
+// 256-bit global accesses (sm_100: LDG/STG.E.256): one full 32-byte sector per lane and half the LSU instructions
+// of two 128-bit accesses.  The address must be 32-byte aligned.
+__device__ __forceinline__ void ldg256(const void* p, uint32_t (&w)[8]) {
+  asm volatile("ld.global.nc.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(w[0]), "=r"(w[1]), "=r"(w[2]), "=r"(w[3]), "=r"(w[4]), "=r"(w[5]), "=r"(w[6]), "=r"(w[7])
+               : "l"(p));
+}
+__device__ __forceinline__ void stg256(void* p, const uint32_t (&w)[8]) {
+  asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "r"(w[0]), "r"(w[1]), "r"(w[2]), "r"(w[3]),
+               "r"(w[4]), "r"(w[5]), "r"(w[6]), "r"(w[7])
+               : "memory");
+}
+
+// v[16] *= act'(saved[0..16)); vec: one 32-byte load (sv 32-byte aligned)
 __device__ __forceinline__ void mask16(float (&v)[16], const __half* sv, bool vec, int nvalid, int act) {
   if (vec) {
-    uint4 q0 = *reinterpret_cast<const uint4*>(sv);
-    uint4 q1 = *reinterpret_cast<const uint4*>(sv + 8);
-    const __half2* h0 = reinterpret_cast<const __half2*>(&q0);
-    const __half2* h1 = reinterpret_cast<const __half2*>(&q1);
+    uint32_t w[8];
+    ldg256(sv, w);
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      float2 f = __half22float2(h0[i]);
+    for (int i = 0; i < 8; ++i) {
+      const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&w[i]));
       v[2 * i] *= act_grad_from_saved(f.x, act);
       v[2 * i + 1] *= act_grad_from_saved(f.y, act);
-      float2 g = __half22float2(h1[i]);
-      v[8 + 2 * i] *= act_grad_from_saved(g.x, act);
-      v[8 + 2 * i + 1] *= act_grad_from_saved(g.y, act);
     }
   } else {
 #pragma unroll
@@ -62,16 +70,13 @@ __device__ __forceinline__ void mask16(float (&v)[16], const __half* sv, bool ve
 }
 __device__ __forceinline__ void store16_f16(const float (&v)[16], __half* out, bool vec, int nvalid) {
   if (vec) {
-    uint4 q0, q1;
-    __half2* h0 = reinterpret_cast<__half2*>(&q0);
-    __half2* h1 = reinterpret_cast<__half2*>(&q1);
+    uint32_t w[8];
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      h0[i] = __floats2half2_rn(v[2 * i], v[2 * i + 1]);
-      h1[i] = __floats2half2_rn(v[8 + 2 * i], v[8 + 2 * i + 1]);
+    for (int i = 0; i < 8; ++i) {
+      const __half2 h = __floats2half2_rn(v[2 * i], v[2 * i + 1]);
+      w[i] = *reinterpret_cast<const uint32_t*>(&h);
     }
-    *reinterpret_cast<uint4*>(out) = q0;
-    *reinterpret_cast<uint4*>(out + 8) = q1;
+    stg256(out, w);
   } else {
 #pragma unroll
     for (int i = 0; i < 16; ++i)

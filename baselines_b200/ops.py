@@ -145,6 +145,18 @@ def im2col(x, cols, B, H, W, C, rf, stride, same_pad=False, src_idx=None, tag=No
               nbytes=float(B) * H * W * C * (1 if src_u8 else 2) + 2.0 * B * OH * OW * rf * rf * C)
 
 
+def frame_stack(prev, frame, news, out, nstack, c):
+    """out = VecFrameStack update of prev with the new frames (vec_frame_stack.py:17-25); uint8 [N, ..., nstack*c]."""
+    for t, nm in ((prev, "prev"), (frame, "frame"), (news, "news"), (out, "out")):
+        _chk(t, torch.uint8, nm)
+    N = out.shape[0]
+    pixels = out[0].numel() // (nstack * c)
+    if prev.numel() != out.numel() or frame.numel() != N * pixels * c or news.numel() != N:
+        raise RuntimeError("frame_stack: shape mismatch")
+    _lib.call("b200rl_frame_stack", _ptr(prev), _ptr(frame), _ptr(news), _ptr(out), int(N), int(pixels), int(nstack),
+              int(c), _stream(), label="frame_stack", nbytes=float(2 * out.numel() + frame.numel()))
+
+
 def s2d_gather(x, out, B, H, W, C, s, src_idx=None):
     _chk(x, torch.uint8, "x")
     _chk(out, torch.float16, "out")

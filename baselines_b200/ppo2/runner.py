@@ -85,8 +85,20 @@ class Runner:
                                                            device=self.device)
         self._cur = torch.zeros((nenv,) + store_shape, dtype=self.rollout.obs.dtype, device=self.device)
         self._obs_src = None
+        # VecFrameStack on the device: only the new frames cross PCIe, the stack lives in the rollout buffer
+        self.fs = bool(getattr(env, "frame_stack_device", False)) and self.u8 and not self.device_env and pin
         if self.device_env:
             self._dev_obs = env.reset_device()
+        elif self.fs:
+            c = env.frame_channels
+            fshape = (nenv,) + tuple(ob_space.shape[:-1]) + (c,)
+            self._frame_pin = torch.zeros(fshape, dtype=torch.uint8).pin_memory()
+            self._frame_dev = torch.zeros(fshape, dtype=torch.uint8, device=self.device)
+            self._news_pin = torch.ones(nenv, dtype=torch.uint8).pin_memory()
+            self._news_dev = torch.zeros(nenv, dtype=torch.uint8, device=self.device)
+            self._zero_obs = torch.zeros_like(self._cur)
+            # reset(): stack = 0, newest slot = first frame  (vec_frame_stack.py:27-31)
+            self._stack_frames(env.reset_frames(), np.ones(nenv, dtype=np.bool_), self._zero_obs, self._cur)
         else:
             self._take_obs(env.reset())                                        # runners.py:11
         self.states = model.initial_state
@@ -104,6 +116,20 @@ class Runner:
             self._obs_src = None
             self.obs = self._obs_pin.numpy()
             self.obs[:] = obs
+
+    def _stack_frames(self, frames, news, prev, out):
+        """out = VecFrameStack.step_wait update (vec_frame_stack.py:17-25) of the stacked observation `prev` with
+        the freshly stepped frames; frames and the done flags are the only host->device traffic."""
+        t = torch.from_numpy(frames) if isinstance(frames, np.ndarray) and frames.flags.c_contiguous else None
+        if t is not None and t.dtype == torch.uint8 and t.shape == self._frame_pin.shape and t.is_pinned():
+            src = t
+        else:
+            self._frame_pin.numpy()[...] = frames
+            src = self._frame_pin
+        self._frame_dev.copy_(src, non_blocking=True)
+        self._news_pin.numpy()[...] = np.asarray(news, dtype=np.uint8)
+        self._news_dev.copy_(self._news_pin, non_blocking=True)
+        ops.frame_stack(prev, self._frame_dev, self._news_dev, out, self.env.nstack, self.env.frame_channels)
 
     # -- stage the current observation into `dst` (rollout.obs[t] or a temp) in the network's input format
     def _upload_obs(self, dst):
@@ -131,8 +157,11 @@ class Runner:
         epinfos = []
         with torch.cuda.device(self.device):
             nz = None if noise is None else torch.as_tensor(np.ascontiguousarray(noise), dtype=torch.float32).to(self.device)
+            if self.fs:
+                ro.obs[0].copy_(self._cur)
             for t in range(T):
-                self._upload_obs(ro.obs[t])
+                if not self.fs:
+                    self._upload_obs(ro.obs[t])
                 model.step_device(ro.obs[t], ro.actions[t], ro.values[t], ro.neglogpacs[t],
                                   noise=None if nz is None else nz[t])
                 if self.device_env:
@@ -144,16 +173,22 @@ class Runner:
                 self._act_pin.copy_(ro.actions[t], non_blocking=True)
                 torch.cuda.current_stream().synchronize()
                 actions = self._act_pin.numpy()
-                obs, rewards, self.dones, infos = self.env.step(actions)                 # runner.py:38
-                self._take_obs(obs)
-                self.dones = np.asarray(self.dones, dtype=np.bool_)
+                if self.fs:
+                    frames, rewards, self.dones, infos = self.env.step_frames(actions)
+                    self.dones = np.asarray(self.dones, dtype=np.bool_)
+                    self._stack_frames(frames, self.dones, ro.obs[t], ro.obs[t + 1] if t + 1 < T else self._cur)
+                else:
+                    obs, rewards, self.dones, infos = self.env.step(actions)             # runner.py:38
+                    self._take_obs(obs)
+                    self.dones = np.asarray(self.dones, dtype=np.bool_)
                 for info in infos:
                     maybeepinfo = info.get('episode') if info else None
                     if maybeepinfo:
                         epinfos.append(maybeepinfo)
                 self._rew_host[t] = torch.from_numpy(np.asarray(rewards, dtype=np.float32))
             # bootstrap value of the final observation (runner.py:50)
-            self._upload_obs(self._cur)
+            if not self.fs:
+                self._upload_obs(self._cur)
             model.value_device(self._cur, ro.last_values)
             if self.device_env:
                 ro.last_dones.copy_(self._dev_dones)

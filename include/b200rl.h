@@ -95,6 +95,13 @@ int b200rl_dgrad_weights(const float* w, void* out, int R, int S, int Cin, int C
 int b200rl_im2col(const void* x, int src_is_u8, const long long* src_idx, void* cols, long long B, int H, int W,
                   int C, int rf, int stride, int same_pad, void* stream);
 /* gather + uint8->fp16 + space-to-depth: out[b,Y,X,(dy*s+dx)*C+c] = x[src_idx[b], s*Y+dy, s*X+dx, c] */
+/* Device half of VecFrameStack.step_wait (common/vec_env/vec_frame_stack.py:17-25): for N envs of `pixels` pixels,
+ * out[n, p, :] = roll(prev[n, p, :], -1) (one channel, as the reference does); zeroed where news[n]; the last c
+ * bytes = frame[n, p, :].
+ * uint8 tensors: prev/out [N, pixels, nstack*c], frame [N, pixels, c], news [N].  out must not alias prev. */
+int b200rl_frame_stack(const void* prev, const void* frame, const void* news, void* out, long long N, long long pixels,
+                       int nstack, int c, void* stream);
+
 int b200rl_s2d_gather(const void* x, const long long* src_idx, void* out, long long B, int H, int W, int C, int s,
                       void* stream);
 int b200rl_col2im(const void* dcols, const void* saved, void* dx, long long B, int H, int W, int C, int rf,

@@ -105,6 +105,71 @@ def gen_gae(Runner, name, T, N, seed, p_done, nrollouts=1):
     return out
 
 
+def _import_reference_frame_stack():
+    """vec_frame_stack.py needs `gym.spaces.Box` (third-party, absent here): a 4-attribute stand-in is put into the
+    gym stub.  The package __init__ (which drags in gym.core via VecMonitor) is bypassed by loading the two files
+    under a synthetic package so the relative import `.vec_env` still resolves."""
+    gym = sys.modules.setdefault("gym", types.ModuleType("gym"))
+    sp = types.ModuleType("gym.spaces")
+
+    class Box:
+        def __init__(self, low, high, shape=None, dtype=np.float32):
+            self.low, self.high, self.dtype = np.asarray(low), np.asarray(high), np.dtype(dtype)
+            self.shape = self.low.shape
+
+    sp.Box = Box
+    gym.spaces = sp
+    sys.modules["gym.spaces"] = sp
+    d = os.path.join(REF, "baselines/common/vec_env")
+    pkg = types.ModuleType("refvec")
+    pkg.__path__ = [d]
+    sys.modules["refvec"] = pkg
+    mods = {}
+    for name in ("vec_env", "vec_frame_stack"):
+        spec = importlib.util.spec_from_file_location("refvec." + name, os.path.join(d, name + ".py"))
+        m = importlib.util.module_from_spec(spec)
+        sys.modules["refvec." + name] = m
+        spec.loader.exec_module(m)
+        mods[name] = m
+    return mods["vec_frame_stack"].VecFrameStack, Box
+
+
+def gen_frame_stack():
+    """Drive the reference VecFrameStack with a scripted venv: random frames, scripted episode ends."""
+    VecFrameStack, Box = _import_reference_frame_stack()
+    for name, N, hw, c, nstack, T, p_done, seed in (("frame_stack_c1.npz", 5, (6, 4), 1, 4, 12, 0.2, 11),
+                                                    ("frame_stack_c2.npz", 3, (3, 5), 2, 3, 9, 0.3, 12)):
+        rng = np.random.RandomState(seed)
+        frames = rng.randint(0, 256, size=(T + 1, N) + hw + (c,)).astype(np.uint8)
+        news = rng.rand(T, N) < p_done
+
+        class Venv:
+            num_envs = N
+            observation_space = Box(np.zeros(hw + (c,), np.uint8), np.full(hw + (c,), 255, np.uint8), dtype=np.uint8)
+            action_space = None
+            t = 0
+
+            def reset(self):
+                self.t = 0
+                return frames[0]
+
+            def step_async(self, actions):
+                pass
+
+            def step_wait(self):
+                self.t += 1
+                return frames[self.t], np.zeros(N, np.float32), news[self.t - 1], [{}] * N
+
+        env = VecFrameStack(Venv(), nstack)
+        out = [env.reset().copy()]
+        for t in range(T):
+            env.step_async(None)
+            o, _, _, _ = env.step_wait()
+            out.append(o.copy())
+        np.savez_compressed(os.path.join(OUT, name), frames=frames, news=news, stacked=np.stack(out),
+                            nstack=nstack, c=c)
+
+
 def gen_segment_tree(Sum, Min):
     rng = np.random.RandomState(7)
     cap = 64
@@ -191,6 +256,7 @@ def main():
     gen_gae(Runner, "gae_alldone.npz", T=6, N=4, seed=3, p_done=1.1)
     gen_segment_tree(Sum, Min)
     gen_per(rb)
+    gen_frame_stack()
     print("golden fixtures written to", OUT)
 
 

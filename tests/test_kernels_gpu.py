@@ -740,3 +740,41 @@ def test_conv_shift_fused_uint8_source(ops, B, gather):
     assert scale > 0
     assert float((G_ref - G_u8).abs().max()) <= 1e-5 * scale + 1e-3, float((G_ref - G_u8).abs().max())
     assert torch.allclose(gb_ref, gb_u8, atol=1e-3, rtol=1e-5)
+
+
+@pytest.mark.parametrize("name", ["frame_stack_c1.npz", "frame_stack_c2.npz"])
+def test_frame_stack_kernel_matches_reference_golden(ops, name):
+    """b200rl_frame_stack against outputs of the reference VecFrameStack (golden) -- bit exact."""
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", name))
+    frames, news, want = g["frames"], g["news"], g["stacked"]
+    nstack, c = int(g["nstack"]), int(g["c"])
+    cur = torch.zeros(want.shape[1:], dtype=torch.uint8, device="cuda")
+    nxt = torch.empty_like(cur)
+    ops.frame_stack(cur, torch.from_numpy(frames[0]).cuda(), torch.ones(want.shape[1], dtype=torch.uint8, device="cuda"),
+                    nxt, nstack, c)
+    assert np.array_equal(nxt.cpu().numpy(), want[0])
+    for t in range(news.shape[0]):
+        cur, nxt = nxt, cur
+        ops.frame_stack(cur, torch.from_numpy(frames[t + 1]).cuda(), torch.from_numpy(news[t].astype(np.uint8)).cuda(),
+                        nxt, nstack, c)
+        assert np.array_equal(nxt.cpu().numpy(), want[t + 1]), t
+
+
+def test_frame_stack_kernel_atari_shape_vs_oracle(ops):
+    """84x84x(4x1) at 64 envs (vectorised 4-pixel path) and an unaligned view (scalar word path) vs the oracle."""
+    from oracle import frame_stack as fs
+    rng = np.random.RandomState(0)
+    N = 64
+    prev = rng.randint(0, 256, (N, 84, 84, 4)).astype(np.uint8)
+    frames = rng.randint(0, 256, (N, 84, 84, 1)).astype(np.uint8)
+    news = rng.rand(N) < 0.3
+    want = fs.frame_stack_step(prev, frames, news)
+    out = torch.empty(N, 84, 84, 4, dtype=torch.uint8, device="cuda")
+    ops.frame_stack(torch.from_numpy(prev).cuda(), torch.from_numpy(frames).cuda(),
+                    torch.from_numpy(news.astype(np.uint8)).cuda(), out, 4, 1)
+    assert np.array_equal(out.cpu().numpy(), want)
+    big = torch.empty(N * 84 * 84 * 4 + 4, dtype=torch.uint8, device="cuda")
+    out2 = big[4:].view(N, 84, 84, 4)                      # 4-byte but not 16-byte aligned
+    ops.frame_stack(torch.from_numpy(prev).cuda(), torch.from_numpy(frames).cuda(),
+                    torch.from_numpy(news.astype(np.uint8)).cuda(), out2, 4, 1)
+    assert np.array_equal(out2.cpu().numpy(), want)

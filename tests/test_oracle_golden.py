@@ -145,3 +145,47 @@ def test_per_ptotal_quirk():
         per.add()
     assert per.sum_tree.sum(0, per.n - 1) == float(g["p_total_used"]) == 3.0
     assert per.sum_tree.sum() == float(g["full_sum"]) == 4.0
+
+
+@pytest.mark.parametrize("name", ["frame_stack_c1.npz", "frame_stack_c2.npz"])
+def test_frame_stack_oracle_matches_reference(name):
+    """oracle.frame_stack vs outputs of the reference VecFrameStack (vec_frame_stack.py) on a scripted venv."""
+    from oracle import frame_stack as fs
+    g = np.load(os.path.join(GOLDEN, name))
+    frames, news, want = g["frames"], g["news"], g["stacked"]
+    cur = fs.frame_stack_reset(frames[0], int(g["nstack"]))
+    assert np.array_equal(cur, want[0])
+    for t in range(news.shape[0]):
+        cur = fs.frame_stack_step(cur, frames[t + 1], news[t])
+        assert np.array_equal(cur, want[t + 1]), t
+
+
+def test_host_vec_frame_stack_matches_reference():
+    """baselines_b200.common.vec_env.VecFrameStack (host path) reproduces the reference outputs."""
+    from baselines_b200.common import spaces
+    from baselines_b200.common.vec_env import VecEnv, VecFrameStack
+    g = np.load(os.path.join(GOLDEN, "frame_stack_c1.npz"))
+    frames, news, want = g["frames"], g["news"], g["stacked"]
+
+    class Scripted(VecEnv):
+        def __init__(self):
+            super().__init__(frames.shape[1], spaces.Box(0, 255, frames.shape[2:], np.uint8), spaces.Discrete(2))
+            self.t = 0
+
+        def reset(self):
+            self.t = 0
+            return frames[0]
+
+        def step_async(self, actions):
+            pass
+
+        def step_wait(self):
+            self.t += 1
+            return frames[self.t], np.zeros(self.num_envs, np.float32), news[self.t - 1], [{}] * self.num_envs
+
+    env = VecFrameStack(Scripted(), int(g["nstack"]))
+    assert env.observation_space.shape == want.shape[2:]
+    assert np.array_equal(env.reset(), want[0])
+    for t in range(news.shape[0]):
+        o, _, d, _ = env.step(None)
+        assert np.array_equal(o, want[t + 1]) and np.array_equal(d, news[t])

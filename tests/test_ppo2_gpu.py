@@ -299,3 +299,52 @@ def test_save_load_roundtrip(tmp_path):
     obs = _obs(rng, case, 8)
     assert np.array_equal(model.value(obs), model2.value(obs))
     assert model2.opt.t == model.opt.t
+
+
+def test_runner_device_frame_stack_equals_host_stacked_upload():
+    """VecFrameStack handled on the device (new frames uploaded, stack kept in the rollout buffer) must give the
+    same rollout, bit for bit, as uploading the reference-style host-stacked observations."""
+    from baselines_b200.common import spaces
+    from baselines_b200.common.vec_env import VecEnv, VecFrameStack
+    from baselines_b200.ppo2.runner import Runner
+    case = CASES["cnn_cat"]
+    T, N = 6, 8
+    env0, model, _ = _mk(nenv=N, nsteps=T, nminibatches=1, **case)
+    rng = np.random.RandomState(3)
+    frames = rng.randint(0, 256, (2 * T + 1, N, 84, 84, 1)).astype(np.uint8)
+    rew = rng.randn(2 * T, N).astype(np.float32)
+    done = rng.rand(2 * T, N) < 0.3
+
+    class Scripted(VecEnv):
+        def __init__(self):
+            super().__init__(N, spaces.Box(0, 255, (84, 84, 1), np.uint8), env0.action_space)
+            self.t = 0
+
+        def reset(self):
+            self.t = 0
+            return frames[0]
+
+        def step_async(self, actions):
+            pass
+
+        def step_wait(self):
+            r, d = rew[self.t], done[self.t]
+            self.t += 1
+            return frames[self.t], r, d, [{} for _ in range(N)]
+
+    noise = rng.rand(2, T, N, 6).astype(np.float32) * 0.98 + 0.01
+    outs = []
+    for device_stack in (True, False):
+        env = VecFrameStack(Scripted(), 4)
+        if not device_stack:
+            env.frame_stack_device = False                 # force the host np.roll path + full upload
+        runner = Runner(env=env, model=model, nsteps=T, gamma=0.99, lam=0.95)
+        assert runner.fs == device_stack
+        res = []
+        for k in range(2):
+            o, ret, masks, act, val, nlp, _, _ = runner.run(noise=noise[k])
+            res.append((o.copy(), ret.copy(), masks.copy(), act.copy(), val.copy(), nlp.copy()))
+        outs.append(res)
+    for a, b in zip(*outs):
+        for x, y in zip(a, b):
+            assert np.array_equal(x, y)
