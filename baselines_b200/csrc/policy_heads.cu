@@ -101,44 +101,48 @@ gauss_step_kernel(const float* __restrict__ mean, long long ld, const float* __r
   values[b] = vpred[b * ldv];
 }
 
-// ---------------------------------------------------------------- advantage moments (two pass, one block)
+// ---------------------------------------------------------------- advantage moments (one block, fp64)
+// One block keeps the summation order fixed (deterministic).  The gathers are dependent loads (index -> returns,
+// values), so each thread keeps 8 of them in flight; sum and sum of squares are accumulated together in fp64
+// (inputs are fp32 differences of O(1): E[x^2] - mean^2 in fp64 loses nothing that fp32 numpy would have kept).
 __global__ void __launch_bounds__(1024)
 adv_stats_kernel(const float* __restrict__ returns, const float* __restrict__ values,
                  const long long* __restrict__ src_idx, long long M, double* __restrict__ out) {
-  __shared__ double red[32];
-  __shared__ double s_mean;
+  __shared__ double red[2][32];
   const int tid = threadIdx.x;
-  double acc = 0.0;
-  for (long long i = tid; i < M; i += blockDim.x) {
-    const long long s = src_idx ? src_idx[i] : i;
-    acc += (double)__fsub_rn(returns[s], values[s]);          // float32 subtraction (model.py:136)
+  constexpr int U = 8;
+  double s1 = 0.0, s2 = 0.0;
+  for (long long i0 = tid; i0 < M; i0 += (long long)blockDim.x * U) {
+    float d[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const long long i = i0 + (long long)u * blockDim.x;
+      d[u] = 0.0f;
+      if (i < M) {
+        const long long s = src_idx ? src_idx[i] : i;
+        d[u] = __fsub_rn(returns[s], values[s]);                 // float32 subtraction (model.py:136)
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      s1 += (double)d[u];
+      s2 += (double)d[u] * (double)d[u];
+    }
   }
-  acc = warp_sum_d(acc);
-  if ((tid & 31) == 0) red[tid >> 5] = acc;
+  s1 = warp_sum_d(s1);
+  s2 = warp_sum_d(s2);
+  if ((tid & 31) == 0) { red[0][tid >> 5] = s1; red[1][tid >> 5] = s2; }
   __syncthreads();
   if (tid < 32) {
-    double v = (tid < (blockDim.x >> 5)) ? red[tid] : 0.0;
-    v = warp_sum_d(v);
-    if (tid == 0) s_mean = v / (double)M;
-  }
-  __syncthreads();
-  const double mean = s_mean;
-  acc = 0.0;
-  for (long long i = tid; i < M; i += blockDim.x) {
-    const long long s = src_idx ? src_idx[i] : i;
-    const double dlt = (double)__fsub_rn(returns[s], values[s]) - mean;
-    acc += dlt * dlt;
-  }
-  acc = warp_sum_d(acc);
-  __syncthreads();
-  if ((tid & 31) == 0) red[tid >> 5] = acc;
-  __syncthreads();
-  if (tid < 32) {
-    double v = (tid < (blockDim.x >> 5)) ? red[tid] : 0.0;
-    v = warp_sum_d(v);
+    double a = (tid < (blockDim.x >> 5)) ? red[0][tid] : 0.0;
+    double b = (tid < (blockDim.x >> 5)) ? red[1][tid] : 0.0;
+    a = warp_sum_d(a);
+    b = warp_sum_d(b);
     if (tid == 0) {
+      const double mean = a / (double)M;
+      const double var = fmax(b / (double)M - mean * mean, 0.0);
       out[0] = mean;
-      out[1] = sqrt(v / (double)M);                              // population std (numpy default ddof=0)
+      out[1] = sqrt(var);                                          // population std (numpy default ddof=0)
     }
   }
 }

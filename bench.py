@@ -317,17 +317,31 @@ def main():
             k["share"] = k["ms_per_step"] / tot if tot else 0.0
         top = max(kernels, key=lambda k: kernels[k]["ms_per_step"])
         tk = kernels[top]
+        # the kernel is judged against the roof it sits closer to: algorithmic flops vs the measured dense-bf16
+        # throughput, algorithmic bytes vs the measured HBM copy bandwidth (both fractions are kept)
+        n_launch = max(1.0, tk["launches_per_step"])
+        f_tensor = f_hbm = 0.0
         if tk.get("flops_per_step"):
-            ach = tk["flops_per_step"] / (tk["ms_per_step"] / 1e3) / 1e12
-            peak = peaks["bf16_tflops_sustained"]
-            roofline = {"kernel": top, "bound": "tensor", "achieved": ach, "peak": peak, "unit": "TFLOP/s",
-                        "frac": ach / peak, "traffic": None, "peak_src": peaks["src"] + " (sustained cuBLAS bf16)",
-                        "share_of_step": tk["share"]}
+            f_tensor = tk["flops_per_step"] / (tk["ms_per_step"] / 1e3) / 1e12 / peaks["bf16_tflops_sustained"]
+        if tk.get("bytes_per_step"):
+            f_hbm = tk["bytes_per_step"] / (tk["ms_per_step"] / 1e3) / 1e9 / peaks["hbm_gbs"]
+        traffic = None
+        tj = os.path.join(ROOT, "profiles", "traffic.json")       # ncu --set full dram bytes, per algorithmic byte
+        if os.path.exists(tj):
+            t = json.load(open(tj)).get(top)
+            if t and tk.get("bytes_per_step"):
+                traffic = t["dram_bytes_per_algorithmic_byte"] * tk["bytes_per_step"] / n_launch
+        if f_tensor >= f_hbm:
+            roofline = {"kernel": top, "bound": "tensor", "achieved": f_tensor * peaks["bf16_tflops_sustained"],
+                        "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s", "frac": f_tensor,
+                        "peak_src": peaks["src"] + " (sustained cuBLAS bf16)"}
         else:
-            ach = tk["bytes_per_step"] / (tk["ms_per_step"] / 1e3) / 1e9
-            roofline = {"kernel": top, "bound": "hbm", "achieved": ach, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                        "frac": ach / peaks["hbm_gbs"], "traffic": None, "peak_src": peaks["src"],
-                        "share_of_step": tk["share"]}
+            roofline = {"kernel": top, "bound": "hbm", "achieved": f_hbm * peaks["hbm_gbs"], "peak": peaks["hbm_gbs"],
+                        "unit": "GB/s", "frac": f_hbm, "peak_src": peaks["src"] + " (sustained copy)"}
+        roofline.update({"traffic": traffic, "algorithmic_bytes_per_launch": tk.get("bytes_per_step", 0.0) / n_launch,
+                         "algorithmic_flops_per_launch": tk.get("flops_per_step", 0.0) / n_launch,
+                         "frac_tensor": f_tensor, "frac_hbm": f_hbm, "ms_per_launch": tk["ms_per_step"] / n_launch,
+                         "share_of_step": tk["share"]})
 
     cpu_baseline = None
     if not args.no_cpu_baseline:
