@@ -363,6 +363,9 @@ def main():
                                 "note": "8.9 MB: L2-resident / launch-bound, not an HBM measurement"},
                    "fc1": [{"kind": c["kind"], "M": c["M"], "tflops": c["tflops"], "peak": peaks["bf16_tflops"],
                             "frac": c["tflops"] / peaks["bf16_tflops"], "target": 0.5} for c in mb["fc1"]],
+                   "gae_cpu_numpy": mb.get("gae_cpu"),          # reference numpy loop (oracle port), host, same sizes
+                   "per_cfg4": mb.get("per"),                   # PER sample/update at capacity 2^20 vs the python port
+                   "dqn_cfg4": mb.get("dqn"),                   # one deepq train step at batch 512
                    "how": mb["l2_flush"] + "; CUDA events per launch, median of 10 after 3 warm-ups"}
     except Exception as ex:                                    # never lose the headline line to an extra
         targets = {"error": repr(ex)}

@@ -73,6 +73,87 @@ def fc1_case(M, kind, flush, K=3136, N=512):
             "tflops": flops / (med * 1e-3) / 1e12}
 
 
+def gae_cpu_case(T, N):
+    """The reference's numpy GAE loop (ppo2/runner.py:53-65, restated in oracle/gae.py) on the host, same sizes."""
+    import time
+    from oracle.gae import gae_reference_order
+    rng = np.random.RandomState(0)
+    rew, val = rng.randn(T, N).astype(np.float32), rng.randn(T, N).astype(np.float32)
+    done = rng.rand(T, N) < 0.01
+    lv, ld = rng.randn(N).astype(np.float32), np.zeros(N, dtype=np.bool_)
+    gae_reference_order(rew[:8], val[:8], done[:8], lv, ld, 0.99, 0.95)
+    t0 = time.perf_counter()
+    gae_reference_order(rew, val, done, lv, ld, 0.99, 0.95)
+    ms = (time.perf_counter() - t0) * 1e3
+    return {"T": T, "N": N, "ms": ms, "gbs": (17.0 * T * N + 5.0 * N) / (ms * 1e-3) / 1e9, "kind": "port (numpy, 1 thread)"}
+
+
+def per_case(flush, cap=1 << 20, batch=512, alpha=0.6, beta=0.4):
+    """cfg-4: prioritized replay at capacity 2^20 -- stratified sample of 512 + importance weights, and the
+    2 x 512 priority writes of one train step (replay_buffer.py:107-115,157-165,169-191); the CPU leg is the
+    oracle port of the same arithmetic (oracle/segment_tree.py), trees filled level by level (same node values)."""
+    import random
+    import time
+    from oracle.segment_tree import PrioritizedSampler
+    rng = np.random.RandomState(0)
+    pr = np.abs(rng.randn(cap)) + 1e-6
+    vals = pr ** alpha
+    dev = "cuda"
+    it_sum = torch.zeros(2 * cap, dtype=torch.float64, device=dev)
+    it_min = torch.full((2 * cap,), float("inf"), dtype=torch.float64, device=dev)
+    ops.tree_set(it_sum, it_min, cap, torch.arange(cap, device=dev), torch.from_numpy(vals).to(dev))
+    random.seed(0)
+    u_host = np.array([random.random() for _ in range(batch)])
+    u = torch.from_numpy(u_host).to(dev)
+    idx = torch.empty(batch, dtype=torch.int64, device=dev)
+    w64 = torch.empty(batch, dtype=torch.float64, device=dev)
+    w32 = torch.empty(batch, dtype=torch.float32, device=dev)
+    ms_s, _ = _time(lambda: ops.per_sample(it_sum, it_min, cap, cap, u, beta, idx, w64, w32), flush=flush)
+    newv = torch.from_numpy((np.abs(rng.randn(batch)) + 1e-6) ** alpha).to(dev)
+    torch.cuda.synchronize()
+    upd_idx = idx.clone()
+    ms_u, _ = _time(lambda: ops.tree_set(it_sum, it_min, cap, upd_idx, newv), flush=flush)
+    # CPU port on the same tree
+    ps = PrioritizedSampler(cap, alpha)
+    ps.n = cap
+    for tree, red in ((ps.sum_tree, np.add), (ps.min_tree, np.minimum)):
+        tree.value[cap:] = vals
+        lvl = cap
+        while lvl > 1:
+            half = lvl // 2
+            tree.value[half:lvl] = red(tree.value[lvl:2 * lvl:2], tree.value[lvl + 1:2 * lvl:2])
+            lvl = half
+    t0 = time.perf_counter()
+    ci = ps.sample_idx(list(u_host))
+    cw = ps.weights(ci, beta)
+    t1 = time.perf_counter()
+    ps.update_priorities(ci, list(np.abs(rng.randn(batch)) + 1e-6))
+    t2 = time.perf_counter()
+    same = bool(np.array_equal(np.array(ci), idx.cpu().numpy()) and np.array_equal(cw, w64.cpu().numpy()))
+    return {"capacity": cap, "batch": batch, "gpu_sample_us": ms_s * 1e3, "gpu_update_us": ms_u * 1e3,
+            "cpu_sample_ms": (t1 - t0) * 1e3, "cpu_update_ms": (t2 - t1) * 1e3, "cpu_kind": "port (python, 1 thread)",
+            "bit_exact_vs_port": same}
+
+
+def dqn_case(flush, batch=512):
+    """cfg-4: one deepq train step (build_graph.py:388-430) at batch 512: conv_only + dueling, double-Q -> three
+    forwards, one backward, per-variable clip, Adam; observations gathered from a device-resident buffer."""
+    from baselines_b200.common import spaces
+    from baselines_b200.deepq.build_graph import DQNModel
+    m = DQNModel(spaces.Box(0, 255, (84, 84, 4), np.uint8), 6, "conv_only", lr=1e-4, gamma=0.99, grad_norm_clipping=10,
+                 batch_cap=batch, seed=0, hiddens=(256,), dueling=True)
+    dev = m.device
+    g = torch.Generator(device="cuda").manual_seed(0)
+    o_t = torch.randint(0, 256, (batch, 84, 84, 4), dtype=torch.uint8, device=dev, generator=g)
+    o_1 = torch.randint(0, 256, (batch, 84, 84, 4), dtype=torch.uint8, device=dev, generator=g)
+    act = torch.randint(0, 6, (batch,), device=dev, generator=g)
+    rew = torch.randn(batch, device=dev, generator=g)
+    done = (torch.rand(batch, device=dev, generator=g) < 0.05).float()
+    w = torch.rand(batch, device=dev, generator=g) * 0.9 + 0.1
+    ms, best = _time(lambda: m.train_device(o_t, o_1, act, rew, done, w, None, batch), flush=flush)
+    return {"batch": batch, "ms": ms, "ms_best": best, "transitions_per_s": batch / (ms * 1e-3)}
+
+
 def run(only=None, quick=False):
     flush = torch.empty(128 * 1024 * 1024, dtype=torch.float32, device="cuda")      # 512 MB > 126 MB L2
     out = {"l2_flush": "512 MB write between iterations"}
@@ -81,6 +162,12 @@ def run(only=None, quick=False):
     if only in (None, "fc1"):
         Ms = [8192, 131072] if not quick else [131072]
         out["fc1"] = [fc1_case(M, k, flush) for M in Ms for k in ("fwd", "dgrad", "wgrad")]
+    if only in (None, "gae"):
+        out["gae_cpu"] = [gae_cpu_case(128, 4096), gae_cpu_case(512, 16384)]
+    if only in (None, "per"):
+        out["per"] = per_case(flush)
+    if only in (None, "dqn"):
+        out["dqn"] = dqn_case(flush)
     return out
 
 
