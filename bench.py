@@ -181,6 +181,7 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-profile", action="store_true", help="skip the per-kernel CUDA-event profile")
+    ap.add_argument("--no-targets", action="store_true", help="skip the stand-alone GAE / fc1 / PER microbenchmarks")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -353,6 +354,8 @@ def main():
 
     targets = None
     try:
+        if args.no_targets:
+            raise RuntimeError("skipped (--no-targets)")
         sys.path.insert(0, os.path.join(ROOT, "tools"))
         import microbench
         mb = microbench.run(quick=True)

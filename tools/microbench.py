@@ -129,10 +129,11 @@ def per_case(flush, cap=1 << 20, batch=512, alpha=0.6, beta=0.4):
     t1 = time.perf_counter()
     ps.update_priorities(ci, list(np.abs(rng.randn(batch)) + 1e-6))
     t2 = time.perf_counter()
-    same = bool(np.array_equal(np.array(ci), idx.cpu().numpy()) and np.array_equal(cw, w64.cpu().numpy()))
+    idx_same = bool(np.array_equal(np.array(ci), idx.cpu().numpy()))     # integer work: must be identical
+    w_err = float(np.max(np.abs(w64.cpu().numpy() - cw) / cw))           # pow() of libm vs CUDA: a few ulps
     return {"capacity": cap, "batch": batch, "gpu_sample_us": ms_s * 1e3, "gpu_update_us": ms_u * 1e3,
             "cpu_sample_ms": (t1 - t0) * 1e3, "cpu_update_ms": (t2 - t1) * 1e3, "cpu_kind": "port (python, 1 thread)",
-            "bit_exact_vs_port": same}
+            "indices_equal_port": idx_same, "weights_max_rel_err_vs_port": w_err}
 
 
 def dqn_case(flush, batch=512):
