@@ -171,6 +171,9 @@ def run_reference(args):
 
 # ---------------------------------------------------------------------------------------------- our arm
 def main():
+    # some images export NCCL_DEBUG=VERSION, which prints a banner on stdout next to the JSON line
+    if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
+        os.environ["NCCL_DEBUG"] = "WARN"
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=3)
