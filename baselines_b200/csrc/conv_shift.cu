@@ -229,6 +229,8 @@ struct ShiftParams {
   __half* out;
   AddrMap omap;
   const __half* saved;
+  uint16_t* bits_out;           // optional (forward): bit k of word e/16 = (out element e + k) > 0, e = element offset
+  const uint16_t* saved_bits;   // optional (DACT): the same bit array of the saved activation, read instead of `saved`
   AddrMap smap;
   const float* bias;
   int act, dact;           // dact = 1: multiply by act'(saved) instead of applying act
@@ -373,7 +375,19 @@ conv_shift_fwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_cons
       for (int c0 = 0; c0 < BN; c0 += 16 * G) {
         uint32_t sv[G][8];
         if (DACT) {
-          if (masked && ok) {
+          if (masked && ok && p.saved_bits != nullptr) {
+            // 1 bit per element instead of the fp16 activation: 2 B instead of 32 B of HBM traffic per 16 columns;
+            // expanded to the half2 words {1.0 | 0.0} the mask code below expects
+            uint32_t bw[G];
+#pragma unroll
+            for (int j = 0; j < G; ++j)
+              bw[j] = __ldg(p.saved_bits + ((sbase + map_coloff(p.smap, c0 + 16 * j)) >> 4));
+#pragma unroll
+            for (int j = 0; j < G; ++j)
+#pragma unroll
+              for (int i = 0; i < 8; ++i)
+                sv[j][i] = (((bw[j] >> (2 * i)) & 1u) ? 0x3c00u : 0u) | (((bw[j] >> (2 * i + 1)) & 1u) ? 0x3c000000u : 0u);
+          } else if (masked && ok) {
 #pragma unroll
             for (int j = 0; j < G; ++j) {
               ldg256(p.saved + sbase + map_coloff(p.smap, c0 + 16 * j), sv[j]);
@@ -412,7 +426,16 @@ conv_shift_fwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_cons
                 packed[i] = *reinterpret_cast<const uint32_t*>(&o);
               }
             }
-            stg256(p.out + obase + map_coloff(p.omap, c), packed);
+            const long long eo = obase + map_coloff(p.omap, c);
+            stg256(p.out + eo, packed);
+            if (!DACT && p.bits_out != nullptr) {
+              uint32_t bits = 0;
+#pragma unroll
+              for (int i = 0; i < 8; ++i)
+                bits |= (((packed[i] & 0x7fffu) != 0u) ? (1u << (2 * i)) : 0u) |
+                        (((packed[i] & 0x7fff0000u) != 0u) ? (2u << (2 * i)) : 0u);
+              p.bits_out[eo >> 4] = (uint16_t)bits;
+            }
           }
         }
       }
@@ -677,8 +700,9 @@ int conv_shift_fwd_impl(const void* X, long long B, int Hg, int Wg, int C, const
                         int taps, const int* shifts, int vy, int vx, void* out, const long long* omap,
                         const void* saved, const long long* smap, const float* bias, int act, int dact, float alpha,
                         const void* u8_x, const long long* u8_idx, int u8_H, int u8_W, int u8_C, int u8_s,
-                        cudaStream_t stream) {
+                        void* bits_out, const void* saved_bits, cudaStream_t stream) {
   B200RL_REQUIRE((X || u8_x) && W && out && omap && B > 0, "conv_shift_fwd: null operand");
+  B200RL_REQUIRE(!(bits_out && dact) && !(saved_bits && !(dact && smap)), "conv_shift_fwd: bits_out is a forward output, saved_bits a dact input (with smap)");
   if (u8_x) {
     B200RL_REQUIRE(C == 64 && u8_s * u8_C == 16 && u8_s == 4 && u8_H == Hg * u8_s && u8_W == Wg * u8_s && !dact &&
                        N == 32 && (reinterpret_cast<uintptr_t>(u8_x) & 15) == 0 && (u8_W * u8_C) % 16 == 0,
@@ -698,8 +722,11 @@ int conv_shift_fwd_impl(const void* X, long long B, int Hg, int Wg, int C, const
   p.vy = vy; p.vx = vx; p.out = reinterpret_cast<__half*>(out);
   B200RL_REQUIRE(fill_map(p.omap, omap), "conv_shift_fwd: output map needs power-of-two Cq >= 16 and s");
   p.saved = reinterpret_cast<const __half*>(saved);
+  p.bits_out = reinterpret_cast<uint16_t*>(bits_out);
+  p.saved_bits = reinterpret_cast<const uint16_t*>(saved_bits);
   if (smap) B200RL_REQUIRE(fill_map(p.smap, smap), "conv_shift_fwd: saved map needs power-of-two Cq >= 16 and s");
   B200RL_REQUIRE(!(saved && !smap), "conv_shift_fwd: saved needs smap");
+  if (saved_bits && !saved) p.saved = reinterpret_cast<const __half*>(saved_bits);   // non-null marker: masking is on
   // the epilogue moves 16 fp16 columns per lane with one 256-bit access
   B200RL_REQUIRE(((omap[1] | omap[2] | omap[3]) & 15) == 0 && (reinterpret_cast<uintptr_t>(out) & 31) == 0,
                  "conv_shift_fwd: output strides must be multiples of 16 elements, base 32-byte aligned");

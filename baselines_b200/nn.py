@@ -439,6 +439,14 @@ class Tower:
         self.x16 = None if self.fused_u8 else torch.empty(cap, g0["Hg"] * g0["Wg"] * g0["Cg"], **f16)
         # activations: layer i's output is stored space-to-depth'ed for layer i+1 (compact after the last conv)
         self.hconv = [torch.empty(cap, c.OH * c.OW * c.nf, **f16) for c in cv]
+        # 1 bit per element "activation > 0" of every conv output a later dgrad masks with: the backward kernels read
+        # these instead of the fp16 activations (16x less mask traffic)
+        self.hbits = [None] * len(cv)
+        if os.environ.get("B200RL_NO_RELU_BITS", "0") != "1":
+            for i, c in enumerate(cv[:-1]):
+                if c.act == ops.ACT_RELU and (c.OH * c.OW * c.nf) % 16 == 0:
+                    self.hbits[i] = torch.zeros(cap * (c.OH * c.OW * c.nf // 16), dtype=torch.int16,
+                                                device=self.hconv[i].device)
         # gradients w.r.t. conv outputs live zero-bordered on the conv's INPUT grid
         self.dY = [torch.zeros(cap, g["Hg"] * g["Wg"] * c.nf, **f16) for c, g in zip(cv, self.sg)]
         # data-gradient weight operands [N' = Cg, taps * nf] (tap blocks of the master weight side by side)
@@ -472,7 +480,7 @@ class Tower:
                 omap = (0, c.OH * c.OW * c.nf, c.OW * c.nf, c.nf, 0, 0)
             ops.conv_shift_fwd(cur, B, g["Hg"], g["Wg"], g["Cg"], c.w_fwd, c.Kp, c.nf, g["shifts"], c.OH, c.OW,
                                self.hconv[i], omap, bias=c.b, act=c.act, tag="fwd." + c.name,
-                               u8=self._u8 if i == 0 else None)
+                               u8=self._u8 if i == 0 else None, bits_out=self.hbits[i])
             cur = self.hconv[i]
         return cur, self.flat
 
@@ -494,7 +502,8 @@ class Tower:
             smap = (0, g["Hg"] * g["Wg"] * g["Cg"], g["Wg"] * g["Cg"], g["Cg"], 0, 0)
             ops.conv_shift_fwd(self.dY[i], B, g["Hg"], g["Wg"], c.nf, self.wd[i], g["k"] * g["k"] * c.nf, g["Cg"],
                                [-sft for sft in g["shifts"]], g["Hg"], g["Wg"], self.dY[i - 1], omap,
-                               saved=self.hconv[i - 1], smap=smap, act=ops.ACT_RELU, dact=True, tag="dgrad." + c.name)
+                               saved=self.hconv[i - 1], smap=smap, act=ops.ACT_RELU, dact=True, tag="dgrad." + c.name,
+                               saved_bits=self.hbits[i - 1])
 
     def refresh(self):
         for l in self.layers:

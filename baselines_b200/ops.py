@@ -90,21 +90,25 @@ def _u8_args(u8):
 
 
 def conv_shift_fwd(X, B, Hg, Wg, C, W, ldw, N, shifts, vy, vx, out, omap, *, saved=None, smap=None, bias=None,
-                   act=ACT_NONE, dact=False, alpha=1.0, tag=None, u8=None):
+                   act=ACT_NONE, dact=False, alpha=1.0, tag=None, u8=None, bits_out=None, saved_bits=None):
     """Shift-GEMM convolution (forward, or data gradient with dact=True).  omap / smap: 6-tuples
     (mode, sN, sY, sX, Cq, s)."""
     _chk(X, torch.float16, "X")
     _chk(W, torch.float16, "W")
     _chk(out, torch.float16, "out")
     u8a = _u8_args(u8)
+    _chk(bits_out, torch.int16, "bits_out")
+    _chk(saved_bits, torch.int16, "saved_bits")
     sh = _iarr(shifts, _C.c_int)
     om = _iarr(omap, _C.c_longlong)
     sm = _iarr(smap, _C.c_longlong) if smap is not None else None
     rows = B * Hg * Wg
     _lib.call("b200rl_conv_shift_fwd", _ptr(X), int(B), Hg, Wg, C, _ptr(W), int(ldw), int(N), len(shifts), sh, vy, vx,
-              _ptr(out), om, _ptr(saved), sm, _ptr(bias), int(act), int(bool(dact)), float(alpha), *u8a, _stream(),
+              _ptr(out), om, _ptr(saved), sm, _ptr(bias), int(act), int(bool(dact)), float(alpha), *u8a,
+              _ptr(bits_out), _ptr(saved_bits), _stream(),
               label="convs." + (tag or "fwd"), flops=2.0 * rows * N * len(shifts) * C,
-              nbytes=(1.0 if u8 is not None else 2.0) * rows * C + 2.0 * rows * N)
+              nbytes=(1.0 if u8 is not None else 2.0) * rows * C + 2.0 * rows * N +
+              (0.0 if saved is None and saved_bits is None else (0.125 if saved_bits is not None else 2.0) * rows * N))
 
 
 def conv_shift_wgrad(X, rows, C, dY, N, shifts, G, ldg, alpha=1.0, max_ctas=0, tag=None, gbias=None, alpha_b=1.0,

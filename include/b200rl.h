@@ -67,8 +67,11 @@ int b200rl_conv_shift_fwd(const void* X, long long B, int Hg, int Wg, int C, con
                           int taps, const int* shifts, int vy, int vx, void* out, const long long* omap,
                           const void* saved, const long long* smap, const float* bias, int act, int dact, float alpha,
                           const void* u8_x, const long long* u8_idx, int u8_H, int u8_W, int u8_C, int u8_s,
-                          void* stream);
-/* u8_x != NULL (first layer): X is ignored; producer warps gather uint8 images u8_x[u8_idx[n], H, W, C], cast them
+                          void* act_bits_out, const void* saved_bits, void* stream);
+/* act_bits_out (forward, optional): uint16[numel(out)/16]; bit k of word e/16 is set iff out element e+k > 0 (e = the
+ * element offset the output map produces, always a multiple of 16).  saved_bits (dact, optional): the same array for
+ * the saved activation; it is read instead of `saved` (1 bit instead of 16 per element of backward HBM traffic).
+ * u8_x != NULL (first layer): X is ignored; producer warps gather uint8 images u8_x[u8_idx[n], H, W, C], cast them
  * to fp16 and build the space-to-depth (factor u8_s) tile directly in shared memory (models.py:19, ppo2.py:165). */
 int b200rl_conv_shift_wgrad(const void* X, long long rows, int C, const void* dY, int N, int taps, const int* shifts,
                             float* G, long long ldg, float alpha, float* gbias, float alpha_b, int max_ctas,

@@ -649,6 +649,24 @@ def test_conv_shift_forward_wgrad_dgrad(ops, name, B, Hg, Wg, C, R, N):
             ref = ref * (saved.float() > 0)
             err = float((dx.float() - ref).abs().max())
             assert torch.allclose(dx.float(), ref, atol=3e-2, rtol=5e-3), (name, "dgrad", err)
+            # the same mask as 1 bit per element: bit k of word e/16 <-> saved element e+k > 0
+            sv_relu = torch.relu(saved)
+            bits = ((sv_relu.reshape(-1, 16) > 0).to(torch.int32) << torch.arange(16, device="cuda", dtype=torch.int32)
+                    ).sum(1).to(torch.int16)                                  # two's complement wrap of bit 15
+            dx2 = torch.zeros_like(dx)
+            ops.conv_shift_fwd(dz, B, Hg, Wg, N, wd, taps * N, C, [-s for s in shifts], Hg, Wg, dx2, gmap, saved=sv_relu,
+                               smap=gmap, act=ops.ACT_RELU, dact=True, saved_bits=bits)
+            torch.cuda.synchronize()
+            assert torch.equal(dx, dx2), (name, "dgrad via bit mask")
+    # ---- forward can emit that bit array for its own (ReLU) output
+    bo = torch.zeros(B * OH * OW * N // 16, dtype=torch.int16, device="cuda")
+    out2 = torch.empty_like(out)
+    ops.conv_shift_fwd(x, B, Hg, Wg, C, wt, K, N, shifts, OH, OW, out2, omap, bias=bias, act=ops.ACT_RELU, bits_out=bo)
+    torch.cuda.synchronize()
+    assert torch.equal(out, out2)
+    want_bits = ((out2.reshape(-1, 16) > 0).to(torch.int32) << torch.arange(16, device="cuda", dtype=torch.int32)
+                 ).sum(1).to(torch.int16)
+    assert torch.equal(bo, want_bits), (name, "fwd bits")
 
 
 def test_conv_shift_address_maps(ops):
