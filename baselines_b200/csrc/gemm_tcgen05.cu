@@ -32,7 +32,7 @@ namespace b200rl {
 static constexpr int BM = 128;
 static constexpr int BK = 64;          // elements of the reduction dimension per pipeline stage
 static constexpr int UMMA_K = 16;
-static constexpr int NUM_THREADS = 256;
+static constexpr int NUM_THREADS = 384;   // TMA, MMA, TMEM alloc, spare + two epilogue warp sets (one per accumulator stage)
 
 
 struct ConvCoords {       // im2col traversal of the A operand (all zero for plain GEMMs)
@@ -275,11 +275,12 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     }
   } else if (warp >= 4) {
     // ------------------------------------------------------------------ epilogue
-    const int ew = warp - 4;            // == warp % 4: TMEM lane quarter this warp may access
+    // warps 4-7 drain accumulator stage 0 (even work items of this CTA), warps 8-11 stage 1 (odd ones)
+    const int ew = warp & 3;            // TMEM lane quarter this warp may access
     const int mode = (TMODE >= 0) ? TMODE : p.mode;
-    int as = 0;
+    const int as = (warp - 4) >> 2;
     uint32_t aph = 0;
-    for (int work = blockIdx.x; work < total_work; work += gridDim.x) {
+    for (int work = blockIdx.x + as * (int)gridDim.x; work < total_work; work += 2 * (int)gridDim.x) {
       const int n_tile = work % p.n_tiles;
       const int t2 = work / p.n_tiles;
       const int m_tile = t2 % p.m_tiles;
@@ -355,7 +356,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       }
       tc_fence_before();
       mbar_arrive(&tempty_bar[as]);
-      if (++as == 2) { as = 0; aph ^= 1; }
+      aph ^= 1;
     }
   }
 
