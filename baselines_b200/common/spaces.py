@@ -16,8 +16,18 @@ class Box:
         self.low = np.broadcast_to(np.asarray(low, dtype=self.dtype), self.shape).copy()
         self.high = np.broadcast_to(np.asarray(high, dtype=self.dtype), self.shape).copy()
 
+    def seed(self, seed=None):
+        self._rng = np.random.RandomState(seed)
+
     def sample(self):
-        return np.random.uniform(self.low, self.high).astype(self.dtype)
+        rng = getattr(self, "_rng", None) or np.random
+        if self.dtype.kind in "iu":
+            return rng.randint(self.low.astype(np.int64), self.high.astype(np.int64) + 1).astype(self.dtype)
+        return rng.uniform(self.low, self.high).astype(self.dtype)
+
+    def contains(self, x):
+        x = np.asarray(x)
+        return x.shape == self.shape and bool(np.all(x >= self.low) and np.all(x <= self.high))
 
     def __repr__(self):
         return f"Box{self.shape}"
@@ -29,8 +39,14 @@ class Discrete:
         self.shape = ()
         self.dtype = np.dtype(np.int64)
 
+    def seed(self, seed=None):
+        self._rng = np.random.RandomState(seed)
+
     def sample(self):
-        return np.random.randint(self.n)
+        return int((getattr(self, "_rng", None) or np.random).randint(self.n))
+
+    def contains(self, x):
+        return 0 <= int(x) < self.n
 
     def __repr__(self):
         return f"Discrete({self.n})"

@@ -74,6 +74,135 @@ class DummyVecEnv(VecEnv):
         return self.buf_obs.copy()
 
 
+def _subproc_worker(remote, parent_remote, fns_pickled, obs_buf, first):
+    """Worker of SubprocVecEnv: owns `len(fns)` envs (run in series), writes their observations straight into
+    rows [first, first+len) of the shared observation buffer and answers (rews, dones, infos) over the pipe."""
+    import pickle
+    parent_remote.close()
+    fns = pickle.loads(fns_pickled) if isinstance(fns_pickled, bytes) else fns_pickled
+    envs = [fn() for fn in fns]
+    view = obs_buf.numpy()
+    try:
+        while True:
+            cmd, data = remote.recv()
+            if cmd == 'step':
+                out = []
+                for k, (env, a) in enumerate(zip(envs, data)):
+                    ob, rew, done, info = env.step(a)
+                    if done:
+                        ob = env.reset()                          # subproc_vec_env.py:8-12: auto-reset
+                    view[first + k] = ob
+                    out.append((rew, done, info))
+                remote.send(out)
+            elif cmd == 'reset':
+                for k, env in enumerate(envs):
+                    view[first + k] = env.reset()
+                remote.send(None)
+            elif cmd == 'get_spaces_spec':
+                remote.send((envs[0].observation_space, envs[0].action_space, getattr(envs[0], "spec", None)))
+            elif cmd == 'close':
+                remote.close()
+                break
+            else:
+                raise NotImplementedError(cmd)
+    except KeyboardInterrupt:
+        pass
+    finally:
+        for env in envs:
+            if hasattr(env, "close"):
+                env.close()
+
+
+class SubprocVecEnv(VecEnv):
+    """Envs stepped in worker processes (subproc_vec_env.py:39-140, with the shared observation buffer of
+    shmem_vec_env.py:23-140): `in_series` envs per process, pipes carry only actions / rewards / dones / infos.
+    The observation batch lives in ONE shared-memory tensor that the workers fill in place; when CUDA is present the
+    parent page-locks that memory (cudaHostRegister), so Runner uploads it with a single async copy and no
+    host-side stacking -- `step_wait` hands out the same array every time (copy it if you keep it)."""
+
+    def __init__(self, env_fns, spaces=None, context='fork', in_series=1):
+        import multiprocessing as mp
+        self.waiting = self.closed = False
+        nenvs = len(env_fns)
+        assert nenvs % in_series == 0, "Number of envs must be divisible by number of envs to run in series"
+        self.nremotes, self.in_series = nenvs // in_series, in_series
+        groups = [list(env_fns[i * in_series:(i + 1) * in_series]) for i in range(self.nremotes)]
+        ctx = mp.get_context(context)
+        if spaces is None:                                   # ask a throw-away env, like shmem_vec_env.py:35-41
+            probe = env_fns[0]()
+            spaces = (probe.observation_space, probe.action_space)
+            self.spec = getattr(probe, "spec", None)
+            if hasattr(probe, "close"):
+                probe.close()
+        ob_space, ac_space = spaces
+        super().__init__(nenvs, ob_space, ac_space)
+        dt = torch.from_numpy(np.zeros(1, dtype=ob_space.dtype)).dtype
+        self._obs = torch.zeros((nenvs,) + tuple(ob_space.shape), dtype=dt).share_memory_()
+        self._pinned = False
+        if torch.cuda.is_available():
+            try:
+                rc = torch.cuda.cudart().cudaHostRegister(self._obs.data_ptr(), self._obs.numel() * self._obs.element_size(), 0)
+                self._pinned = int(rc) == 0
+            except Exception:
+                self._pinned = False
+        self.remotes, self.work_remotes = zip(*[ctx.Pipe() for _ in range(self.nremotes)])
+        self.ps = []
+        for k, (work_remote, remote, fns) in enumerate(zip(self.work_remotes, self.remotes, groups)):
+            payload = fns
+            if context != 'fork':
+                import cloudpickle
+                payload = cloudpickle.dumps(fns)
+            proc = ctx.Process(target=_subproc_worker, args=(work_remote, remote, payload, self._obs, k * in_series),
+                               daemon=True)                  # a crashed parent must not leave workers behind
+            proc.start()
+            self.ps.append(proc)
+        for r in self.work_remotes:
+            r.close()
+
+    def step_async(self, actions):
+        assert not self.closed
+        actions = np.asarray(actions)
+        for k, remote in enumerate(self.remotes):
+            remote.send(('step', actions[k * self.in_series:(k + 1) * self.in_series]))
+        self.waiting = True
+
+    def step_wait(self):
+        assert not self.closed
+        results = [r for remote in self.remotes for r in remote.recv()]
+        self.waiting = False
+        rews, dones, infos = zip(*results)
+        return self._obs.numpy(), np.asarray(rews, dtype=np.float32), np.asarray(dones, dtype=np.bool_), list(infos)
+
+    def reset(self):
+        assert not self.closed
+        for remote in self.remotes:
+            remote.send(('reset', None))
+        for remote in self.remotes:
+            remote.recv()
+        return self._obs.numpy()
+
+    def close(self):
+        if self.closed:
+            return
+        if self.waiting:
+            for remote in self.remotes:
+                remote.recv()
+        for remote in self.remotes:
+            remote.send(('close', None))
+        for proc in self.ps:
+            proc.join()
+        if self._pinned:
+            try:
+                torch.cuda.cudart().cudaHostUnregister(self._obs.data_ptr())
+            except Exception:
+                pass
+        self.closed = True
+
+    def __del__(self):
+        if not getattr(self, "closed", True):
+            self.close()
+
+
 class VecEnvWrapper(VecEnv):
     """vec_env.py:140-175: a wrapper over a whole batch of envs; unknown public attributes fall through to venv."""
 
@@ -135,6 +264,89 @@ class VecFrameStack(VecEnvWrapper):
         """(new frames [N, ..., c], rews, news, infos): the wrapped env's step; stacking is left to the caller."""
         self.venv.step_async(actions)
         return self.venv.step_wait()
+
+
+class VecNormalize(VecEnvWrapper):
+    """vec_normalize.py:4-49: running normalisation of observations and of rewards (by the std of the discounted
+    return), both clipped.  Host numpy, float64 statistics (the reference's use_tf=True variant only changes where
+    the three statistics are stored)."""
+
+    def __init__(self, venv, ob=True, ret=True, clipob=10., cliprew=10., gamma=0.99, epsilon=1e-8, use_tf=False):
+        super().__init__(venv)
+        from .running_mean_std import RunningMeanStd
+        self.ob_rms = RunningMeanStd(shape=self.observation_space.shape) if ob else None
+        self.ret_rms = RunningMeanStd(shape=()) if ret else None
+        self.clipob, self.cliprew, self.gamma, self.epsilon = clipob, cliprew, gamma, epsilon
+        self.ret = np.zeros(self.num_envs)
+
+    def _obfilt(self, obs):
+        if self.ob_rms is None:
+            return obs
+        self.ob_rms.update(obs)
+        return np.clip((obs - self.ob_rms.mean) / np.sqrt(self.ob_rms.var + self.epsilon), -self.clipob, self.clipob)
+
+    def step_wait(self):
+        obs, rews, news, infos = self.venv.step_wait()
+        self.ret = self.ret * self.gamma + rews
+        obs = self._obfilt(obs)
+        if self.ret_rms is not None:
+            self.ret_rms.update(self.ret)
+            rews = np.clip(rews / np.sqrt(self.ret_rms.var + self.epsilon), -self.cliprew, self.cliprew)
+        self.ret[np.asarray(news, dtype=np.bool_)] = 0.
+        return obs, rews, news, infos
+
+    def reset(self):
+        self.ret = np.zeros(self.num_envs)
+        return self._obfilt(self.venv.reset())
+
+
+class VecMonitor(VecEnvWrapper):
+    """vec_monitor.py:7-55: per-env episode return / length bookkeeping for a whole VecEnv; finished episodes are
+    reported as info['episode'] = {'r','l','t'} (what ppo2.learn's epinfobuf consumes) and optionally appended to a
+    monitor.csv."""
+
+    def __init__(self, venv, filename=None, keep_buf=0, info_keywords=()):
+        import time
+        from collections import deque
+        super().__init__(venv)
+        self.eprets = self.eplens = None
+        self.epcount = 0
+        self.tstart = time.time()
+        self.info_keywords = info_keywords
+        self.results_writer = None
+        if filename:
+            from ..bench.monitor import ResultsWriter
+            self.results_writer = ResultsWriter(filename, header={'t_start': self.tstart}, extra_keys=info_keywords)
+        self.keep_buf = keep_buf
+        if keep_buf:
+            self.epret_buf, self.eplen_buf = deque([], maxlen=keep_buf), deque([], maxlen=keep_buf)
+
+    def reset(self):
+        obs = self.venv.reset()
+        self.eprets = np.zeros(self.num_envs, 'f')
+        self.eplens = np.zeros(self.num_envs, 'i')
+        return obs
+
+    def step_wait(self):
+        import time
+        obs, rews, dones, infos = self.venv.step_wait()
+        self.eprets += rews
+        self.eplens += 1
+        infos = list(infos)
+        for i in np.nonzero(np.asarray(dones))[0]:
+            info = dict(infos[i])
+            ep = {'r': self.eprets[i], 'l': self.eplens[i], 't': round(time.time() - self.tstart, 6)}
+            ep.update({k: info[k] for k in self.info_keywords})
+            info['episode'] = ep
+            if self.keep_buf:
+                self.epret_buf.append(ep['r'])
+                self.eplen_buf.append(ep['l'])
+            self.epcount += 1
+            self.eprets[i], self.eplens[i] = 0, 0
+            if self.results_writer:
+                self.results_writer.write_row(ep)
+            infos[i] = info
+        return obs, rews, dones, infos
 
 
 class EpisodeStats:

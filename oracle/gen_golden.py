@@ -170,6 +170,57 @@ def gen_frame_stack():
                             nstack=nstack, c=c)
 
 
+def gen_vec_normalize():
+    """Reference VecNormalize (vec_normalize.py, numpy RunningMeanStd) driven by a scripted venv.  `tensorflow` and
+    `baselines.common.tf_util` are stubbed (running_mean_std.py imports them at module level; the numpy class does
+    not use them)."""
+    _import_reference_frame_stack()                      # installs the synthetic package `refvec`
+    sys.modules.setdefault("tensorflow", types.ModuleType("tensorflow"))
+    tfu = types.ModuleType("baselines.common.tf_util")
+    tfu.get_session = lambda *a, **k: None
+    sys.modules.setdefault("baselines.common.tf_util", tfu)
+    pkg = sys.modules["refvec"]
+    pkg.VecEnvWrapper = sys.modules["refvec.vec_env"].VecEnvWrapper
+    d = os.path.join(REF, "baselines/common/vec_env")
+    spec = importlib.util.spec_from_file_location("refvec.vec_normalize", os.path.join(d, "vec_normalize.py"))
+    m = importlib.util.module_from_spec(spec)
+    sys.modules["refvec.vec_normalize"] = m
+    spec.loader.exec_module(m)
+    N, D, T = 4, 3, 40
+    rng = np.random.RandomState(21)
+    obs = (rng.randn(T + 1, N, D) * np.array([1.0, 5.0, 0.1]) + np.array([0.0, 2.0, -1.0])).astype(np.float32)
+    rews = rng.randn(T, N).astype(np.float32) * 3.0
+    news = rng.rand(T, N) < 0.1
+
+    class Venv:
+        num_envs = N
+        observation_space = _Space((D,), np.float32)
+        action_space = None
+        t = 0
+
+        def reset(self):
+            self.t = 0
+            return obs[0]
+
+        def step_async(self, a):
+            pass
+
+        def step_wait(self):
+            self.t += 1
+            return obs[self.t], rews[self.t - 1], news[self.t - 1], [{}] * N
+
+    env = m.VecNormalize(Venv())
+    out_o, out_r = [np.asarray(env.reset()).copy()], []
+    for t in range(T):
+        env.step_async(None)
+        o, r, _, _ = env.step_wait()
+        out_o.append(np.asarray(o).copy())
+        out_r.append(np.asarray(r).copy())
+    np.savez_compressed(os.path.join(OUT, "vec_normalize_trace.npz"), obs=obs, rews=rews, news=news,
+                        norm_obs=np.stack(out_o), norm_rews=np.stack(out_r), ob_mean=env.ob_rms.mean,
+                        ob_var=env.ob_rms.var, ob_count=env.ob_rms.count, ret_var=env.ret_rms.var)
+
+
 def gen_segment_tree(Sum, Min):
     rng = np.random.RandomState(7)
     cap = 64
@@ -257,6 +308,7 @@ def main():
     gen_segment_tree(Sum, Min)
     gen_per(rb)
     gen_frame_stack()
+    gen_vec_normalize()
     print("golden fixtures written to", OUT)
 
 

@@ -348,3 +348,27 @@ def test_runner_device_frame_stack_equals_host_stacked_upload():
     for a, b in zip(*outs):
         for x, y in zip(a, b):
             assert np.array_equal(x, y)
+
+
+def test_command_line_trains_and_saves(tmp_path):
+    """`python -m baselines_b200.run` control flow (run.py:52-84,202-222): worker-process envs with Monitor files,
+    progress.csv, checkpoint in the reference's variable-name format."""
+    import joblib
+    from baselines_b200 import logger, run
+    log_dir, save = str(tmp_path / "log"), str(tmp_path / "model")
+    try:
+        model = run.main(["--alg=ppo2", "--env=CartPole-v0", "--num_timesteps=2048", "--num_env=2", "--seed=0",
+                          "--network=mlp", "--nsteps=256", "--nminibatches=4", "--noptepochs=2", "--log_interval=1",
+                          "--lr=1e-3", f"--log_path={log_dir}", f"--save_path={save}"])
+    finally:
+        logger.configure(None)
+    assert os.path.exists(os.path.join(log_dir, "progress.csv"))
+    rows = open(os.path.join(log_dir, "progress.csv")).read().splitlines()
+    assert len(rows) == 1 + 4 and "eprewmean" in rows[0] and "loss/policy_loss" in rows[0]
+    for k in (0, 1):
+        mon = open(os.path.join(log_dir, f"0.{k}.monitor.csv")).read().splitlines()
+        assert mon[0].startswith("#") and mon[1] == "r,l,t" and len(mon) > 3        # CartPole episodes are short
+    ck = joblib.load(save)
+    assert "ppo2_model/pi/mlp_fc0/w:0" in ck and ck["ppo2_model/pi/mlp_fc0/w:0"].shape == (4, 64)
+    a, v, s, nlp = model.step(np.zeros((2, 4), np.float32))
+    assert a.shape == (2,) and s is None
