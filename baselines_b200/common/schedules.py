@@ -1,5 +1,6 @@
-"""Schedules used by deepq.learn -- same behaviour as baselines/common/schedules.py:76-103 (LinearSchedule) and
-:5-12 (ConstantSchedule)."""
+"""Schedules used by deepq.learn -- same behaviour as baselines/common/schedules.py:76-103 (LinearSchedule),
+:18-31 (ConstantSchedule) and :34-73 (PiecewiseSchedule); pinned by tests/golden/host_misc.npz (values produced by
+the reference classes)."""
 
 
 class ConstantSchedule(object):
@@ -19,3 +20,26 @@ class LinearSchedule(object):
     def value(self, t):
         fraction = min(float(t) / self.schedule_timesteps, 1.0)
         return self.initial_p + fraction * (self.final_p - self.initial_p)
+
+
+def linear_interpolation(l, r, alpha):
+    return l + alpha * (r - l)
+
+
+class PiecewiseSchedule(object):
+    """Interpolates between (time, value) endpoints; outside them `outside_value` (or an AssertionError)."""
+
+    def __init__(self, endpoints, interpolation=linear_interpolation, outside_value=None):
+        idxes = [e[0] for e in endpoints]
+        assert idxes == sorted(idxes)
+        self._interpolation = interpolation
+        self._outside_value = outside_value
+        self._endpoints = endpoints
+
+    def value(self, t):
+        for (l_t, l), (r_t, r) in zip(self._endpoints[:-1], self._endpoints[1:]):
+            if l_t <= t and t < r_t:
+                alpha = float(t - l_t) / (r_t - l_t)
+                return self._interpolation(l, r, alpha)
+        assert self._outside_value is not None
+        return self._outside_value

@@ -221,6 +221,25 @@ def gen_vec_normalize():
                         ob_var=env.ob_rms.var, ob_count=env.ob_rms.count, ret_var=env.ret_rms.var)
 
 
+def gen_host_misc():
+    """Small host helpers the learn loops call: schedules (deepq.py:222-231) and explained_variance (ppo2.py:195)."""
+    sys.path.insert(0, REF)
+    from baselines.common.schedules import LinearSchedule, PiecewiseSchedule, ConstantSchedule
+    from baselines.common.math_util import explained_variance
+    ts = np.array([0, 1, 7, 99, 100, 101, 5000, 10000, 12345, 10 ** 6], np.int64)
+    lin = LinearSchedule(schedule_timesteps=int(0.1 * 100000), initial_p=1.0, final_p=0.02)
+    beta = LinearSchedule(100000, initial_p=0.4, final_p=1.0)
+    pw = PiecewiseSchedule([(0, 1.0), (100, 0.5), (10000, 0.1)], outside_value=0.05)
+    rng = np.random.RandomState(4)
+    y = rng.randn(257).astype(np.float32)
+    yp = (y + 0.3 * rng.randn(257)).astype(np.float32)
+    np.savez_compressed(os.path.join(OUT, "host_misc.npz"), ts=ts,
+                        lin=np.array([lin.value(int(t)) for t in ts]), beta=np.array([beta.value(int(t)) for t in ts]),
+                        pw=np.array([pw.value(int(t)) for t in ts]), const=ConstantSchedule(0.7).value(3),
+                        y=y, yp=yp, ev=explained_variance(yp, y), ev_perfect=explained_variance(y, y),
+                        ev_const=explained_variance(yp, np.ones_like(y)))
+
+
 def gen_segment_tree(Sum, Min):
     rng = np.random.RandomState(7)
     cap = 64
@@ -309,6 +328,7 @@ def main():
     gen_per(rb)
     gen_frame_stack()
     gen_vec_normalize()
+    gen_host_misc()
     print("golden fixtures written to", OUT)
 
 

@@ -203,3 +203,17 @@ def test_command_line_plumbing(tmp_path, monkeypatch):
         assert isinstance(env, VecFrameStack) and env.observation_space.shape == (84, 84, 4) and env.frame_stack_device
     finally:
         env.close()
+
+
+def test_schedules_and_explained_variance_match_reference():
+    from baselines_b200.common.misc_util import explained_variance
+    from baselines_b200.common.schedules import ConstantSchedule, LinearSchedule, PiecewiseSchedule
+    g = np.load(os.path.join(GOLDEN, "host_misc.npz"))
+    lin = LinearSchedule(schedule_timesteps=int(0.1 * 100000), initial_p=1.0, final_p=0.02)    # deepq.py:228-230
+    beta = LinearSchedule(100000, initial_p=0.4, final_p=1.0)                                  # deepq.py:222-226
+    pw = PiecewiseSchedule([(0, 1.0), (100, 0.5), (10000, 0.1)], outside_value=0.05)
+    for i, t in enumerate(g["ts"]):
+        assert lin.value(int(t)) == g["lin"][i] and beta.value(int(t)) == g["beta"][i] and pw.value(int(t)) == g["pw"][i]
+    assert ConstantSchedule(0.7).value(3) == float(g["const"])
+    assert explained_variance(g["yp"], g["y"]) == g["ev"] and explained_variance(g["y"], g["y"]) == g["ev_perfect"]
+    assert np.isnan(explained_variance(g["yp"], np.ones_like(g["y"]))) and np.isnan(g["ev_const"])
