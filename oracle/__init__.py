@@ -19,7 +19,12 @@ Parity pinning status (see DESIGN.md "Oracle"):
   TensorFlow 1.x (``tensorflow<2``, reference Dockerfile:14) is a third-party
   dependency that is absent from /root/reference and from this image.  The
   restatement follows the reference call sites line by line (citations in each
-  docstring), is cross-checked with float64 finite differences, and the Adam
-  formula is pinned to the reference's own numpy statement
-  (``baselines/common/mpi_adam.py:37-42``).
+  docstring) and is cross-checked with float64 finite differences.  Two pieces of
+  it ARE pinned by executing reference code under a TensorFlow import stub
+  (``tests/golden/init_adam.npz``): ``ortho_init`` (``a2c/utils.py:20-35``, numpy +
+  SVD) for every nature_cnn / mlp / head shape, and the Adam update through the
+  reference's numpy statement of TF-Adam (``common/mpi_adam.py:25-42``; m, v exact).
+* ``oracle.frame_stack`` and the host helpers (VecNormalize, schedules,
+  explained_variance) -- pinned: outputs of the executed reference classes
+  (``frame_stack_*.npz``, ``vec_normalize_trace.npz``, ``host_misc.npz``).
 """

@@ -240,6 +240,67 @@ def gen_host_misc():
                         ev_const=explained_variance(yp, np.ones_like(y)))
 
 
+class _TfStub(types.ModuleType):
+    """Any attribute / call resolves to another stub: lets reference modules that `import tensorflow as tf` be
+    imported so that their PURE-NUMPY functions can be executed (nothing TF-backed is ever called)."""
+
+    def __getattr__(self, k):
+        if k.startswith('__'):
+            raise AttributeError(k)
+        return _TfStub(k)
+
+    def __call__(self, *a, **k):
+        return _TfStub('call')
+
+
+def gen_init_and_adam():
+    """(1) a2c/utils.py:20-35 ortho_init is numpy + SVD under a TF signature -> executed for the layer shapes of
+    nature_cnn / mlp / heads under fixed seeds.  (2) common/mpi_adam.py:25-42 MpiAdam.update is the reference's
+    numpy statement of TF-Adam -> executed on a bare instance (no TF variables: getflat/setfromflat are closures over
+    a numpy vector, comm=None) for 5 steps."""
+    saved_tf = sys.modules.get("tensorflow")
+    sys.modules["tensorflow"] = _TfStub("tensorflow")
+    try:
+        spec = importlib.util.spec_from_file_location("ref_a2c_utils", os.path.join(REF, "baselines/a2c/utils.py"))
+        u = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(u)
+        out = {}
+        shapes = [((8, 8, 4, 32), np.sqrt(2)), ((4, 4, 32, 64), np.sqrt(2)), ((3, 3, 64, 64), np.sqrt(2)),
+                  ((64, 17), 0.01), ((376, 64), np.sqrt(2)), ((64, 1), 1.0), ((5, 9), 1.0), ((9, 5), 1.0)]
+        np.random.seed(1234)
+        for i, (shp, sc) in enumerate(shapes):
+            out[f"w{i}"] = u.ortho_init(sc)(shp, np.float32)
+            out[f"shape{i}"] = np.array(shp)
+            out[f"scale{i}"] = sc
+        sys.modules["baselines.common.tf_util"] = _TfStub("baselines.common.tf_util")
+        spec = importlib.util.spec_from_file_location("ref_mpi_adam", os.path.join(REF, "baselines/common/mpi_adam.py"))
+        ma = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(ma)
+        rng = np.random.RandomState(7)
+        theta = rng.randn(257).astype(np.float32)
+        out["adam_theta0"] = theta.copy()
+        opt = object.__new__(ma.MpiAdam)
+        opt.beta1, opt.beta2, opt.epsilon, opt.scale_grad_by_procs, opt.comm, opt.t = 0.9, 0.999, 1e-5, True, None, 0
+        opt.m, opt.v = np.zeros(257, 'float32'), np.zeros(257, 'float32')
+        state = {"theta": theta}
+        opt.getflat = lambda: state["theta"]
+        opt.setfromflat = lambda x: state.__setitem__("theta", x)
+        grads, thetas = [], []
+        for k in range(5):
+            g = (rng.randn(257) * (10.0 ** rng.randint(-3, 2))).astype(np.float32)
+            opt.update(g, 2.5e-4 * (1 - 0.1 * k))
+            grads.append(g)
+            thetas.append(np.asarray(state["theta"]).copy())
+        out.update(adam_grads=np.stack(grads), adam_thetas=np.stack(thetas), adam_m=opt.m, adam_v=opt.v)
+        np.savez_compressed(os.path.join(OUT, "init_adam.npz"), **out)
+    finally:
+        if saved_tf is None:
+            sys.modules.pop("tensorflow", None)
+        else:
+            sys.modules["tensorflow"] = saved_tf
+        sys.modules.pop("baselines.common.tf_util", None)
+
+
 def gen_segment_tree(Sum, Min):
     rng = np.random.RandomState(7)
     cap = 64
@@ -329,6 +390,7 @@ def main():
     gen_frame_stack()
     gen_vec_normalize()
     gen_host_misc()
+    gen_init_and_adam()
     print("golden fixtures written to", OUT)
 
 

@@ -189,3 +189,38 @@ def test_host_vec_frame_stack_matches_reference():
     for t in range(news.shape[0]):
         o, _, d, _ = env.step(None)
         assert np.array_equal(o, want[t + 1]) and np.array_equal(d, news[t])
+
+
+def test_ortho_init_matches_executed_reference():
+    """a2c/utils.py:20-35 executed (numpy + SVD under a TF stub) for the nature_cnn / mlp / head shapes: the oracle's
+    and the product's initialisers consume the global RandomState identically and return the same matrices.  The
+    fixture comparison allows 1e-6 (LAPACK kernels differ between host CPUs); oracle vs product is exact."""
+    import torch  # noqa: F401  (baselines_b200.nn imports it)
+    from baselines_b200 import nn
+    from oracle import nets
+    g = np.load(os.path.join(GOLDEN, "init_adam.npz"))
+    shapes = [(tuple(int(x) for x in g[f"shape{i}"]), float(g[f"scale{i}"])) for i in range(8)]
+    np.random.seed(1234)
+    wo = [nets.ortho_init_np(s, sc) for s, sc in shapes]
+    np.random.seed(1234)
+    wp = [nn.ortho_init(s, sc) for s, sc in shapes]
+    for i, (a, b) in enumerate(zip(wo, wp)):
+        assert a.dtype == np.float32 and a.shape == shapes[i][0]
+        assert np.array_equal(a, b), i
+        assert np.allclose(a, g[f"w{i}"], atol=1e-6, rtol=0), (i, float(np.abs(a - g[f"w{i}"]).max()))
+
+
+def test_adam_matches_executed_reference_numpy_adam():
+    """common/mpi_adam.py:25-42 (the reference's numpy statement of TF-Adam, proven equal to
+    tf.train.AdamOptimizer by its own test :64-99) executed for 5 steps.  m and v are float32 in both and must be
+    identical; the reference's parameter vector is promoted to float64 under numpy >= 2 (np.float64 step size times
+    a float32 array), ours stays float32 like TF's: agreement to float32 rounding."""
+    import torch
+    from oracle import nets
+    g = np.load(os.path.join(GOLDEN, "init_adam.npz"))
+    p = torch.from_numpy(g["adam_theta0"].copy())
+    m, v = torch.zeros_like(p), torch.zeros_like(p)
+    for k in range(5):
+        p, m, v = nets.adam_tf(p, torch.from_numpy(g["adam_grads"][k]), m, v, k + 1, 2.5e-4 * (1 - 0.1 * k), eps=1e-5)
+        assert np.allclose(p.numpy(), g["adam_thetas"][k], atol=1e-6, rtol=0), k
+    assert np.array_equal(m.numpy(), g["adam_m"]) and np.array_equal(v.numpy(), g["adam_v"])
