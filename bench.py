@@ -348,7 +348,7 @@ def main():
                          "share_of_step": tk["share"]})
 
     cpu_baseline = None
-    if not args.no_cpu_baseline:
+    if not args.no_cpu_baseline and world == 1:              # rank 0 at N=1 only (contract)
         n = args.ref_envs
         nb, times = cpu_reference_update(cfg, n, threads=pick_cpu_threads(), steps=1, warmup=0)
         cpu_baseline = {"value": nb / times[0], "unit": "env-steps/s", "cores": torch.get_num_threads(),
@@ -357,8 +357,8 @@ def main():
 
     targets = None
     try:
-        if args.no_targets:
-            raise RuntimeError("skipped (--no-targets)")
+        if args.no_targets or world > 1:
+            raise RuntimeError("skipped (--no-targets or N > 1: stand-alone kernels are a 1-GPU measurement)")
         sys.path.insert(0, os.path.join(ROOT, "tools"))
         import microbench
         mb = microbench.run(quick=True)
