@@ -86,7 +86,10 @@ class Runner:
         self._cur = torch.zeros((nenv,) + store_shape, dtype=self.rollout.obs.dtype, device=self.device)
         self._obs_src = None
         # VecFrameStack on the device: only the new frames cross PCIe, the stack lives in the rollout buffer
-        self.fs = bool(getattr(env, "frame_stack_device", False)) and self.u8 and not self.device_env and pin
+        # (only when VecFrameStack is the OUTERMOST wrapper: step_frames() would bypass anything wrapped around it)
+        from ..common.vec_env import VecFrameStack
+        self.fs = isinstance(env, VecFrameStack) and bool(env.frame_stack_device) and self.u8 and \
+            not self.device_env and pin
         if self.device_env:
             self._dev_obs = env.reset_device()
         elif self.fs:
