@@ -62,7 +62,10 @@ class Runner:
         self.batch_ob_shape = (nenv * nsteps,) + tuple(ob_space.shape)
         self.device = model.device
         net = model.net
-        self.device_env = hasattr(env, "step_device")
+        from ..common.vec_env import VecEnvWrapper
+        # wrappers forward unknown attributes to the env they wrap: a device env hidden under a wrapper must be
+        # stepped through the wrapper, not around it
+        self.device_env = hasattr(env, "step_device") and not isinstance(env, VecEnvWrapper)
         self.u8 = net.tower_pi.in_u8
         store_shape = tuple(ob_space.shape) if self.u8 else (net.tower_pi.in_pad,)
         self.rollout = Rollout(nsteps, nenv, store_shape, torch.uint8 if self.u8 else torch.float16, net.discrete,
