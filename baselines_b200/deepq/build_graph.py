@@ -8,7 +8,6 @@ train(obs_t, action, reward, obs_tp1, done, weight) -> td_error, doing: q(s), do
 argmax and the target network (:399-408), Huber loss (tf_util.py:39-45) weighted by the importance weights
 (:413), per-variable clip_by_norm(10) (:416-421), Adam (eps 1e-8, deepq.py:205).
 """
-import math
 
 import numpy as np
 import torch

@@ -10,7 +10,6 @@ import os
 import tempfile
 
 import numpy as np
-import torch
 
 from .. import logger
 from ..common.misc_util import set_global_seeds

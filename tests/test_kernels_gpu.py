@@ -3,7 +3,6 @@
 Integer / index / float64 work is bit-exact; fp16-operand GEMM work is compared with an fp32 evaluation
 of the SAME fp16-rounded operands (tolerance stated per test)."""
 import os
-import random
 
 import numpy as np
 import pytest
