@@ -217,3 +217,16 @@ def test_schedules_and_explained_variance_match_reference():
     assert ConstantSchedule(0.7).value(3) == float(g["const"])
     assert explained_variance(g["yp"], g["y"]) == g["ev"] and explained_variance(g["y"], g["y"]) == g["ev_perfect"]
     assert np.isnan(explained_variance(g["yp"], np.ones_like(g["y"]))) and np.isnan(g["ev_const"])
+
+
+def test_subproc_vec_env_spawn_context():
+    """'spawn' start method (the reference's default, subproc_vec_env.py:44): thunks travel through cloudpickle."""
+    from baselines_b200.common.vec_env import SubprocVecEnv
+    env = SubprocVecEnv([_cartpole_thunk(i) for i in range(2)], context='spawn')
+    try:
+        o = env.reset()
+        assert o.shape == (2, 4) and np.all(np.abs(o) <= 0.05)
+        o2, r, d, infos = env.step(np.array([0, 1]))
+        assert o2.shape == (2, 4) and r.tolist() == [1.0, 1.0] and not d.any() and len(infos) == 2
+    finally:
+        env.close()
