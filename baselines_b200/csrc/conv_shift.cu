@@ -12,6 +12,13 @@
 //   conv_shift_wgrad_kernel (MN-major): G[t, c, n] += alpha * sum_m X[m + sh_t, c] * dY[m, n]         wgrad
 //                                       (all taps' accumulators live in TMEM at once; X and dY are read once)
 //
+// Warp roles (forward, 384 threads [+256]): 0 TMA loads (weights once, A tile per tile) | 1 MMA issue (elect.sync) |
+// 2 TMEM alloc | 3 spare | 4-7 / 8-11 epilogue sets for accumulator stage 0 / 1 | 12-19 (first layer only) uint8
+// producer warps that build the A tile from raw frames instead of the TMA.  wgrad (256 threads [+256]): 0 TMA | 1 MMA |
+// 2 TMEM | 3 spare | 4-7 fused bias-gradient sums during the main loop, then the epilogue | 8-15 uint8 producers.
+// The forward epilogue can also write 1 bit per output element (act > 0); the dgrad of the next layer reads that
+// instead of the fp16 activation.
+//
 // Outputs at grid positions that are not valid conv outputs are computed from wrapped rows and discarded (fwd),
 // or multiply a zero of the zero-bordered dY (wgrad / dgrad) -- so dY tensors live on the conv's INPUT grid.
 // Replaces tf.nn.conv2d (a2c/utils.py:56) and its gradients (ppo2/model.py:102) of the reference.
