@@ -371,6 +371,7 @@ def main():
                             "frac": c["tflops"] / peaks["bf16_tflops"], "target": 0.5} for c in mb["fc1"]],
                    "gae_cpu_numpy": mb.get("gae_cpu"),          # reference numpy loop (oracle port), host, same sizes
                    "per_cfg4": mb.get("per"),                   # PER sample/update at capacity 2^20 vs the python port
+                   "replay_gather_cfg4": mb.get("replay_gather"),   # obs gather + cast of one replay sample
                    "dqn_cfg4": mb.get("dqn"),                   # one deepq train step at batch 512
                    "how": mb["l2_flush"] + "; CUDA events per launch, median of 10 after 3 warm-ups"}
     except Exception as ex:                                    # never lose the headline line to an extra

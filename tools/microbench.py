@@ -136,6 +136,29 @@ def per_case(flush, cap=1 << 20, batch=512, alpha=0.6, beta=0.4):
             "indices_equal_port": idx_same, "weights_max_rel_err_vs_port": w_err}
 
 
+def replay_gather_case(flush, batch=512, pool=32768):
+    """cfg-4: the observation gather of one replay sample (replay_buffer.py:33-43 `_encode_sample`: obs_t and
+    obs_tp1 of 512 random transitions) as it runs on the device: index gather + uint8 -> fp16 cast in one pass per
+    array.  Algorithmic bytes = 2 arrays x 512 x 28224 x (1 B read + 2 B written) = 86.7 MB (28.9 MB of
+    uint8 reads).  The pool (2 x 0.92 GB) is larger than L2."""
+    n_el = 84 * 84 * 4
+    g = torch.Generator(device="cuda").manual_seed(0)
+    obs_t = torch.randint(0, 256, (pool, n_el), dtype=torch.uint8, device="cuda", generator=g)
+    obs_1 = torch.randint(0, 256, (pool, n_el), dtype=torch.uint8, device="cuda", generator=g)
+    idx = torch.randint(0, pool, (batch,), device="cuda", generator=g)
+    out_t = torch.empty(batch, n_el, dtype=torch.float16, device="cuda")
+    out_1 = torch.empty(batch, n_el, dtype=torch.float16, device="cuda")
+
+    def fn():
+        ops.im2col(obs_t, out_t, batch, 1, 1, n_el, 1, 1, False, src_idx=idx, tag="replay_gather")
+        ops.im2col(obs_1, out_1, batch, 1, 1, n_el, 1, 1, False, src_idx=idx, tag="replay_gather")
+    ms, best = _time(fn, flush=flush)
+    ok = bool(torch.equal(out_t, obs_t[idx].half()) and torch.equal(out_1, obs_1[idx].half()))
+    nbytes = 2.0 * batch * n_el * 3
+    return {"batch": batch, "pool": pool, "ms": ms, "ms_best": best, "bytes": nbytes, "gbs": nbytes / (ms * 1e-3) / 1e9,
+            "matches_torch_index": ok}
+
+
 def dqn_case(flush, batch=512):
     """cfg-4: one deepq train step (build_graph.py:388-430) at batch 512: conv_only + dueling, double-Q -> three
     forwards, one backward, per-variable clip, Adam; observations gathered from a device-resident buffer."""
@@ -158,17 +181,24 @@ def dqn_case(flush, batch=512):
 def run(only=None, quick=False):
     flush = torch.empty(128 * 1024 * 1024, dtype=torch.float32, device="cuda")      # 512 MB > 126 MB L2
     out = {"l2_flush": "512 MB write between iterations"}
-    if only in (None, "gae"):
-        out["gae"] = [gae_case(128, 4096, -1, flush), gae_case(512, 16384, 1, flush), gae_case(512, 16384, 0, flush)]
-    if only in (None, "fc1"):
-        Ms = [8192, 131072] if not quick else [131072]
-        out["fc1"] = [fc1_case(M, k, flush) for M in Ms for k in ("fwd", "dgrad", "wgrad")]
-    if only in (None, "gae"):
-        out["gae_cpu"] = [gae_cpu_case(128, 4096), gae_cpu_case(512, 16384)]
-    if only in (None, "per"):
-        out["per"] = per_case(flush)
-    if only in (None, "dqn"):
-        out["dqn"] = dqn_case(flush)
+    Ms = [8192, 131072] if not quick else [131072]
+    cases = [
+        ("gae", "gae", lambda: [gae_case(128, 4096, -1, flush), gae_case(512, 16384, 1, flush),
+                                gae_case(512, 16384, 0, flush)]),
+        ("fc1", "fc1", lambda: [fc1_case(M, k, flush) for M in Ms for k in ("fwd", "dgrad", "wgrad")]),
+        ("gae", "gae_cpu", lambda: [gae_cpu_case(128, 4096), gae_cpu_case(512, 16384)]),
+        ("per", "per", lambda: per_case(flush)),
+        ("per", "replay_gather", lambda: replay_gather_case(flush)),
+        ("dqn", "dqn", lambda: dqn_case(flush)),
+    ]
+    for group, key, fn in cases:                      # one failing case must not take the others with it
+        if only not in (None, group):
+            continue
+        try:
+            out[key] = fn()
+        except Exception as ex:                       # noqa: BLE001
+            out[key] = {"error": repr(ex)}
+        torch.cuda.empty_cache()
     return out
 
 
