@@ -230,3 +230,24 @@ def test_subproc_vec_env_spawn_context():
         assert o2.shape == (2, 4) and r.tolist() == [1.0, 1.0] and not d.any() and len(infos) == 2
     finally:
         env.close()
+
+
+def test_build_env_for_deepq_is_a_single_env():
+    """run.py:97-99: deepq gets ONE env; for atari-type ids the frame stack is built in (4 stacked frames)."""
+    from baselines_b200 import run
+    from baselines_b200.common.cmd_util import common_arg_parser
+    a, _ = common_arg_parser().parse_known_args(["--alg=deepq", "--env=SyntheticAtari-v0", "--seed=0"])
+    env = run.build_env(a)
+    try:
+        ob = env.reset()
+        assert ob.shape == (84, 84, 4) and env.observation_space.shape == (84, 84, 4) and env.action_space.n == 6
+        ob2, rew, done, info = env.step(3)
+        assert ob2.shape == (84, 84, 4) and isinstance(rew, float) and isinstance(done, bool) and isinstance(info, dict)
+        assert np.array_equal(ob2[..., 2], ob[..., 3]) or done
+    finally:
+        env.close()
+    a, _ = common_arg_parser().parse_known_args(["--alg=deepq", "--env=CartPole-v0", "--seed=0"])
+    env = run.build_env(a)
+    ob = env.reset()
+    assert ob.shape == (4,) and not hasattr(env, "num_envs")
+    env.close()
