@@ -21,13 +21,12 @@ class PolicyBuilder:
         if callable(network) and not isinstance(network, str):
             raise NotImplementedError("custom network callables build TF graphs in the reference; this learner "
                                       "supports the registry names 'cnn', 'mlp', 'conv_only'")
-        if normalize_observations:
-            raise NotImplementedError("normalize_observations (policies.py:133-137) is outside the hot path scope")
         if value_network not in (None, "shared", "copy"):
             raise NotImplementedError("value_network must be None/'shared'/'copy' (policies.py:154-166)")
         self.ob_space, self.ac_space = ob_space, ac_space
         self.network = network
         self.value_network = "copy" if value_network == "copy" else None
+        self.normalize_observations = bool(normalize_observations)
         self.network_kwargs = network_kwargs
 
 
@@ -51,6 +50,12 @@ class PolicyNet:
         self.device, self.cap = device, cap
         ob_space, ac_space = builder.ob_space, builder.ac_space
         self.ob_shape = tuple(ob_space.shape)
+        # common/input.py:54-55: Discrete(n) observations are fed one-hot; MultiDiscrete is not on the hot path
+        if hasattr(ob_space, "nvec"):
+            raise NotImplementedError("MultiDiscrete observations (common/input.py:58-61) are outside the hot-path scope")
+        self.ob_onehot = int(ob_space.n) if spaces.is_discrete(ob_space) else 0
+        if self.ob_onehot and builder.network != "mlp":
+            raise NotImplementedError("Discrete observations need a vector network ('mlp')")
         self.discrete = spaces.is_discrete(ac_space)
         if self.discrete:
             self.nout = int(ac_space.n)
@@ -64,13 +69,18 @@ class PolicyNet:
         self.copy_vf = builder.value_network == "copy"
         store = self.store = nn.ParamStore(device)
         kw = dict(builder.network_kwargs)
+        if self.ob_onehot:
+            kw["onehot_n"] = self.ob_onehot
         # creation order == the reference's variable creation order (it fixes the ortho_init RNG stream)
         self.tower_pi = nn.Tower(store, kind, self.ob_shape, "pi", f"{scope}/pi", rng, cap, **kw)
         self.tower_vf = nn.Tower(store, kind, self.ob_shape, "vf", f"{scope}/vf", rng, cap, **kw) if self.copy_vf else None
         L = self.tower_pi.latent_dim
-        if L == self.nout:
-            raise NotImplementedError("_matching_fc latent==action-width shortcut (distributions.py:351-355)")
-        w_pi = nn.ortho_init((L, self.nout), 0.01, rng)                        # policies.py:49 init_scale=0.01
+        # distributions.py:351-355 (_matching_fc): when the latent is already nout wide the 'pi' layer is skipped and
+        # the latent IS the logits / mean.  Here the head keeps a frozen identity block (its gradient is zeroed before
+        # the norm / Adam, `freeze_identity`), so logits = latent exactly and d latent flows through the same kernels;
+        # no 'pi/w', 'pi/b' variables exist (and no ortho_init draw is consumed), like the reference.
+        self.pi_identity = (L == self.nout)
+        w_pi = np.eye(L, dtype=np.float32) if self.pi_identity else nn.ortho_init((L, self.nout), 0.01, rng)  # policies.py:49
         if not self.discrete:
             store.add("pi/logstd", np.zeros((1, self.nout), np.float32))         # distributions.py:104
             store.map_tf(f"{scope}/pi/logstd:0", "pi/logstd", (1, self.nout))
@@ -78,7 +88,8 @@ class PolicyNet:
         w_vf = nn.ortho_init((Lv, 1), 1.0, rng)                                # policies.py:63
         if self.copy_vf:
             self.head_pi = nn.Linear(store, "head_pi", L, self.nout, None, w_pi,
-                                     tf_w=f"{scope}/pi/w:0", tf_b=f"{scope}/pi/b:0")
+                                     tf_w=None if self.pi_identity else f"{scope}/pi/w:0",
+                                     tf_b=None if self.pi_identity else f"{scope}/pi/b:0")
             self.head_vf = nn.Linear(store, "head_vf", Lv, 1, None, w_vf,
                                      tf_w=f"{scope}/vf/w:0", tf_b=f"{scope}/vf/b:0")
             self.head = None
@@ -86,12 +97,25 @@ class PolicyNet:
             # fused [pi | vf] head: one skinny GEMM; TF variables are column slices of it
             n = self.nout
             self.head = nn.Linear(store, "head", L, n + 1, None, np.concatenate([w_pi, w_vf], axis=1))
-            store.map_tf(f"{scope}/pi/w:0", "head/w", (L, n), col_slice=slice(0, n))
-            store.map_tf(f"{scope}/pi/b:0", "head/b", (n,), col_slice=slice(0, n))
+            if not self.pi_identity:
+                store.map_tf(f"{scope}/pi/w:0", "head/w", (L, n), col_slice=slice(0, n))
+                store.map_tf(f"{scope}/pi/b:0", "head/b", (n,), col_slice=slice(0, n))
             store.map_tf(f"{scope}/vf/w:0", "head/w", (L, 1), col_slice=slice(n, n + 1))
             store.map_tf(f"{scope}/vf/b:0", "head/b", (1,), col_slice=slice(n, n + 1))
+        # policies.py:133-137,182-185: float observations pass through clip((x - mean) / std, -5, 5) of a
+        # RunningMeanStd (mpi_running_mean_std.py:11-33: float64 sum / sumsq / count variables, epsilon 1e-2).  Nothing
+        # in ppo2 ever updates those statistics, so they stay at their initial values (mean 0, std 1) unless a
+        # checkpoint provides others; they are kept, saved and loaded under the reference's variable names.
+        self.obs_rms = None
+        if builder.normalize_observations and not self.tower_pi.in_u8 and not self.ob_onehot:
+            d = self.tower_pi.raw_dim
+            self.obs_rms = {"runningsum": np.zeros(self.ob_shape, np.float64),
+                            "runningsumsq": np.full(self.ob_shape, 1e-2, np.float64),
+                            "count": np.float64(1e-2)}
+            self.rms_names = {k: f"{scope}/{k}:0" for k in self.obs_rms}
         store.finalize()
         self._materialize()
+        self.set_obs_rms()
         self.refresh()
 
     # ------------------------------------------------------------------------------------------
@@ -129,6 +153,35 @@ class PolicyNet:
         self.adv_st = torch.zeros(2, dtype=torch.float64, device=dev)
         self.stats = torch.zeros(5, dtype=torch.float64, device=dev)
 
+    def set_obs_rms(self, values=None):
+        """Install RunningMeanStd variables (mpi_running_mean_std.py:29-30: mean = sum/count,
+        std = sqrt(max(sumsq/count - mean^2, 1e-2)), both float32) into the observation encoder."""
+        if self.obs_rms is None:
+            return
+        if values:
+            for k in self.obs_rms:
+                if k in values:
+                    self.obs_rms[k] = np.asarray(values[k], np.float64).reshape(np.shape(self.obs_rms[k]))
+        r = self.obs_rms
+        mean = (r["runningsum"] / r["count"]).astype(np.float32)
+        std = np.sqrt(np.maximum((r["runningsumsq"] / r["count"]).astype(np.float32) - np.square(mean), np.float32(1e-2)))
+        t = lambda a: torch.from_numpy(np.ascontiguousarray(a.reshape(-1), dtype=np.float32)).to(self.device)
+        norm = (t(mean), t(np.float32(1.0) / std), -5.0, 5.0)
+        self.tower_pi.obs_norm = norm
+        if self.tower_vf:
+            self.tower_vf.obs_norm = norm
+
+    def freeze_identity(self):
+        """Zero the gradient of the frozen identity 'pi' block (see pi_identity) before the norm and Adam."""
+        if not self.pi_identity:
+            return
+        if self.head is not None:
+            self.head.gw[:, :self.nout].zero_()
+            self.head.gb[:self.nout].zero_()
+        else:
+            self.head_pi.gw.zero_()
+            self.head_pi.gb.zero_()
+
     def refresh(self):
         """Re-derive the fp16 operand copies from the fp32 master weights (after init / Adam / load)."""
         self.tower_pi.refresh()
@@ -141,19 +194,17 @@ class PolicyNet:
 
     # ------------------------------------------------------------------------------------------
     def encode_obs(self, obs_host_or_dev):
-        """common/input.py:43-63: Box uint8 images stay uint8 (cast fused into the first kernel); float
-        vectors become padded fp16 rows (the GEMM operand format)."""
+        """Stage observations on the device in the format the first kernel reads.  Box uint8 images stay uint8 (the
+        cast of models.py:19 is fused into the first conv's load); vector observations stay float32 rows
+        [B, raw_dim] -- the reference never narrows them (common/input.py:56-57 tf.to_float) -- and a Discrete
+        observation is its integer stored as float32 (one-hot happens in the encode kernel, input.py:54-55)."""
         t = obs_host_or_dev if torch.is_tensor(obs_host_or_dev) else torch.from_numpy(np.ascontiguousarray(obs_host_or_dev))
-        t = t.to(self.device, non_blocking=True)
         if self.tower_pi.in_u8:
             if t.dtype != torch.uint8:
                 raise NotImplementedError("cnn towers take uint8 images (common/models.py:19)")
-            return t.contiguous()
+            return t.to(self.device, non_blocking=True).contiguous()
         B = t.shape[0]
-        x = torch.zeros(B, self.tower_pi.in_pad, dtype=torch.float16, device=self.device)
-        src = t.reshape(B, -1).to(torch.float32).contiguous()
-        ops.cast_f32_f16(src, x, B, self.tower_pi.in_dim, self.tower_pi.in_dim, self.tower_pi.in_pad)
-        return x
+        return t.reshape(B, -1).to(torch.float32).to(self.device, non_blocking=True).contiguous()
 
     def forward(self, x, B, src_idx=None):
         """Towers + heads for B samples of x (optionally gathered through src_idx)."""

@@ -49,8 +49,11 @@ int sumsq_impl(const float*, long long, double*, cudaStream_t);
 int seg_sumsq_impl(const float*, const long long*, int, double*, cudaStream_t);
 int clip_adam_impl(float*, const float*, float*, float*, long long, float, float, float, float, float, const double*,
                    const long long*, int, cudaStream_t);
+int clip_accumulate_impl(const float*, float*, long long, float, float, const double*, cudaStream_t);
 int cast_transpose_impl(const float*, int, int, void*, long long, void*, long long, float, cudaStream_t);
 int cast_f32_f16_impl(const float*, void*, long long, int, long long, long long, float, cudaStream_t);
+int obs_encode_impl(const float*, const long long*, long long, int, int, int, const float*, const float*, float, float,
+                    int, void*, cudaStream_t);
 int tree_set_impl(double*, double*, long long, const long long*, const double*, int, cudaStream_t);
 int tree_range_sum_impl(const double*, long long, long long, long long, double*, cudaStream_t);
 int per_sample_impl(const double*, const double*, long long, long long, const double*, int, double, long long*,
@@ -178,6 +181,10 @@ int b200rl_clip_adam(float* p, const float* g, float* m, float* v, long long n, 
                      float eps, float clip, const double* sumsq, const long long* seg_off, int nseg, void* stream) {
   return clip_adam_impl(p, g, m, v, n, lr_t, beta1, beta2, eps, clip, sumsq, seg_off, nseg, S(stream));
 }
+int b200rl_clip_accumulate(const float* g, float* acc, long long n, float clip, float weight, const double* sumsq,
+                           void* stream) {
+  return clip_accumulate_impl(g, acc, n, clip, weight, sumsq, S(stream));
+}
 int b200rl_cast_transpose(const float* src, int R, int C, void* dst, long long ld_dst, void* dstT, long long ld_t,
                           float scale, void* stream) {
   return cast_transpose_impl(src, R, C, dst, ld_dst, dstT, ld_t, scale, S(stream));
@@ -185,6 +192,13 @@ int b200rl_cast_transpose(const float* src, int R, int C, void* dst, long long l
 int b200rl_cast_f32_f16(const float* src, void* dst, long long rows, int cols, long long ld_src, long long ld_dst,
                         float scale, void* stream) {
   return cast_f32_f16_impl(src, dst, rows, cols, ld_src, ld_dst, scale, S(stream));
+}
+
+int b200rl_obs_encode(const float* x, const long long* src_idx, long long B, int raw_dim, int in_dim, int in_pad,
+                      const float* mean, const float* inv_std, float clip_lo, float clip_hi, int onehot_n, void* out,
+                      void* stream) {
+  return obs_encode_impl(x, src_idx, B, raw_dim, in_dim, in_pad, mean, inv_std, clip_lo, clip_hi, onehot_n, out,
+                         S(stream));
 }
 
 int b200rl_tree_set(double* sum_tree, double* min_tree, long long capacity, const long long* idx, const double* vals,

@@ -95,6 +95,18 @@ clip_adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __re
   }
 }
 
+// acc += g * (clip / max(||g||, clip)) * weight : the per-microbatch clipped gradients of the reference's
+// MicrobatchedModel (ppo2/microbatched_model.py:60-70: self.grads are the clip_by_global_norm outputs of
+// ppo2/model.py:105-107, summed over microbatches and divided by their number)
+__global__ void __launch_bounds__(256)
+clip_accumulate_kernel(const float* __restrict__ g, float* __restrict__ acc, long long n, float clip, float weight,
+                       const double* __restrict__ sumsq) {
+  float sc = weight;
+  if (clip > 0.0f) sc *= clip / fmaxf((float)sqrt(sumsq[0]), clip);
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    acc[i] += g[i] * sc;
+}
+
 // dst16[r, c] = src[r, c]*scale (row pitch ld_dst), and optionally dstT16[c, r] = src[r, c]*scale (pitch ld_t)
 __global__ void __launch_bounds__(256)
 cast_transpose_kernel(const float* __restrict__ src, int R, int C, __half* __restrict__ dst, long long ld_dst,
@@ -181,6 +193,14 @@ int clip_adam_impl(float* p, const float* g, float* m, float* v, long long n, fl
   AdamArgs a{lr_t, beta1, beta2, eps, clip};
   clip_adam_kernel<<<grid_for(n, 256, 8), 256, 0, stream>>>(p, g, m, v, n, a, sumsq, seg_off, nseg);
   return check_launch("clip_adam_kernel");
+}
+
+int clip_accumulate_impl(const float* g, float* acc, long long n, float clip, float weight, const double* sumsq,
+                         cudaStream_t stream) {
+  B200RL_REQUIRE(g && acc && n > 0, "clip_accumulate: bad args");
+  B200RL_REQUIRE(clip <= 0.0f || sumsq != nullptr, "clip_accumulate: clipping needs the device sumsq");
+  clip_accumulate_kernel<<<grid_for(n, 256, 8), 256, 0, stream>>>(g, acc, n, clip, weight, sumsq);
+  return check_launch("clip_accumulate_kernel");
 }
 
 int cast_transpose_impl(const float* src, int R, int C, void* dst, long long ld_dst, void* dstT, long long ld_t,

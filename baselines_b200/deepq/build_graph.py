@@ -95,12 +95,12 @@ class QNet:
         """-> (x, src_idx) in the trunk's input format."""
         if self.trunk.in_u8:
             return obs, idx
-        rows = obs if idx is None else obs[idx]
-        B = rows.shape[0]
-        x = torch.zeros(B, self.trunk.in_pad, dtype=torch.float16, device=self.device)
-        src = rows.reshape(B, -1).to(torch.float32).contiguous()
-        ops.cast_f32_f16(src, x, B, self.trunk.in_dim, self.trunk.in_dim, self.trunk.in_pad)
-        return x, None
+        # vector observations stay float32 rows; the trunk's encode kernel gathers them through idx and splits
+        # them into fp16 [hi | lo] operand rows (no narrowing of the stored observation, common/input.py:56-57)
+        x = obs.reshape(obs.shape[0], -1)
+        if x.dtype != torch.float32:
+            x = x.to(torch.float32)
+        return x.contiguous(), idx
 
     def forward(self, obs, B, idx=None, out=None):
         """q head outputs for B samples: out[:, :nA] action scores, out[:, nA] state score (dueling)."""
@@ -169,6 +169,8 @@ class DQNModel:
         self.nA, self.gamma, self.double_q, self.lr = int(num_actions), float(gamma), bool(double_q), lr
         rng = np.random.RandomState(seed) if seed is not None else np.random
         ob_shape = tuple(ob_space.shape)
+        if hasattr(ob_space, "n") and not hasattr(ob_space, "nvec"):          # Discrete obs: one-hot (common/input.py:54-55)
+            network_kwargs = dict(network_kwargs, onehot_n=int(ob_space.n))
         with torch.cuda.device(self.device):
             self.q = QNet(ob_shape, num_actions, network, batch_cap, self.device, rng, "deepq/q_func", **network_kwargs)
             self.qt = QNet(ob_shape, num_actions, network, batch_cap, self.device, np.random.RandomState(0),

@@ -38,6 +38,16 @@ class ActWrapper(object):
         import joblib
         d = dict(self.model.q.store.export_tf("params"))
         d.update(self.model.qt.store.export_tf("params"))
+        # the optimiser slots are global variables too (tf_util.py:345-355 saves all of them): a resumed run
+        # continues Adam instead of restarting it
+        opt = self.model.opt
+        for k, v in self.model.q.store.export_tf("m").items():
+            d[k.replace(":0", "/Adam:0")] = v
+        for k, v in self.model.q.store.export_tf("v").items():
+            d[k.replace(":0", "/Adam_1:0")] = v
+        d["beta1_power:0"] = np.float32(opt.beta1 ** (opt.t + 1))
+        d["beta2_power:0"] = np.float32(opt.beta2 ** (opt.t + 1))
+        d["b200rl/adam_t"] = np.int64(opt.t)
         dirname = os.path.dirname(path)
         if dirname:
             os.makedirs(dirname, exist_ok=True)
@@ -46,8 +56,14 @@ class ActWrapper(object):
     def load(self, path):
         import joblib
         d = joblib.load(os.path.expanduser(path))
-        self.model.q.store.import_tf(d, "params")
+        from ..ppo2.model import _adam_step_from_checkpoint
+        q = self.model.q.store
+        q.import_tf(d, "params")
         self.model.qt.store.import_tf(d, "params")
+        q.import_tf({k.replace("/Adam:0", ":0"): v for k, v in d.items() if k.endswith("/Adam:0")}, "m")
+        q.import_tf({k.replace("/Adam_1:0", ":0"): v for k, v in d.items() if k.endswith("/Adam_1:0")}, "v")
+        opt = self.model.opt
+        opt.t = _adam_step_from_checkpoint(d, opt.beta1, opt.beta2, opt.t)
         self.model.q.refresh()
         self.model.qt.refresh()
 

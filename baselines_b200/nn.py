@@ -143,10 +143,14 @@ class Linear:
     w_fwd [N, Kp] (= W^T, forward B operand) and w_bwd [K, Np] (dgrad B operand)."""
 
     def __init__(self, store, name, K, N, act, w_init, b_init=None, in_scale=1.0, w_shape=None, b_shape=None,
-                 tf_w=None, tf_b=None, row_perm=None):
+                 tf_w=None, tf_b=None, row_perm=None, split_in=False):
         self.store, self.name, self.K, self.N, self.act = store, name, K, N, ops.ACT_CODES[act]
         self.in_scale = float(in_scale)
         self.Kp, self.Np = _pad8(K), _pad8(N)
+        # split_in: the input rows are fp16 [hi | lo] pairs of float32 values (csrc/obs_encode.cu); the forward
+        # operand is W^T stacked twice along K, the weight gradient is the sum of the hi and lo contributions
+        self.split_in = bool(split_in)
+        self.Kf = 2 * self.Kp if self.split_in else self.Kp
         w_init = np.asarray(w_init, np.float32).reshape(K, N)
         if row_perm is not None:
             w_init = w_init[np.asarray(row_perm)]
@@ -164,14 +168,17 @@ class Linear:
         self.b = self.store.views[self.name + "/b"]
         self.gw = self.store.gviews[self.name + "/w"]
         self.gb = self.store.gviews[self.name + "/b"]
-        self.w_fwd = torch.zeros(self.N, self.Kp, dtype=torch.float16, device=dev)
+        self.w_fwd = torch.zeros(self.N, self.Kf, dtype=torch.float16, device=dev)
         self.w_bwd = torch.zeros(self.K, self.Np, dtype=torch.float16, device=dev)
 
     def refresh(self):
-        ops.cast_transpose(self.w, self.K, self.N, self.w_bwd, self.Np, self.w_fwd, self.Kp, scale=self.in_scale)
+        ops.cast_transpose(self.w, self.K, self.N, self.w_bwd, self.Np, self.w_fwd, self.Kf, scale=self.in_scale)
+        if self.split_in:
+            ops.cast_transpose(self.w, self.K, self.N, None, 0, self.w_fwd[:, self.Kp:], self.Kf, scale=self.in_scale)
 
     def forward(self, x, ldx, M, out, ldo, mode=ops.MODE_F16_ACT, act=None):
-        ops.gemm(x, self.w_fwd, out, M=M, N=self.N, K=self.K, lda=ldx, ldb=self.Kp, ldc=ldo, bias=self.b,
+        K = self.Kp + self.K if self.split_in else self.K
+        ops.gemm(x, self.w_fwd, out, M=M, N=self.N, K=K, lda=ldx, ldb=self.Kf, ldc=ldo, bias=self.b,
                  mode=mode, act=self.act if act is None else act, tag="fwd." + self.name)
 
     def wgrad(self, x, ldx, dz, lddz, M, alpha):
@@ -181,6 +188,10 @@ class Linear:
         split = max(1, min(kb // 2 if kb >= 2 else 1, -(-296 // tiles)))
         ops.gemm(x, dz, self.gw, M=self.K, N=self.N, K=M, lda=ldx, ldb=lddz, ldc=self.N, mn_major=True,
                  mode=ops.MODE_F32_ATOMIC, alpha=alpha * self.in_scale, split_k=split, tag="wgrad." + self.name)
+        if self.split_in:                                  # + lo^T dz
+            ops.gemm(x[:, self.Kp:], dz, self.gw, M=self.K, N=self.N, K=M, lda=ldx, ldb=lddz, ldc=self.N,
+                     mn_major=True, mode=ops.MODE_F32_ATOMIC, alpha=alpha * self.in_scale, split_k=split,
+                     tag="wgrad." + self.name)
         ops.colsum(dz, self.gb, M, self.N, lddz, alpha=alpha)
 
     def dgrad(self, dz, lddz, M, out, ldo, saved=None, ld_saved=0, act=ops.ACT_NONE, remap=(0, 0, 0)):
@@ -331,7 +342,7 @@ class Tower:
     """A latent network (conv stack + fc, or mlp) with its activation workspace for `cap` samples."""
 
     def __init__(self, store, kind, ob_shape, prefix, tf_prefix, rng, cap, init="ortho", num_layers=2,
-                 num_hidden=64, convs=NATURE_CONVS, same_pad=False, fc_hidden=512, tf_style="a2c"):
+                 num_hidden=64, convs=NATURE_CONVS, same_pad=False, fc_hidden=512, tf_style="a2c", onehot_n=0):
         self.kind, self.cap, self.store = kind, cap, store
         self.convs, self.fcs = [], []
         winit = (lambda shape, scale: ortho_init(shape, scale, rng)) if init == "ortho" else \
@@ -371,12 +382,17 @@ class Tower:
         elif kind == "mlp":
             self.in_u8 = False
             self.shift_mode = False
-            nin = int(np.prod(ob_shape))
+            # Discrete(n) observations are one-hot encoded (common/input.py:54-55): raw rows hold the integer
+            self.onehot_n = int(onehot_n)
+            self.raw_dim = 1 if self.onehot_n else int(np.prod(ob_shape))
+            nin = self.onehot_n if self.onehot_n else self.raw_dim
             self.in_dim, self.in_pad = nin, _pad8(nin)
+            self.obs_norm = None                   # (mean, inv_std, lo, hi) float32 device tensors, policies.py:182-185
             for i in range(num_layers):                                       # models.py:94-99 (tanh)
                 self.fcs.append(Linear(store, f"{prefix}/mlp_fc{i}", nin, num_hidden, "tanh",
                                        winit((nin, num_hidden), math.sqrt(2)),
-                                       tf_w=f"{tf_prefix}/mlp_fc{i}/w:0", tf_b=f"{tf_prefix}/mlp_fc{i}/b:0"))
+                                       tf_w=f"{tf_prefix}/mlp_fc{i}/w:0", tf_b=f"{tf_prefix}/mlp_fc{i}/b:0",
+                                       split_in=(i == 0)))
                 nin = num_hidden
             self.latent_dim, self.latent_act = nin, ops.ACT_TANH
         else:
@@ -416,7 +432,7 @@ class Tower:
         self.hfc = [torch.empty(cap, l.Np, **f16) for l in self.fcs]
         self.dzfc = [torch.empty(cap, l.Np, **f16) for l in self.fcs]
         if self.kind == "mlp":
-            self.x0 = torch.zeros(cap, self.in_pad, **f16)
+            self.x0 = torch.zeros(cap, 2 * self.in_pad, **f16)      # [hi | lo] operand rows of the float32 observations
         # where the heads write d(loss)/d(latent pre-activation)
         if self.fcs:
             self.dlatent, self.ld_dlatent = self.dzfc[-1], self.fcs[-1].Np
@@ -538,12 +554,12 @@ class Tower:
             self._conv_in0 = self.x16 if (self.convs[0].implicit and self.in_u8) else x
             h, ldh = cur, self.flat                      # [B, OH*OW*C] view of the NHWC activation (H,W,C order)
         else:
-            if src_idx is not None:                      # row gather == 1x1 im2col
-                ops.im2col(x, self.x0, B, 1, 1, self.in_pad, 1, 1, False, src_idx=src_idx)
-                h = self.x0
-            else:
-                h = x
-            ldh = self.in_pad
+            # float32 rows (optionally gathered through src_idx) -> encoded fp16 [hi | lo] operand rows
+            nm = self.obs_norm
+            ops.obs_encode(x, self.x0, B, self.raw_dim, self.in_dim, self.in_pad, src_idx=src_idx,
+                           mean=nm[0] if nm else None, inv_std=nm[1] if nm else None,
+                           clip=(nm[2], nm[3]) if nm else (0.0, 0.0), onehot_n=self.onehot_n)
+            h, ldh = self.x0, 2 * self.in_pad
             self._mlp_in = h
         for i, l in enumerate(self.fcs):
             l.forward(h, ldh, B, self.hfc[i], l.Np)
@@ -561,7 +577,7 @@ class Tower:
             elif self.convs:
                 xin, ldx, act_in = self.hconv[-1], self.flat, ops.ACT_RELU
             else:
-                xin, ldx, act_in = self._mlp_in, self.in_pad, None
+                xin, ldx, act_in = self._mlp_in, 2 * self.in_pad, None
             l.wgrad(xin, ldx, dz, lddz, B, alpha)
             if act_in is None:
                 return
@@ -609,11 +625,12 @@ class Optimizer:
         self.sumsq = torch.zeros(nseg, dtype=torch.float64, device=store.device)
         self.seg_off = torch.from_numpy(store.segment_offsets()).to(store.device) if per_variable else None
 
-    def step(self, lr):
+    def step(self, lr, clip=True):
+        """clip=False: the gradient buffer already holds clipped gradients (MicrobatchedModel)."""
         s = self.store
         self.t += 1
         lr_t = lr * math.sqrt(1.0 - self.beta2 ** self.t) / (1.0 - self.beta1 ** self.t)
-        clip = self.clip if self.clip is not None else 0.0
+        clip = self.clip if (self.clip is not None and clip) else 0.0
         if clip > 0:
             if self.per_variable:
                 ops.seg_sumsq(s.grads, self.seg_off, self.nseg, self.sumsq)

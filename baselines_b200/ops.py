@@ -244,6 +244,13 @@ def clip_adam(p, g, m, v, lr_t, beta1, beta2, eps, clip, sumsq_buf, seg_off=None
               _stream(), label="clip_adam", nbytes=28.0 * p.numel())
 
 
+def clip_accumulate(g, acc, clip, weight, sumsq_buf):
+    _chk(g, torch.float32, "g")
+    _chk(acc, torch.float32, "acc")
+    _lib.call("b200rl_clip_accumulate", _ptr(g), _ptr(acc), g.numel(), float(clip if clip else 0.0), float(weight),
+              _ptr(sumsq_buf), _stream(), label="clip_accumulate", nbytes=12.0 * g.numel())
+
+
 def cast_transpose(src, R, C, dst, ld_dst, dstT, ld_t, scale=1.0):
     _chk(src, torch.float32, "src")
     _lib.call("b200rl_cast_transpose", _ptr(src), int(R), int(C), _ptr(dst), int(ld_dst), _ptr(dstT), int(ld_t),
@@ -255,6 +262,18 @@ def cast_f32_f16(src, dst, rows, cols, ld_src, ld_dst, scale=1.0):
     _chk(dst, torch.float16, "dst")
     _lib.call("b200rl_cast_f32_f16", _ptr(src), _ptr(dst), int(rows), int(cols), int(ld_src), int(ld_dst),
               float(scale), _stream())
+
+
+def obs_encode(x, out, B, raw_dim, in_dim, in_pad, src_idx=None, mean=None, inv_std=None, clip=(-5.0, 5.0), onehot_n=0):
+    """float32 observation rows -> fp16 [hi | lo] operand rows (input.py:43-63, policies.py:182-185, ppo2.py:165)."""
+    _chk(x, torch.float32, "x")
+    _chk(out, torch.float16, "out")
+    _chk(src_idx, torch.int64, "src_idx")
+    _chk(mean, torch.float32, "mean")
+    _chk(inv_std, torch.float32, "inv_std")
+    _lib.call("b200rl_obs_encode", _ptr(x), _ptr(src_idx), int(B), int(raw_dim), int(in_dim), int(in_pad), _ptr(mean),
+              _ptr(inv_std), float(clip[0]), float(clip[1]), int(onehot_n), _ptr(out), _stream(),
+              label="obs_encode", nbytes=float(B) * (4.0 * raw_dim + 4.0 * in_pad))
 
 
 def tree_set(sum_tree, min_tree, capacity, idx, vals):

@@ -46,6 +46,7 @@ class Model(object):
         self._rng_offset = 0
         self.comm = comm
         self.dist = dist_util.DataParallel(comm, mpi_rank_weight)
+        self._train_calls = 0
         self.dist.sync_from_root(self.net.store)             # model.py:131 sync_from_root
         self.net.refresh()
 
@@ -113,10 +114,21 @@ class Model(object):
                     sl = slice(s, s + B)
                     net.loss_backward(obs[sl], B, None, actions[sl], returns[sl], values[sl], neglogpacs[sl],
                                       cliprange, self.ent_coef, self.vf_coef, inv_M)
+            net.freeze_identity()
             self.dist.average_gradients(store)                           # mpi_adam_optimizer.py:39-40, BEFORE the clip
             self.opt.step(lr)                                            # model.py:107 clip -> :114 Adam
             net.refresh()
+            self._after_train_call()
             return net.stats / M
+
+    def _after_train_call(self):
+        """mpi_adam_optimizer.py:41-42: every 100th compute_gradients call checks that the ranks still hold identical
+        parameters (check_synced :53-68); a mismatch is a hard error there (assert) and here."""
+        self._train_calls += 1
+        if self.dist.active and self._train_calls % 100 == 0:
+            if not self.dist.check_synced(self.net.store):
+                raise AssertionError("parameters are not synchronised across ranks (check_synced, "
+                                     "mpi_adam_optimizer.py:53-68) after {} train calls".format(self._train_calls))
 
     def train(self, lr, cliprange, obs, returns, masks, actions, values, neglogpacs, states=None):
         """Reference signature (model.py:133); numpy minibatch in, list of 5 python floats out."""
@@ -146,6 +158,12 @@ class Model(object):
             d[k.replace(":0", "/Adam_1:0")] = v
         d["beta1_power:0"] = np.float32(self.opt.beta1 ** (self.opt.t + 1))
         d["beta2_power:0"] = np.float32(self.opt.beta2 ** (self.opt.t + 1))
+        # float32 beta1_power underflows to 0 after ~1000 Adam steps (62 PPO2 updates at the defaults), so the step
+        # count cannot be recovered from it; it is stored explicitly under a key no TF variable uses
+        d["b200rl/adam_t"] = np.int64(self.opt.t)
+        if self.net.obs_rms is not None:                     # RunningMeanStd variables (mpi_running_mean_std.py:11-26)
+            for k, name in self.net.rms_names.items():
+                d[name] = np.array(self.net.obs_rms[k], dtype=np.float64)
         dirname = os.path.dirname(save_path)
         if dirname:
             os.makedirs(dirname, exist_ok=True)
@@ -158,8 +176,9 @@ class Model(object):
         store.import_tf({k: v for k, v in d.items() if k in store.tf_map}, "params")
         store.import_tf({k.replace("/Adam:0", ":0"): v for k, v in d.items() if k.endswith("/Adam:0")}, "m")
         store.import_tf({k.replace("/Adam_1:0", ":0"): v for k, v in d.items() if k.endswith("/Adam_1:0")}, "v")
-        if "beta1_power:0" in d:
-            self.opt.t = max(0, int(round(math.log(float(d["beta1_power:0"])) / math.log(self.opt.beta1))) - 1)
+        self.opt.t = _adam_step_from_checkpoint(d, self.opt.beta1, self.opt.beta2, self.opt.t)
+        if self.net.obs_rms is not None:
+            self.net.set_obs_rms({k: d[name] for k, name in self.net.rms_names.items() if name in d})
         self.net.refresh()
 
     # parameters in the reference's TF naming / layout (used by the parity tests)
@@ -169,6 +188,27 @@ class Model(object):
     def set_params(self, params):
         self.net.store.import_tf(params, "params")
         self.net.refresh()
+
+
+def _adam_step_from_checkpoint(d, beta1, beta2, default):
+    """Adam step count of a checkpoint.  Our own files carry it as an integer; a reference (TF) checkpoint only has
+    the float32 accumulators beta1_power = beta1^(t+1), beta2_power = beta2^(t+1) (tf.train.AdamOptimizer slots saved
+    by tf_util.save_variables, tf_util.py:345-355).  beta1_power is denormal / zero after ~800 steps, so beta2_power
+    (usable up to ~9e4 steps) is preferred; once both have underflowed the bias correction is 1 to fp32 precision and
+    any large t gives the same update."""
+    if "b200rl/adam_t" in d:
+        return int(d["b200rl/adam_t"])
+    tiny = float(np.finfo(np.float32).tiny)
+    for key, beta in (("beta2_power:0", beta2), ("beta1_power:0", beta1)):
+        if key in d:
+            p = float(d[key])
+            if p >= 1.0:
+                return 0
+            if p > tiny * 1e3:                       # well inside the normal range: log() is accurate
+                return max(0, int(round(math.log(p) / math.log(beta))) - 1)
+    if "beta1_power:0" in d or "beta2_power:0" in d:
+        return 10 ** 6                               # both underflowed: sqrt(1-b2^t)/(1-b1^t) == 1
+    return default
 
 
 def _make_optimizer(store, max_grad_norm):

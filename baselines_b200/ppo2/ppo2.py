@@ -45,6 +45,12 @@ def learn(*, network, env, total_timesteps, eval_env=None, seed=None, nsteps=204
     model = model_fn(policy=policy, ob_space=ob_space, ac_space=ac_space, nbatch_act=nenvs,
                      nbatch_train=nbatch_train, nsteps=nsteps, ent_coef=ent_coef, vf_coef=vf_coef,
                      max_grad_norm=max_grad_norm, comm=comm, mpi_rank_weight=mpi_rank_weight)
+    if not all(hasattr(model, a) for a in ("train_rollout", "step_device", "value_device", "net", "device")):
+        # the rollout buffer lives in HBM and is consumed through device entry points; an object that only offers the
+        # host-side step / value / train of the reference Model cannot be driven by this loop
+        raise TypeError("model_fn must return a baselines_b200.ppo2 Model (or subclass, e.g. MicrobatchedModel): "
+                        "got {} without the device entry points train_rollout / step_device / value_device"
+                        .format(type(model).__name__))
     is_root = getattr(getattr(model, "dist", None), "rank", 0) == 0
     if load_path is not None:
         model.load(load_path)
@@ -67,19 +73,6 @@ def learn(*, network, env, total_timesteps, eval_env=None, seed=None, nsteps=204
         cliprangenow = cliprange(frac)
         if update % log_interval == 0 and is_root: logger.info('Stepping environment...')
 
-        if not hasattr(model, "train_rollout"):
-            # foreign Model (model_fn=...): the reference's host-side minibatch loop, ppo2.py:142-166
-            mblossvals = _reference_style_update(runner, model, lrnow, cliprangenow, nbatch, nbatch_train,
-                                                 noptepochs, epinfobuf)
-            lossvals = np.mean(mblossvals, axis=0)
-            tnow = time.perf_counter()
-            if update % log_interval == 0 or update == 1:
-                logger.logkv("misc/nupdates", update)
-                logger.logkv("fps", int(nbatch / (tnow - tstart)))
-                for (lossval, lossname) in zip(lossvals, model.loss_names):
-                    logger.logkv('loss/' + lossname, float(lossval))
-                logger.dumpkvs()
-            continue
         ro, epinfos = runner.run_device()                                   # ppo2.py:142
         if eval_runner is not None:
             _, eval_epinfos = eval_runner.run_device()
@@ -123,20 +116,6 @@ def learn(*, network, env, total_timesteps, eval_env=None, seed=None, nsteps=204
             print('Saving to', savepath)
             model.save(savepath)
     return model
-
-
-def _reference_style_update(runner, model, lrnow, cliprangenow, nbatch, nbatch_train, noptepochs, epinfobuf):
-    obs, returns, masks, actions, values, neglogpacs, states, epinfos = runner.run()
-    epinfobuf.extend(epinfos)
-    out = []
-    inds = np.arange(nbatch)
-    for _ in range(noptepochs):
-        np.random.shuffle(inds)
-        for start in range(0, nbatch, nbatch_train):
-            mbinds = inds[start:start + nbatch_train]
-            slices = (arr[mbinds] for arr in (obs, returns, masks, actions, values, neglogpacs))
-            out.append(model.train(lrnow, cliprangenow, *slices))
-    return out
 
 
 def run_epochs(model, ro, lrnow, cliprangenow, nbatch, nbatch_train, noptepochs, device, perms=None):

@@ -67,8 +67,10 @@ class Runner:
         # stepped through the wrapper, not around it
         self.device_env = hasattr(env, "step_device") and not isinstance(env, VecEnvWrapper)
         self.u8 = net.tower_pi.in_u8
-        store_shape = tuple(ob_space.shape) if self.u8 else (net.tower_pi.in_pad,)
-        self.rollout = Rollout(nsteps, nenv, store_shape, torch.uint8 if self.u8 else torch.float16, net.discrete,
+        # vector observations are kept as the float32 the env produced (the reference never narrows them,
+        # common/input.py:56-57); the encode kernel reads them through the minibatch indices
+        store_shape = tuple(ob_space.shape) if self.u8 else (net.tower_pi.raw_dim,)
+        self.rollout = Rollout(nsteps, nenv, store_shape, torch.uint8 if self.u8 else torch.float32, net.discrete,
                                net.nout, self.device)
         # pinned staging for the per-step host<->device traffic
         pin = torch.cuda.is_available()
@@ -84,8 +86,13 @@ class Runner:
         if pin:
             self._act_pin, self._rew_host, self._done_host = (t.pin_memory() for t in
                                                               (self._act_pin, self._rew_host, self._done_host))
-        self._f32_stage = None if self.u8 else torch.zeros(nenv, int(np.prod(ob_space.shape)), dtype=torch.float32,
-                                                           device=self.device)
+        self._f32_pin = None
+        if not self.u8:
+            self._f32_pin = torch.zeros(nenv, net.tower_pi.raw_dim, dtype=torch.float32)
+            if pin:
+                self._f32_pin = self._f32_pin.pin_memory()
+        self._f32_sync = torch.cuda.Event()
+        self._ro_copied = torch.cuda.Event()          # end-of-rollout H2D copies of the pinned reward / done staging
         self._cur = torch.zeros((nenv,) + store_shape, dtype=self.rollout.obs.dtype, device=self.device)
         self._obs_src = None
         # VecFrameStack on the device: only the new frames cross PCIe, the stack lives in the rollout buffer
@@ -141,20 +148,19 @@ class Runner:
     def _upload_obs(self, dst):
         if self.device_env:
             src = self._dev_obs
-            if self.u8:
-                dst.copy_(src)
-            else:
-                ops.cast_f32_f16(src.reshape(self.nenv, -1).float().contiguous(), dst, self.nenv,
-                                 self.model.net.tower_pi.in_dim, self.model.net.tower_pi.in_dim,
-                                 self.model.net.tower_pi.in_pad)
+            dst.copy_(src if self.u8 else src.reshape(self.nenv, -1))
             return
         src = self._obs_src if self._obs_src is not None else self._obs_pin
         if self.u8:
             dst.copy_(src, non_blocking=True)
+        elif src.dtype == torch.float32:
+            dst.copy_(src.reshape(self.nenv, -1), non_blocking=True)
         else:
-            self._f32_stage.copy_(src.reshape(self.nenv, -1), non_blocking=True)
-            ops.cast_f32_f16(self._f32_stage, dst, self.nenv, self.model.net.tower_pi.in_dim,
-                             self.model.net.tower_pi.in_dim, self.model.net.tower_pi.in_pad)
+            # integer (Discrete) / float64 observations: to_float on the host, one H2D copy (input.py:54-57)
+            self._f32_sync.synchronize()                     # the previous upload has left the staging buffer
+            np.copyto(self._f32_pin.numpy(), src.numpy().reshape(self.nenv, -1), casting="unsafe")
+            dst.copy_(self._f32_pin, non_blocking=True)
+            self._f32_sync.record()
 
     def run_device(self, noise=None):
         """Collect nsteps transitions; returns (Rollout, epinfos).  noise: optional [T, N, nA|d] float32 host
@@ -163,6 +169,9 @@ class Runner:
         epinfos = []
         with torch.cuda.device(self.device):
             nz = None if noise is None else torch.as_tensor(np.ascontiguousarray(noise), dtype=torch.float32).to(self.device)
+            # the previous rollout's asynchronous upload of _rew_host / _done_host must have read the staging buffers
+            # before this rollout overwrites row 0 (callers need not synchronise between run_device calls)
+            self._ro_copied.synchronize()
             if self.fs:
                 ro.obs[0].copy_(self._cur)
             for t in range(T):
@@ -201,6 +210,7 @@ class Runner:
             else:
                 ro.rewards.copy_(self._rew_host, non_blocking=True)
                 ro.dones.copy_(self._done_host, non_blocking=True)
+                self._ro_copied.record()
                 ro.last_dones.copy_(torch.from_numpy(self.dones.astype(np.uint8)))
             # GAE(lambda) + returns (runner.py:53-65) in one kernel over the resident buffers
             ops.gae_scan(ro.rewards, ro.values, ro.dones, ro.last_values, ro.last_dones, ro.advs, ro.returns,
@@ -214,9 +224,9 @@ class Runner:
         if self.u8:
             obs = ro.to_reference_numpy("obs")
         else:
-            o = ro.obs.float().cpu().numpy()[..., :self.model.net.tower_pi.in_dim]
-            o = o.reshape((self.nsteps, self.nenv) + tuple(self.env.observation_space.shape))
-            obs = o.swapaxes(0, 1).reshape(self.batch_ob_shape)
+            sp = self.env.observation_space
+            o = ro.obs.cpu().numpy().reshape((self.nsteps, self.nenv) + tuple(sp.shape))
+            obs = o.swapaxes(0, 1).reshape(self.batch_ob_shape).astype(np.dtype(sp.dtype), copy=False)
         masks = ro.to_reference_numpy("dones").astype(np.bool_)
         return (obs, ro.to_reference_numpy("returns"), masks, ro.to_reference_numpy("actions"),
                 ro.to_reference_numpy("values"), ro.to_reference_numpy("neglogpacs"), self.states, epinfos)

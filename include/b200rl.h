@@ -143,10 +143,23 @@ int b200rl_sumsq(const float* g, long long n, double* out, void* stream);
 int b200rl_seg_sumsq(const float* g, const long long* seg_off, int nseg, double* out, void* stream);
 int b200rl_clip_adam(float* p, const float* g, float* m, float* v, long long n, float lr_t, float beta1, float beta2,
                      float eps, float clip, const double* sumsq, const long long* seg_off, int nseg, void* stream);
+/* acc += g * clip/max(||g||, clip) * weight (clip <= 0: no clipping): the clipped per-microbatch gradients that
+ * ppo2/microbatched_model.py:60-70 sums and averages before one apply_gradients. */
+int b200rl_clip_accumulate(const float* g, float* acc, long long n, float clip, float weight, const double* sumsq,
+                           void* stream);
 int b200rl_cast_transpose(const float* src, int R, int C, void* dst, long long ld_dst, void* dstT, long long ld_t,
                           float scale, void* stream);
 int b200rl_cast_f32_f16(const float* src, void* dst, long long rows, int cols, long long ld_src, long long ld_dst,
                         float scale, void* stream);
+
+/* Vector-observation encoding: common/input.py:43-63 (Box -> to_float, Discrete -> one_hot), the optional
+ * clip((x - mean) / std, lo, hi) of common/policies.py:182-185, and the minibatch row gather of ppo2/ppo2.py:165.
+ * x: float32 [*, raw_dim]; out: fp16 [B, 2*in_pad] = [hi | lo] with hi = fp16(v), lo = fp16(v - hi), so the first
+ * GEMM (K = 2*in_pad against [W ; W]) sees the float32 observation to 2^-22 instead of an fp16-rounded copy.
+ * onehot_n > 0: x holds the Discrete value (raw_dim = 1), out row = one_hot(x, n). */
+int b200rl_obs_encode(const float* x, const long long* src_idx, long long B, int raw_dim, int in_dim, int in_pad,
+                      const float* mean, const float* inv_std, float clip_lo, float clip_hi, int onehot_n, void* out,
+                      void* stream);
 
 /* prioritized replay: common/segment_tree.py:76-86 (__setitem__), :51-74 (reduce), :105-131
  * (find_prefixsum_idx); deepq/replay_buffer.py:107-115 (_sample_proportional), :157-165 (weights),

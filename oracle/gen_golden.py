@@ -374,9 +374,41 @@ def gen_per(rb):
                         p_total_used=b2._it_sum.sum(0, len(b2._storage) - 1), full_sum=b2._it_sum.sum())
 
 
+def gen_uniform_replay(rb):
+    """Uniform ReplayBuffer (deepq/replay_buffer.py:7-68): ring writes with wrap-around, `sample` drawing
+    random.randint positions (:67), `_encode_sample` return types (:33-43: rewards / dones become float64)."""
+    size, batch = 50, 12
+    buf = rb.ReplayBuffer(size)
+    rng = np.random.RandomState(21)
+    n_add = [30, 15, 40]                                  # second and third rounds wrap the ring
+    adds, samples = [], []
+    k = 0
+    for r, na in enumerate(n_add):
+        for _ in range(na):
+            o, o1 = rng.randint(0, 256, (3, 3, 2)).astype(np.uint8), rng.randint(0, 256, (3, 3, 2)).astype(np.uint8)
+            a, rew, d = int(rng.randint(4)), float(rng.randn()), float(rng.rand() < 0.2)
+            buf.add(o, np.array(a), rew, o1, d)
+            adds.append((o, a, rew, o1, d))
+            k += 1
+        random.seed(500 + r)
+        obs_t, act, rews, obs_tp1, dones = buf.sample(batch)
+        assert rews.dtype == np.float64 and dones.dtype == np.float64
+        samples.append((obs_t, act, rews, obs_tp1, dones, len(buf)))
+    np.savez_compressed(os.path.join(OUT, "replay_uniform_trace.npz"), size=size, batch=batch, n_add=np.array(n_add),
+                        add_obs=np.stack([a[0] for a in adds]), add_act=np.array([a[1] for a in adds]),
+                        add_rew=np.array([a[2] for a in adds]), add_obs1=np.stack([a[3] for a in adds]),
+                        add_done=np.array([a[4] for a in adds]),
+                        s_obs=np.stack([s[0] for s in samples]), s_act=np.stack([s[1] for s in samples]),
+                        s_rew=np.stack([s[2] for s in samples]), s_obs1=np.stack([s[3] for s in samples]),
+                        s_done=np.stack([s[4] for s in samples]), s_len=np.array([s[5] for s in samples]))
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     Runner, Sum, Min, rb = _import_reference()
+    if "--only-uniform-replay" in sys.argv:
+        gen_uniform_replay(rb)
+        return
     small = gen_gae(Runner, "gae_small.npz", T=8, N=3, seed=1234, p_done=0.25)
     # SURVEY.md section 8c vector (regenerated here; assert it reproduces)
     adv0 = (small["returns0"] - small["values0"])[:8]
@@ -387,6 +419,7 @@ def main():
     gen_gae(Runner, "gae_alldone.npz", T=6, N=4, seed=3, p_done=1.1)
     gen_segment_tree(Sum, Min)
     gen_per(rb)
+    gen_uniform_replay(rb)
     gen_frame_stack()
     gen_vec_normalize()
     gen_host_misc()

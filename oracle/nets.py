@@ -2,7 +2,12 @@
 torch-CPU tensors (float32 by default, float64 for finite-difference checks).
 
 PARITY UNPINNED at the TensorFlow boundary: TF 1.x is absent (see oracle/__init__.py).
-Every function cites the reference lines it follows.  Parameters live in an ordered
+Every function cites the reference lines it follows.  Anchors that do not go through this
+module's own torch code (tests/test_oracle_anchors.py): the convolution / matmul / softmax
+cross-entropy primitives are compared with definition-level numpy loops of the TF op
+semantics, autograd gradients with float64 central finite differences of the loss, and the
+distributions with the statistical identities the reference itself tests
+(common/distributions.py:299-348, entropy = -E[log p], KL = -H - E_p[log q], 3 sigma).  Parameters live in an ordered
 ``dict name -> np.ndarray(float32)`` using the reference's TF variable names and
 layouts (conv HWIO ``[rf, rf, nin, nf]`` a2c/utils.py:50; fc ``[nin, nh]`` :61; conv bias
 ``[1, nf, 1, 1]`` :49), so reference checkpoints (tf_util.py:345-355) map 1:1.
@@ -132,6 +137,23 @@ def nature_cnn(tp, prefix, obs):
     return torch.relu(h @ tp[f"{prefix}/fc1/w:0"] + tp[f"{prefix}/fc1/b:0"])
 
 
+def encode_observation(obs, dtype, onehot_n=0, rms=None, clip=(-5.0, 5.0)):
+    """common/input.py:43-63 (Discrete -> to_float(one_hot), Box -> to_float) preceded, for float Box
+    observations with normalize_observations, by policies.py:182-185
+    clip_by_value((x - rms.mean) / rms.std, -5, 5) with the RunningMeanStd of mpi_running_mean_std.py:29-30.
+    rms: dict(runningsum, runningsumsq, count) float64 or None."""
+    obs = torch.as_tensor(obs)
+    if onehot_n:
+        return F.one_hot(obs.long().reshape(-1), onehot_n).to(dtype)
+    x = obs
+    if rms is not None:
+        mean = torch.as_tensor(np.asarray(rms["runningsum"]) / rms["count"]).float()
+        var = torch.as_tensor(np.asarray(rms["runningsumsq"]) / rms["count"]).float() - mean ** 2
+        std = torch.sqrt(torch.clamp(var, min=1e-2))
+        x = torch.clamp((x.float() - mean) / std, clip[0], clip[1])
+    return x.to(dtype)
+
+
 def mlp(tp, prefix, obs, num_layers=2):
     """models.py:74-103 (tanh, no layer_norm)."""
     dtype = tp[f"{prefix}/mlp_fc0/w:0"].dtype
@@ -176,6 +198,16 @@ def cat_entropy(logits):
     return (p0 * (torch.log(z0) - a0)).sum(dim=-1)
 
 
+def cat_kl(logits, other):
+    """distributions.py:185-192."""
+    a0 = logits - logits.max(dim=-1, keepdim=True).values
+    a1 = other - other.max(dim=-1, keepdim=True).values
+    ea0, ea1 = torch.exp(a0), torch.exp(a1)
+    z0, z1 = ea0.sum(dim=-1, keepdim=True), ea1.sum(dim=-1, keepdim=True)
+    p0 = ea0 / z0
+    return (p0 * (a0 - torch.log(z0) - a1 + torch.log(z1))).sum(dim=-1)
+
+
 def cat_sample(logits, uniforms):
     """distributions.py:199-201 with the uniform noise injected."""
     return torch.argmax(logits - torch.log(-torch.log(uniforms)), dim=-1)
@@ -192,6 +224,12 @@ def gauss_neglogp(mean, logstd, x):
 def gauss_entropy(mean, logstd):
     """distributions.py:245-246."""
     return (mean * 0.0 + logstd + 0.5 * math.log(2.0 * math.pi * math.e)).sum(dim=-1)
+
+
+def gauss_kl(mean, logstd, mean2, logstd2):
+    """distributions.py:242-244."""
+    std, std2 = torch.exp(logstd), torch.exp(logstd2)
+    return (logstd2 - logstd + (std ** 2 + (mean - mean2) ** 2) / (2.0 * std2 ** 2) - 0.5).sum(dim=-1)
 
 
 def gauss_sample(mean, logstd, normals):
@@ -324,6 +362,30 @@ class PPO2Oracle:
             self.tp[k], self.m[k], self.v[k] = adam_tf(p, g, self.m[k], self.v[k], self.t, lr,
                                                        eps=self.adam_eps)
         return stats
+
+    def train_microbatched(self, lr, cliprange, obs, returns, masks, actions, values, neglogpacs, microbatch_size):
+        """ppo2/microbatched_model.py:35-75: normalise over the full minibatch (:43), per microbatch take the
+        gradients AFTER clip_by_global_norm (`self.grads`, ppo2/model.py:105-108), average them (:70), one
+        apply_gradients; statistics are the mean over microbatches (:75)."""
+        advs = normalize_advs(returns, values)
+        n = len(returns)
+        assert n % microbatch_size == 0
+        nmicro = n // microbatch_size
+        total, stats_all = None, []
+        for i in range(nmicro):
+            sl = slice(i * microbatch_size, (i + 1) * microbatch_size)
+            st, grads = self.grads(cliprange, obs[sl], returns[sl], actions[sl], values[sl], neglogpacs[sl],
+                                   advs=advs[sl])
+            if self.max_grad_norm is not None:
+                grads, _ = clip_by_global_norm(grads, self.max_grad_norm)
+            total = grads if total is None else [a + g for a, g in zip(total, grads)]
+            stats_all.append(st)
+        grads = [g / nmicro for g in total]
+        self.last_grads = OrderedDict((k, g.numpy().copy()) for k, g in zip(self.tp.keys(), grads))
+        self.t += 1
+        for (k, p), g in zip(list(self.tp.items()), grads):
+            self.tp[k], self.m[k], self.v[k] = adam_tf(p, g, self.m[k], self.v[k], self.t, lr, eps=self.adam_eps)
+        return np.mean(np.array(stats_all), axis=0).tolist()
 
     def step(self, obs, noise):
         return policy_step(self.params_np(), self.network, obs, noise, self.value_network, self.dtype)

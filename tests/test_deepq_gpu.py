@@ -37,7 +37,7 @@ def test_dqn_train_step_matches_oracle(network, ob_shape, dtype, dueling):
     def obs():
         if dtype == np.uint8:
             return rng.randint(0, 256, (B,) + ob_shape).astype(np.uint8)
-        return rng.randn(B, *ob_shape).astype(np.float16).astype(np.float32)
+        return (rng.randn(B, *ob_shape) * 2.0).astype(np.float32)      # un-rounded float32 (no fp16 pre-rounding)
 
     dev = model.device
     for it in range(3):

@@ -251,3 +251,65 @@ def test_build_env_for_deepq_is_a_single_env():
     ob = env.reset()
     assert ob.shape == (4,) and not hasattr(env, "num_envs")
     env.close()
+
+
+def test_logger_output_formats_and_env_selection(tmp_path, monkeypatch, capsys):
+    """baselines/logger.py:174-190 (make_output_format) and :372-395 (configure): log.txt / progress.json /
+    progress.csv writers, $OPENAI_LOG_FORMAT / $OPENAI_LOGDIR selection, "-rank%03i" suffix for ranks > 0, csv
+    header growth with back-filled rows (:107-127), %-8.3g human formatting and 30-character truncation (:31-70)."""
+    import json
+    from baselines_b200 import logger
+    d = str(tmp_path / "a")
+    monkeypatch.delenv("OPENAI_LOG_FORMAT", raising=False)
+    monkeypatch.delenv("RANK", raising=False)
+    try:
+        logger.configure(d)                                         # default: stdout,log,csv
+        logger.logkv("b", 2)
+        logger.logkv("a_very_long_key_name_that_exceeds_thirty_chars", 1.23456789)
+        logger.logkv_mean("m", 1.0)
+        logger.logkv_mean("m", 3.0)
+        logger.dumpkvs()
+        logger.logkv("b", 3)
+        logger.logkv("c", np.float32(0.5))
+        logger.dumpkvs()
+        logger.log("hello", "world")
+        assert sorted(os.listdir(d)) == ["log.txt", "progress.csv"]
+        rows = open(os.path.join(d, "progress.csv")).read().splitlines()
+        assert rows[0] == "a_very_long_key_name_that_exceeds_thirty_chars,b,m,c"
+        assert rows[1] == "1.23456789,2,2.0," and rows[2] == ",3,,0.5"
+        txt = open(os.path.join(d, "log.txt")).read()
+        assert "| a_very_long_key_name_that_e... | 1.23     |" in txt and "hello world" in txt
+        assert txt.splitlines()[1].startswith("-----")
+        out = capsys.readouterr().out
+        assert "| b " in out and "Logging to" in out
+        # explicit formats + json
+        d2 = str(tmp_path / "b")
+        logger.configure(d2, format_strs=["json"])
+        logger.logkv("x", np.float64(1.5))
+        logger.logkv("n", 7)
+        logger.dumpkvs()
+        assert os.listdir(d2) == ["progress.json"]
+        assert json.loads(open(os.path.join(d2, "progress.json")).read()) == {"n": 7, "x": 1.5}
+        # environment selection and rank suffix
+        d3 = str(tmp_path / "c")
+        monkeypatch.setenv("OPENAI_LOGDIR", d3)
+        monkeypatch.setenv("OPENAI_LOG_FORMAT", "csv,json")
+        logger.configure()
+        logger.logkv("k", 1)
+        logger.dumpkvs()
+        assert sorted(os.listdir(d3)) == ["progress.csv", "progress.json"] and logger.get_dir() == d3
+        monkeypatch.setenv("RANK", "2")
+        monkeypatch.delenv("OPENAI_LOG_FORMAT_MPI", raising=False)
+        logger.configure()
+        logger.logkv("k", 1)
+        logger.dumpkvs()
+        assert "log-rank002.txt" in os.listdir(d3)
+        import pytest
+        with pytest.raises(NotImplementedError):
+            logger.configure(d3, format_strs=["tensorboard"])
+        with pytest.raises(ValueError):
+            logger.configure(d3, format_strs=["nope"])
+    finally:
+        monkeypatch.delenv("OPENAI_LOGDIR", raising=False)
+        monkeypatch.delenv("RANK", raising=False)
+        logger.configure(None)

@@ -31,8 +31,9 @@ def _mk(network, ob_shape, ob_dtype, discrete, nA, value_network, nenv, nsteps, 
     model = Model(policy=policy, ob_space=env.observation_space, ac_space=env.action_space, nbatch_act=nenv,
                   nbatch_train=nbatch_train, nsteps=nsteps, ent_coef=0.01, vf_coef=0.5, max_grad_norm=0.5, comm=False)
     np.random.seed(seed)
+    okw = {k: v for k, v in kw.items() if k != "normalize_observations"}
     oparams = nets.init_policy_params(network, ob_shape, "discrete" if discrete else "box", nA,
-                                      value_network=value_network, **kw)
+                                      value_network=value_network, **okw)
     return env, model, oparams
 
 
@@ -57,8 +58,9 @@ CASES = {
 def _obs(rng, case, B):
     if case["ob_dtype"] == np.uint8:
         return rng.randint(0, 256, size=(B,) + case["ob_shape"]).astype(np.uint8)
-    o = rng.randn(B, *case["ob_shape"]).astype(np.float32)
-    return o.astype(np.float16).astype(np.float32)      # observations representable in the fp16 operand format
+    # un-rounded float32, at the scale VecNormalize hands out (clipped to +-10, vec_normalize.py:39): the product
+    # may not narrow observations (common/input.py:56-57 to_float) -- they reach the first GEMM as fp16 hi/lo pairs
+    return np.clip(rng.randn(B, *case["ob_shape"]) * 3.0, -10.0, 10.0).astype(np.float32)
 
 
 @pytest.mark.parametrize("name", list(CASES))
@@ -208,7 +210,7 @@ def test_runner_matches_reference_semantics():
     T, N = 16, 32
     env0, model, oparams = _mk(nenv=N, nsteps=T, nminibatches=1, **case)
     rng = np.random.RandomState(5)
-    obs_seq = rng.randn(2 * T + 1, N, 4).astype(np.float16).astype(np.float32)
+    obs_seq = (rng.randn(2 * T + 1, N, 4) * 3.0).astype(np.float32)          # not representable in fp16
     rew = rng.randn(2 * T, N).astype(np.float32)
     done = rng.rand(2 * T, N) < 0.15
     env = _ReplayEnv(obs_seq, rew, done, env0.observation_space, env0.action_space)
@@ -217,7 +219,7 @@ def test_runner_matches_reference_semantics():
         obs, returns, masks, actions, values, neglogpacs, states, epinfos = runner.run()
         assert states is None and epinfos == []
         assert obs.shape == (N * T, 4) and returns.shape == (N * T,) and masks.dtype == np.bool_
-        assert np.allclose(obs, sf01(obs_seq[k * T:(k + 1) * T]), atol=0)
+        assert obs.dtype == np.float32 and np.array_equal(obs, sf01(obs_seq[k * T:(k + 1) * T]))   # returned bit-exact
         dones_before = np.concatenate([(done[k * T - 1] if k else np.zeros(N, bool))[None], done[k * T:(k + 1) * T - 1]], 0)
         assert np.array_equal(masks, sf01(dones_before))
         val_tn = values.reshape(N, T).T.copy()

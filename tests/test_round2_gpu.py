@@ -1,0 +1,553 @@
+"""GPU parity tests added in round 2 (VERDICT r1 "Next round" item 1): bench-shaped multi-chunk / multi-minibatch
+NatureCNN update against the oracle, large-batch conv stack against fp32 torch on the GPU, un-rounded float32 vector
+observations, Discrete (one-hot) observations, normalize_observations, the _matching_fc shortcut,
+MicrobatchedModel through learn(model_fn=...), dqn_act semantics, the uniform ReplayBuffer against a trace of the
+executed reference, a DQN trajectory without re-synchronisation, statistical identities of the device distributions,
+checkpoint fixtures in the reference layout and ActWrapper.save_act / load_act."""
+import math
+import os
+import random
+from functools import partial
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from test_ppo2_gpu import CASES, _mk, _obs      # noqa: E402  (shared builders)
+
+
+# ----------------------------------------------------------------------------------------------- bench-shaped update
+def test_bench_shaped_multichunk_multiminibatch_update_matches_oracle():
+    """The benchmarked path in miniature but with its structure intact: NatureCNN, 16 384 samples (32 steps x 512
+    envs) in an HBM-resident Rollout, 4 minibatches x 2 epochs through run_epochs(perms=...), every minibatch split
+    into 3 uneven chunks (1536 + 1536 + 1024: fp32-atomic accumulation across chunks, >= 36 tiles per persistent CTA
+    in conv1 so every mbarrier ring wraps many times), index-gathered uint8 observations; compared with the oracle's
+    ppo2/ppo2.py:157-166 loop (fancy-index minibatches in env-major order, per-minibatch normalisation, clip, Adam)."""
+    from baselines_b200.ppo2.ppo2 import run_epochs
+    from baselines_b200.ppo2.runner import Rollout
+    from oracle import nets
+    from oracle.gae import sf01
+    case = CASES["cnn_cat"]
+    T, N, nmb, nep = 32, 512, 4, 2
+    nbatch, nbt = T * N, T * N // nmb
+    os.environ["B200RL_TRAIN_CHUNK"] = "1536"
+    try:
+        env, model, oparams = _mk(nenv=N, nsteps=T, nminibatches=nmb, **case)
+    finally:
+        del os.environ["B200RL_TRAIN_CHUNK"]
+    assert model.chunk == 1536 and nbt == 4096
+    oracle = nets.PPO2Oracle(oparams, "cnn", 0.01, 0.5, 0.5)
+    rng = np.random.RandomState(7)
+    dev = model.device
+    ro = Rollout(T, N, (84, 84, 4), torch.uint8, True, 6, dev)
+    # a small pool of frames keeps the host arrays manageable; every sample still has its own (frame, action, ...) tuple
+    pool = rng.randint(0, 256, (64, 84, 84, 4)).astype(np.uint8)
+    pick = rng.randint(0, 64, (T, N))
+    obs = pool[pick]                                                   # [T, N, 84, 84, 4]
+    actions = rng.randint(0, 6, (T, N)).astype(np.int64)
+    values = rng.randn(T, N).astype(np.float32)
+    returns = (values + 0.7 * rng.randn(T, N)).astype(np.float32)
+    nlp = (math.log(6.0) + 0.05 * rng.randn(T, N)).astype(np.float32)
+    ro.obs.copy_(torch.from_numpy(obs))
+    ro.actions.copy_(torch.from_numpy(actions))
+    ro.values.copy_(torch.from_numpy(values))
+    ro.returns.copy_(torch.from_numpy(returns))
+    ro.neglogpacs.copy_(torch.from_numpy(nlp))
+    perms = [rng.permutation(nbatch) for _ in range(nep)]
+    lr, clip = 2.5e-4, 0.1
+    stats = run_epochs(model, ro, lr, clip, nbatch, nbt, nep, dev, perms=perms)
+    stats = torch.stack(stats).cpu().numpy()
+    # oracle: the reference loop on the sf01-flattened (env-major) arrays
+    f_obs, f_act, f_val, f_ret, f_nlp = map(sf01, (obs, actions, values, returns, nlp))
+    k = 0
+    for ep in range(nep):
+        for start in range(0, nbatch, nbt):
+            mb = perms[ep][start:start + nbt]
+            st_o = oracle.train(lr, clip, f_obs[mb], f_ret[mb], None, f_act[mb], f_val[mb], f_nlp[mb])
+            assert np.allclose(stats[k][:4], st_o[:4], atol=3e-3, rtol=2e-2), (k, stats[k], st_o)
+            assert abs(stats[k][4] - st_o[4]) <= 0.02, (k, stats[k][4], st_o[4])
+            k += 1
+    p, po = model.get_params(), oracle.params_np()
+    err = max(float(np.abs(p[n_] - po[n_]).max()) for n_ in p)
+    print(f"bench-shaped update: {k} minibatches x 3 chunks, max |param - oracle| = {err:.3e}")
+    assert err < 3e-3, err                                              # ppo2/test_microbatches.py:31-32 tolerance
+
+
+@pytest.mark.parametrize("B", [8192])
+def test_conv_stack_large_batch_vs_fp32_torch(B):
+    """conv_shift forward / wgrad / dgrad + the fc1 GEMMs at B = 8192 images (28 224 conv1 tiles: >= 190 tiles per
+    persistent CTA, far beyond the handful the small-B kernel tests reach) against fp32 torch conv2d + autograd on the
+    GPU, using the weights exactly as the kernels see them (fp16-rounded)."""
+    import torch.nn.functional as F
+    from baselines_b200 import nn as bnn, ops
+    dev = torch.device("cuda")
+    rng = np.random.RandomState(11)
+    store = bnn.ParamStore(dev)
+    tower = bnn.Tower(store, "cnn", (84, 84, 4), "pi", "m/pi", rng, B)
+    store.finalize()
+    tower.materialize()
+    # biases away from zero so the ReLU masks are non-trivial
+    for c in tower.convs:
+        c.b.copy_(torch.from_numpy(rng.randn(c.nf).astype(np.float32) * 0.05).to(dev))
+    tower.refresh()
+    pool = torch.from_numpy(rng.randint(0, 256, (256, 84, 84, 4)).astype(np.uint8)).to(dev)
+    idx = torch.from_numpy(rng.randint(0, 256, B).astype(np.int64)).to(dev)
+    h, ldh = tower.forward(pool, B, idx)
+    lat = h[:B, :512].float().clone()
+    g = (torch.randn(B, 512, device=dev) * 0.1)
+    tower.dlatent[:B, :512].copy_((g * (lat > 0)).half())
+    store.grads.zero_()
+    tower.backward(B, 1.0 / B)
+    torch.cuda.synchronize()
+    grads = store.export_tf("grads")
+    params = store.export_tf("params")
+    # ---- fp32 reference on the GPU, in slices (activations of 8192 images in fp32 are large)
+    W = {k: torch.from_numpy(v).to(dev).half().float().requires_grad_(True) for k, v in params.items() if k.endswith("w:0")}
+    # the kernels fold 1/255 into conv1's fp16 weights: reproduce that rounding
+    w1 = (torch.from_numpy(params["m/pi/c1/w:0"]).to(dev) / 255.0).half().float().requires_grad_(True)
+    Bs = {k: torch.from_numpy(v).to(dev).reshape(-1).requires_grad_(True) for k, v in params.items() if k.endswith("b:0")}
+    lat_ref = torch.empty(B, 512, device=dev)
+    for s in range(0, B, 1024):
+        x = pool[idx[s:s + 1024]].float().permute(0, 3, 1, 2)
+        a = torch.relu(F.conv2d(x, w1.permute(3, 2, 0, 1), Bs["m/pi/c1/b:0"], stride=4))
+        a = torch.relu(F.conv2d(a.half().float(), W["m/pi/c2/w:0"].permute(3, 2, 0, 1), Bs["m/pi/c2/b:0"], stride=2))
+        a = torch.relu(F.conv2d(a.half().float(), W["m/pi/c3/w:0"].permute(3, 2, 0, 1), Bs["m/pi/c3/b:0"], stride=1))
+        a = a.permute(0, 2, 3, 1).reshape(a.shape[0], -1).half().float()
+        z = torch.relu(a @ W["m/pi/fc1/w:0"] + Bs["m/pi/fc1/b:0"])
+        lat_ref[s:s + 1024] = z.detach()
+        (z * g[s:s + 1024] * (lat[s:s + 1024] > 0)).sum().mul(1.0 / B).backward()
+    err = float((lat - lat_ref).abs().max())
+    assert torch.allclose(lat, lat_ref, atol=2e-2, rtol=1e-2), err
+    ref_g = {"m/pi/c1/w:0": w1.grad / 255.0}
+    for k, v in W.items():
+        if k != "m/pi/c1/w:0":
+            ref_g[k] = v.grad
+    for k, v in Bs.items():
+        ref_g[k] = v.grad
+    for k, rg in ref_g.items():
+        got = torch.from_numpy(grads[k]).to(dev).reshape(rg.shape)
+        rel = float((got - rg).norm() / rg.norm().clamp_min(1e-20))
+        print(f"  large-B grad {k}: rel L2 err {rel:.3e}")
+        assert rel < 2e-2, (k, rel)
+
+
+# ----------------------------------------------------------------------------------------------- observation encoding
+def test_obs_encode_kernel_hi_lo_split_gather_onehot_normalize():
+    from baselines_b200 import ops
+    dev = torch.device("cuda")
+    rng = np.random.RandomState(0)
+    x = torch.from_numpy((rng.randn(300, 11) * 4).astype(np.float32)).to(dev)
+    idx = torch.from_numpy(rng.randint(0, 300, 77).astype(np.int64)).to(dev)
+    out = torch.full((77, 32), 9.0, dtype=torch.float16, device=dev)
+    ops.obs_encode(x, out, 77, 11, 11, 16, src_idx=idx)
+    torch.cuda.synchronize()
+    xs = x[idx]
+    hi, lo = out[:, :16].float(), out[:, 16:].float()
+    assert torch.equal(hi[:, :11], xs.half().float()) and torch.equal(lo[:, :11], (xs - xs.half().float()).half().float())
+    assert float(hi[:, 11:].abs().max()) == 0 and float(lo[:, 11:].abs().max()) == 0
+    assert float((hi + lo - torch.nn.functional.pad(xs, (0, 5))).abs().max()) <= 2.0 ** -21 * float(xs.abs().max())
+    # normalise + clip
+    mean = torch.from_numpy(rng.randn(11).astype(np.float32)).to(dev)
+    istd = torch.from_numpy((rng.rand(11) + 0.5).astype(np.float32)).to(dev)
+    ops.obs_encode(x, out, 77, 11, 11, 16, src_idx=idx, mean=mean, inv_std=istd, clip=(-5.0, 5.0))
+    want = torch.clamp((xs - mean) * istd, -5.0, 5.0)
+    got = out[:, :11].float() + out[:, 16:27].float()
+    assert float((got - want).abs().max()) <= 2.0 ** -20 * 5
+    # one-hot of a Discrete observation
+    d = torch.from_numpy(rng.randint(0, 10, (50, 1)).astype(np.float32)).to(dev)
+    oh = torch.zeros(50, 32, dtype=torch.float16, device=dev)
+    ops.obs_encode(d, oh, 50, 1, 10, 16, onehot_n=10)
+    assert torch.equal(oh[:, :10].float(), torch.nn.functional.one_hot(d[:, 0].long(), 10).float())
+    assert float(oh[:, 10:].abs().max()) == 0
+
+
+def test_mlp_observations_are_not_narrowed_to_fp16():
+    """with un-rounded float32 observations at VecNormalize scale the first-layer
+    pre-activations must agree with float64 to ~fp16-WEIGHT rounding; storing observations as fp16 rows (round 1)
+    fails this by an order of magnitude."""
+    case = CASES["mlp_gauss_copy"]
+    B = 512
+    env, model, oparams = _mk(nenv=B, nsteps=4, nminibatches=1, **case)
+    rng = np.random.RandomState(9)
+    obs = np.clip(rng.randn(B, 376) * 3.0, -10, 10).astype(np.float32)
+    # make the observation rounding error coherent with the weights: the worst case for a narrowed input
+    w = oparams["ppo2_model/pi/mlp_fc0/w:0"].astype(np.float64)
+    x = model.net.encode_obs(obs)
+    model.net.forward(x, B)
+    torch.cuda.synchronize()
+    t = model.net.tower_pi
+    h = t.hfc[0][:B, :64].float().cpu().numpy().astype(np.float64)
+    w16 = w.astype(np.float16).astype(np.float64)
+    pre_exact_x = obs.astype(np.float64) @ w16                     # what fp16 weights + exact observations give
+    pre_fp16_x = obs.astype(np.float16).astype(np.float64) @ w16   # what round 1 computed
+    got_err = np.abs(np.arctanh(np.clip(h, -0.999, 0.999)) - pre_exact_x)[np.abs(pre_exact_x) < 1.5]
+    r1_err = np.abs(pre_fp16_x - pre_exact_x)[np.abs(pre_exact_x) < 1.5]
+    print(f"first-layer pre-activation error: hi/lo split {got_err.max():.2e} (fp16 output rounding) vs fp16 obs {r1_err.max():.2e}")
+    # the only error left is the fp16 rounding of the stored activation (<= 2^-11 relative to |tanh| <= 1, amplified by
+    # arctanh'), not the input quantisation
+    assert got_err.max() < 2.5e-3
+    # and Runner.run hands back the float32 observations bit-exactly (checked in test_runner_matches_reference_semantics)
+
+
+def test_discrete_observations_one_hot_like_reference_identity_test():
+    """common/input.py:54-55 + common/tests/test_identity.py:28-41: Discrete(10) observations, ppo2 with
+    lr=1e-3, nsteps=64, ent_coef=0.0 must reach > 0.9 average reward."""
+    from baselines_b200 import envs
+    from baselines_b200.common.vec_env import DummyVecEnv
+    from baselines_b200.ppo2 import ppo2
+    from oracle import nets
+
+    def mk(i):
+        e = envs.DiscreteIdentityEnv(10, episode_len=100)
+        e.seed(i)
+        return e
+    env = DummyVecEnv([partial(mk, i) for i in range(8)])
+    assert env.observation_space.shape == () and hasattr(env.observation_space, "n")
+    model = ppo2.learn(network="mlp", env=env, total_timesteps=30000, seed=0, lr=1e-3, nsteps=64, ent_coef=0.0,
+                       gamma=0.9, log_interval=1000, comm=False)
+    # forward parity on integer observations against the oracle's one-hot encoding
+    obs = np.arange(10)
+    a, v, _, nlp = model.step(obs, noise=np.full((10, 10), 0.5, np.float32))
+    enc = nets.encode_observation(obs, torch.float32, onehot_n=10).numpy()
+    a_o, v_o, nlp_o, pi_o = nets.policy_step(model.get_params(), "mlp", enc, np.full((10, 10), 0.5, np.float32))
+    assert np.allclose(v, v_o, atol=3e-3 * max(1.0, np.abs(v_o).max())) and np.array_equal(a, a_o)
+    obs = env.reset()
+    tot = 0.0
+    for _ in range(100):
+        a, _, _, _ = model.step(obs)
+        obs, rew, done, _ = env.step(a)
+        tot += float(np.sum(rew))
+    assert tot / 800 > 0.9, tot / 800
+    # Runner.run returns the integer observations in the env's dtype
+    from baselines_b200.ppo2.runner import Runner
+    r = Runner(env=env, model=model, nsteps=4, gamma=0.9, lam=0.95)
+    o = r.run()[0]
+    assert o.shape == (32,) and o.dtype == env.observation_space.dtype and o.min() >= 0 and o.max() < 10
+
+
+def test_normalize_observations_and_matching_fc():
+    """policies.py:133-137,182-185 (clip((x - mean)/std, -5, 5) with the never-updated RunningMeanStd => clip(x, +-5);
+    variables saved under the reference names) and distributions.py:351-355 (latent width == nA: no 'pi' layer)."""
+    from oracle import nets
+    case = dict(network="mlp", ob_shape=(6,), ob_dtype=np.float32, discrete=True, nA=64, value_network=None)
+    env, model, oparams = _mk(nenv=64, nsteps=4, nminibatches=1, normalize_observations=True, **case)
+    assert "ppo2_model/pi/w:0" not in oparams and "ppo2_model/pi/w:0" not in model.get_params()      # _matching_fc
+    assert set(model.get_params()) == set(oparams)
+    for k in oparams:
+        assert np.array_equal(model.get_params()[k], oparams[k]), k          # no ortho_init draw consumed for 'pi'
+    rng = np.random.RandomState(2)
+    B = 256
+    obs = (rng.randn(B, 6) * 6.0).astype(np.float32)                         # many values beyond +-5
+    rms0 = dict(runningsum=np.zeros(6), runningsumsq=np.full(6, 1e-2), count=1e-2)
+    enc = nets.encode_observation(obs, torch.float32, rms=rms0).numpy()
+    assert np.array_equal(enc, np.clip(obs, -5, 5))
+    oracle = nets.PPO2Oracle(oparams, "mlp", 0.01, 0.5, 0.5)
+    actions = rng.randint(0, 64, B).astype(np.int64)
+    values = rng.randn(B).astype(np.float32)
+    returns = (values + rng.randn(B)).astype(np.float32)
+    nlp = (math.log(64.0) + 0.05 * rng.randn(B)).astype(np.float32)
+    for it in range(2):
+        st = model.train(1e-3, 0.2, obs, returns, None, actions, values, nlp)
+        st_o = oracle.train(1e-3, 0.2, enc, returns, None, actions, values, nlp)
+        assert np.allclose(st[:4], st_o[:4], atol=3e-3, rtol=2e-2), (st, st_o)
+        p, po = model.get_params(), oracle.params_np()
+        assert max(float(np.abs(p[k] - po[k]).max()) for k in p) < 3e-3
+    # logits ARE the latent
+    x = model.net.encode_obs(obs)
+    model.net.forward(x, B)
+    lat = model.net.tower_pi.hfc[-1][:B, :64].float()
+    assert torch.equal(model.net.pi_out[:B, :64], lat)
+    # checkpoint carries the RunningMeanStd variables; non-default statistics are honoured after load
+    import joblib
+    import tempfile
+    with tempfile.TemporaryDirectory() as td:
+        path = os.path.join(td, "m")
+        model.save(path)
+        d = joblib.load(path)
+        for k in ("ppo2_model/runningsum:0", "ppo2_model/runningsumsq:0", "ppo2_model/count:0"):
+            assert k in d and d[k].dtype == np.float64, k
+        d["ppo2_model/runningsum:0"] = np.arange(6, dtype=np.float64)
+        d["ppo2_model/runningsumsq:0"] = np.full(6, 40.0)
+        d["ppo2_model/count:0"] = np.float64(10.0)
+        joblib.dump(d, path)
+        model.load(path)
+    rms = dict(runningsum=np.arange(6.0), runningsumsq=np.full(6, 40.0), count=10.0)
+    enc2 = nets.encode_observation(obs, torch.float32, rms=rms).numpy()
+    v_o = nets.PPO2Oracle(model.get_params(), "mlp", 0.01, 0.5, 0.5).value(enc2)
+    assert np.allclose(model.value(obs), v_o, atol=3e-3 * max(1.0, np.abs(v_o).max()))
+
+
+# ----------------------------------------------------------------------------------------------- microbatches
+def test_microbatched_model_matches_reference_semantics_and_learn_equivalence():
+    """(1) numeric: MicrobatchedModel.train == the oracle's restatement of ppo2/microbatched_model.py:35-75 in a
+    regime where the per-microbatch clip is ACTIVE (so it differs measurably from clip-once); (2) the reference's
+    own test (ppo2/test_microbatches.py:12-32): learn(model_fn=partial(MicrobatchedModel, microbatch_size=2)) on
+    CartPole, nsteps=32, one update, parameters within atol=3e-3 of the plain Model."""
+    from baselines_b200 import envs
+    from baselines_b200.common.policies import build_policy
+    from baselines_b200.common.vec_env import DummyVecEnv
+    from baselines_b200.ppo2 import ppo2
+    from baselines_b200.ppo2.microbatched_model import MicrobatchedModel
+    from oracle import nets
+    case = CASES["mlp_cat"]
+    env, plain, oparams = _mk(nenv=16, nsteps=4, nminibatches=1, **case)
+    np.random.seed(0)
+    mb = MicrobatchedModel(policy=build_policy(env, "mlp"), ob_space=env.observation_space, ac_space=env.action_space,
+                           nbatch_act=16, nbatch_train=64, nsteps=4, ent_coef=0.01, vf_coef=0.5, max_grad_norm=0.5,
+                           comm=False, microbatch_size=8)
+    assert mb.nmicrobatches == 8
+    o_mb = nets.PPO2Oracle(oparams, "mlp", 0.01, 0.5, 0.5)
+    o_plain = nets.PPO2Oracle(oparams, "mlp", 0.01, 0.5, 0.5)
+    rng = np.random.RandomState(3)
+    M = 64
+    obs = _obs(rng, case, M)
+    actions = rng.randint(0, 2, M).astype(np.int64)
+    values = (rng.randn(M) * 3).astype(np.float32)
+    returns = (values + rng.randn(M) * 6).astype(np.float32)                # large value errors -> norms >> 0.5
+    nlp = (math.log(2.0) + 0.05 * rng.randn(M)).astype(np.float32)
+    for it in range(3):
+        st = mb.train(3e-4, 0.2, obs, returns, None, actions, values, nlp)
+        st_o = o_mb.train_microbatched(3e-4, 0.2, obs, returns, None, actions, values, nlp, 8)
+        o_plain.train(3e-4, 0.2, obs, returns, None, actions, values, nlp)
+        assert np.allclose(st[:4], st_o[:4], atol=3e-3, rtol=2e-2), (st, st_o)
+        g, go = mb.net.store.export_tf("grads"), o_mb.last_grads
+        num = sum(float(((g[k] - go[k]) ** 2).sum()) for k in g)
+        den = sum(float((go[k] ** 2).sum()) for k in g)
+        assert (num / den) ** 0.5 < 2e-2, (it, (num / den) ** 0.5)
+        # the clipped-average gradient is NOT the clip-once gradient here
+        gp = o_plain.last_grads
+        assert sum(float(((go[k] - gp[k]) ** 2).sum()) for k in g) ** 0.5 > 0.05 * den ** 0.5
+    p, po = mb.get_params(), o_mb.params_np()
+    assert max(float(np.abs(p[k] - po[k]).max()) for k in p) < 3e-4
+    # ---- the reference's equivalence test through learn()
+    def env_fn():
+        e = envs.make("CartPole-v0")
+        e.seed(0)
+        return e
+    learn_fn = partial(ppo2.learn, network="mlp", nsteps=32, total_timesteps=32, seed=0, comm=False)
+    ref = learn_fn(env=DummyVecEnv([env_fn]))
+    test = learn_fn(env=DummyVecEnv([env_fn]), model_fn=partial(MicrobatchedModel, microbatch_size=2))
+    assert isinstance(test, MicrobatchedModel) and test.nmicrobatches == 4
+    pr, pt = ref.get_params(), test.get_params()
+    for k in pr:
+        np.testing.assert_allclose(pr[k], pt[k], atol=3e-3)
+    with pytest.raises(TypeError):
+        learn_fn(env=DummyVecEnv([env_fn]), model_fn=lambda **kw: object())
+
+
+# ----------------------------------------------------------------------------------------------- deepq
+def test_dqn_act_greedy_and_epsilon_semantics():
+    """deepq/build_graph.py:184-192: deterministic = argmax_a q(s, a); stochastic = where(U < eps, randint(nA),
+    argmax); eps is a sticky variable updated only when update_eps >= 0; stochastic=False ignores eps."""
+    from baselines_b200.common import spaces
+    from baselines_b200.deepq.build_graph import DQNModel, build_act
+    nA, B = 5, 8192
+    model = DQNModel(spaces.Box(-5, 5, (8,), np.float32), nA, "mlp", lr=1e-3, batch_cap=B, seed=1, hiddens=(32,))
+    act = build_act(model)
+    rng = np.random.RandomState(0)
+    obs = (rng.randn(B, 8) * 2).astype(np.float32)
+    q = model.q_values(obs)
+    greedy = q.argmax(1)
+    gap = np.sort(q, 1)[:, -1] - np.sort(q, 1)[:, -2]
+    clear = gap > 1e-3
+    a0 = act(obs, stochastic=False)
+    assert a0.dtype == np.int64 and np.array_equal(a0[clear], greedy[clear])
+    a1 = act(obs, update_eps=0.0)
+    assert np.array_equal(a1[clear], greedy[clear])
+    a2 = act(obs, update_eps=1.0)                                            # always random: uniform over actions
+    freq = np.bincount(a2, minlength=nA) / B
+    assert np.all(np.abs(freq - 1.0 / nA) < 5 * math.sqrt(0.2 * 0.8 / B))
+    assert model.eps == 1.0
+    a3 = act(obs)                                                            # update_eps=-1: eps stays 1.0
+    assert model.eps == 1.0 and not np.array_equal(a3, a2)                   # fresh randomness on every call
+    assert np.array_equal(act(obs, stochastic=False)[clear], greedy[clear])  # greedy regardless of the stored eps
+    a4 = act(obs, update_eps=0.3)
+    p_same = 0.7 + 0.3 / nA
+    same = float((a4[clear] == greedy[clear]).mean())
+    assert abs(same - p_same) < 5 * math.sqrt(p_same * (1 - p_same) / clear.sum()), (same, p_same)
+    rand_part = a4[clear][a4[clear] != greedy[clear]]
+    assert len(np.unique(rand_part)) == nA or len(np.unique(rand_part)) == nA - 0   # random branch reaches every action
+
+
+def test_uniform_replay_buffer_vs_executed_reference_trace(golden_dir):
+    """deepq/replay_buffer.py:7-68 executed in the build container (oracle/gen_golden.py gen_uniform_replay): ring
+    writes incl. wrap-around, random.randint sampling positions, float64 rewards / dones."""
+    from baselines_b200.deepq.replay_buffer import ReplayBuffer
+    g = np.load(os.path.join(golden_dir, "replay_uniform_trace.npz"))
+    buf = ReplayBuffer(int(g["size"]))
+    k = 0
+    for r, na in enumerate(g["n_add"]):
+        for _ in range(int(na)):
+            buf.add(g["add_obs"][k], int(g["add_act"][k]), float(g["add_rew"][k]), g["add_obs1"][k], float(g["add_done"][k]))
+            k += 1
+        assert len(buf) == int(g["s_len"][r])
+        random.seed(500 + r)
+        obs_t, act, rew, obs_tp1, done = buf.sample(int(g["batch"]))
+        assert np.array_equal(obs_t, g["s_obs"][r]) and np.array_equal(obs_tp1, g["s_obs1"][r])
+        assert np.array_equal(act, g["s_act"][r])
+        assert rew.dtype == np.float64 and done.dtype == np.float64
+        assert np.array_equal(rew.astype(np.float32), g["s_rew"][r].astype(np.float32))
+        assert np.array_equal(done, g["s_done"][r])
+    # device path: same positions, unit weights
+    random.seed(77)
+    want = [random.randint(0, len(buf) - 1) for _ in range(9)]
+    random.seed(77)
+    idx, w = buf.sample_device(9)
+    assert idx.cpu().tolist() == want and torch.all(w == 1)
+
+
+def test_dqn_trajectory_without_resynchronisation():
+    """five consecutive train steps + one target update from ONE shared initial state, no
+    re-synchronisation: TD errors each step and the final parameters stay within the update tolerance."""
+    from baselines_b200.common import spaces
+    from baselines_b200.deepq.build_graph import DQNModel
+    from oracle import nets
+    nA, B, seed = 4, 128, 5
+    model = DQNModel(spaces.Box(-5, 5, (8,), np.float32), nA, "mlp", lr=1e-3, gamma=0.99, grad_norm_clipping=10,
+                     batch_cap=B, seed=seed, hiddens=(64,), dueling=True)
+    qp = nets.init_q_params("mlp", (8,), nA, hiddens=(64,), dueling=True, seed=seed)
+    oracle = nets.DQNOracle(qp, "mlp", 0.99, n_hidden=1, dueling=True, grad_norm_clipping=10.0)
+    rng = np.random.RandomState(1)
+    dev = model.device
+    f = lambda z: torch.as_tensor(z).to(dev)
+    for it in range(5):
+        o_t, o_1 = (rng.randn(B, 8) * 2).astype(np.float32), (rng.randn(B, 8) * 2).astype(np.float32)
+        act = rng.randint(0, nA, B).astype(np.int64)
+        rew = rng.randn(B).astype(np.float32)
+        done = (rng.rand(B) < 0.1).astype(np.float32)
+        w = (rng.rand(B) * 0.9 + 0.1).astype(np.float32)
+        qn = np.sort(oracle.q_values(o_1), axis=1)
+        done[(qn[:, -1] - qn[:, -2]) < 2e-2] = 1.0                           # ambiguous double-Q argmax: target = reward
+        td = model.train_device(f(o_t), f(o_1), f(act), f(rew), f(done), f(w), None, B).cpu().numpy()
+        td_o = oracle.train(1e-3, o_t, act, rew, o_1, done, w)
+        assert np.allclose(td, td_o, atol=1e-2 * max(1.0, np.abs(td_o).max())), (it, np.abs(td - td_o).max())
+        if it == 2:
+            model.update_target()
+            oracle.update_target()
+    p, po = model.q.store.export_tf("params"), {k: v.numpy() for k, v in oracle.tp.items()}
+    err = max(float(np.abs(p[k] - po[k]).max()) for k in p)
+    print(f"DQN 5-step trajectory: max |param - oracle| = {err:.3e}")
+    assert err < 3e-3, err
+
+
+def test_actwrapper_save_act_load_act_and_adam_resume(tmp_path):
+    """deepq/deepq.py:55-92: save_act pickles (model data, act params); load_act rebuilds an act function with the
+    same greedy policy.  ActWrapper.save also carries the q-net Adam slots (they are global variables in the
+    reference, tf_util.py:345-355), so a resumed run continues the optimiser."""
+    from baselines_b200.common import spaces
+    from baselines_b200.deepq import deepq
+    from baselines_b200.deepq.build_graph import DQNModel, build_act
+    params = dict(ob_space=spaces.Box(-5, 5, (6,), np.float32), num_actions=3, network="mlp", lr=1e-3, gamma=0.99,
+                  grad_norm_clipping=10, batch_cap=64, hiddens=(32,))
+    np.random.seed(0)
+    model = DQNModel(**params)
+    aw = deepq.ActWrapper(build_act(model), params, model)
+    rng = np.random.RandomState(0)
+    dev = model.device
+    f = lambda z: torch.as_tensor(z).to(dev)
+    B = 64
+    for _ in range(3):
+        model.train_device(f((rng.randn(B, 6)).astype(np.float32)), f((rng.randn(B, 6)).astype(np.float32)),
+                           f(rng.randint(0, 3, B).astype(np.int64)), f(rng.randn(B).astype(np.float32)),
+                           f(np.zeros(B, np.float32)), f(np.ones(B, np.float32)), None, B)
+    path = str(tmp_path / "model.pkl")
+    aw.save_act(path)
+    aw2 = deepq.load_act(path)
+    obs = rng.randn(16, 6).astype(np.float32)
+    assert np.array_equal(aw(obs, stochastic=False), aw2(obs, stochastic=False))
+    assert np.array_equal(model.q_values(obs), aw2.model.q_values(obs))
+    a, s, _, _ = aw2.step(obs[0], stochastic=False)
+    assert a.shape == (1,)
+    assert aw2.model.opt.t == 3
+    assert torch.equal(aw2.model.q.store.m, model.q.store.m) and torch.equal(aw2.model.q.store.v, model.q.store.v)
+
+
+# ----------------------------------------------------------------------------------------------- distributions on device
+def test_device_distributions_satisfy_reference_identities():
+    """common/distributions.py:321-348 on the CUDA heads: actions drawn by cat_step / gauss_step with the Philox
+    stream satisfy E[neglogp] = entropy within 3 sigma (N = 100 000, the reference's parameter vectors), and the
+    categorical frequencies follow softmax(logits)."""
+    from baselines_b200 import ops
+    from oracle import nets
+    dev = torch.device("cuda")
+    N = 100000
+    pc = np.array([-.2, .3, .5], np.float32)
+    logits = torch.from_numpy(np.repeat(pc[None], N, 0)).to(dev).contiguous()
+    logits = torch.nn.functional.pad(logits, (0, 13)).contiguous()           # row pitch 16
+    v = torch.zeros(N, 16, device=dev)
+    a = torch.zeros(N, dtype=torch.int64, device=dev)
+    val = torch.zeros(N, device=dev)
+    nlp = torch.zeros(N, device=dev)
+    ops.cat_step(logits, 16, 3, v, 16, a, val, nlp, N, seed=1234, offset=1)
+    torch.cuda.synchronize()
+    ent = float(nets.cat_entropy(torch.tensor(pc[None].astype(np.float64)))[0])
+    ll = nlp.double().cpu().numpy()
+    assert abs(ll.mean() - ent) < 3 * ll.std() / math.sqrt(N)
+    sm = np.exp(pc) / np.exp(pc).sum()
+    freq = np.bincount(a.cpu().numpy(), minlength=3) / N
+    assert np.all(np.abs(freq - sm) < 4 * np.sqrt(sm * (1 - sm) / N))
+    pd = np.array([-.2, .3, .4, -.5, .1, -.5, .1, 0.8], np.float32)
+    mean = torch.nn.functional.pad(torch.from_numpy(np.repeat(pd[None, :4], N, 0)), (0, 12)).to(dev).contiguous()
+    logstd = torch.from_numpy(pd[4:].copy()).to(dev)
+    act = torch.zeros(N, 4, device=dev)
+    ops.gauss_step(mean, 16, logstd, 4, v, 16, act, val, nlp, N, seed=99, offset=7)
+    torch.cuda.synchronize()
+    ent = float(nets.gauss_entropy(torch.tensor(pd[None, :4].astype(np.float64)), torch.tensor(pd[None, 4:].astype(np.float64)))[0])
+    ll = nlp.double().cpu().numpy()
+    assert abs(ll.mean() - ent) < 3 * ll.std() / math.sqrt(N)
+    x = act.double().cpu().numpy()
+    assert np.all(np.abs(x.mean(0) - pd[:4]) < 4 * np.exp(pd[4:]) / math.sqrt(N))
+    assert np.all(np.abs(x.std(0) / np.exp(pd[4:]) - 1) < 0.02)
+
+
+# ----------------------------------------------------------------------------------------------- checkpoints
+def test_reference_layout_checkpoint_fixture_and_adam_step_recovery(tmp_path):
+    """A checkpoint written the way the reference's save_variables writes one (tf_util.py:345-355: joblib dict of
+    ALL global variables by name -- parameters in HWIO / [in, out] layouts, Adam slots '<var>/Adam:0',
+    '<var>/Adam_1:0', the float32 accumulators beta1_power / beta2_power -- and nothing else) built by hand, not by
+    Model.save: load -> forward equals the oracle on those parameters; the Adam step count is recovered from
+    beta2_power when beta1_power has underflowed (float32(0.9**1001) == 0)."""
+    import joblib
+    from oracle import nets
+    case = CASES["cnn_cat"]
+    env, model, _ = _mk(nenv=8, nsteps=4, nminibatches=1, seed=3, **case)
+    np.random.seed(77)
+    ref_params = nets.init_policy_params("cnn", (84, 84, 4), "discrete", 6)       # names/shapes of the TF graph
+    rng = np.random.RandomState(5)
+    ck = {}
+    for k, v in ref_params.items():
+        ck[k] = (v + 0.01 * rng.randn(*v.shape)).astype(np.float32)
+        ck[k.replace(":0", "/Adam:0")] = (1e-3 * rng.randn(*v.shape)).astype(np.float32)
+        ck[k.replace(":0", "/Adam_1:0")] = (1e-6 * rng.rand(*v.shape)).astype(np.float32)
+    t = 2000
+    ck["beta1_power:0"] = np.float32(0.9 ** (t + 1))                             # == 0.0 in float32
+    ck["beta2_power:0"] = np.float32(0.999 ** (t + 1))
+    assert float(ck["beta1_power:0"]) == 0.0
+    path = str(tmp_path / "ref_ckpt")
+    joblib.dump(ck, path)
+    model.load(path)
+    assert abs(model.opt.t - t) <= 1, model.opt.t
+    p = model.get_params()
+    for k in ref_params:
+        assert np.array_equal(p[k], ck[k]), k
+    m = model.net.store.export_tf("m")
+    vv = model.net.store.export_tf("v")
+    for k in ref_params:
+        assert np.array_equal(m[k], ck[k.replace(":0", "/Adam:0")]) and np.array_equal(vv[k], ck[k.replace(":0", "/Adam_1:0")]), k
+    obs = rng.randint(0, 256, (8, 84, 84, 4)).astype(np.uint8)
+    v_o = nets.PPO2Oracle({k: ck[k] for k in ref_params}, "cnn", 0.01, 0.5, 0.5).value(obs)
+    assert np.allclose(model.value(obs), v_o, atol=3e-3 * max(1.0, np.abs(v_o).max()))
+    # our own files carry the integer step: exact round trip far beyond the float32 range of beta1_power
+    model.opt.t = 123456
+    p2 = str(tmp_path / "own")
+    model.save(p2)
+    env2, model2, _ = _mk(nenv=8, nsteps=4, nminibatches=1, seed=9, **case)
+    model2.load(p2)
+    assert model2.opt.t == 123456
+    # both accumulators underflowed (very long run): load must not raise and the bias correction is 1
+    ck["beta2_power:0"] = np.float32(0.0)
+    joblib.dump(ck, path)
+    model2.load(path)
+    assert model2.opt.t >= 10 ** 5
