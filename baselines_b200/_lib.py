@@ -75,6 +75,7 @@ def load():
 
 LAUNCHES = 0          # C-ABI kernel-launching calls made by this process (bench.py reports the delta)
 _prof = None          # list of (label, start_event, end_event, flops, bytes) while profiling
+phase = ""            # profile-label suffix ("@act" / "@train"): the same kernel runs at two very different sizes
 
 
 def call(name, *args, label=None, flops=0, nbytes=0):
@@ -87,7 +88,7 @@ def call(name, *args, label=None, flops=0, nbytes=0):
         e0.record()
         rc = getattr(lib, name)(*args)
         e1.record()
-        _prof.append((label or name, e0, e1, flops, nbytes))
+        _prof.append(((label or name) + phase, e0, e1, flops, nbytes))
     else:
         rc = getattr(lib, name)(*args)
     if rc != 0:

@@ -8,7 +8,7 @@ explicit sequence of libb200rl kernel launches.
 import numpy as np
 import torch
 
-from .. import nn, ops
+from .. import _lib, nn, ops
 from . import spaces
 
 
@@ -220,6 +220,7 @@ class PolicyNet:
 
     def act(self, x, B, actions, values, neglogp, noise=None, seed=0, offset=0):
         """PolicyWithValue.step (policies.py:77-96) into caller-provided device tensors."""
+        _lib.phase = "@act"
         self.forward(x, B)
         if self.discrete:
             ops.cat_step(self.pi_out, self.ld_pi, self.nout, self.v_out, self.ld_v, actions, values, neglogp, B,
@@ -232,6 +233,7 @@ class PolicyNet:
                       inv_M):
         """One chunk of ppo2/model.py:57-114: forward, loss statistics, full backward into store.grads
         (gradients of the MEAN loss: every wgrad carries alpha = 1/M)."""
+        _lib.phase = "@train"
         self.forward(x, B, src_idx)
         if self.discrete:
             ops.cat_loss(self.pi_out, self.ld_pi, self.nout, self.v_out, self.ld_v, actions, src_idx, returns,

@@ -148,10 +148,19 @@ class PrioritizedReplayBuffer(ReplayBuffer):
         dev = self.device
         self._it_sum = torch.zeros(2 * it_capacity, dtype=torch.float64, device=dev)
         self._it_min = torch.full((2 * it_capacity,), float("inf"), dtype=torch.float64, device=dev)
-        self._max_priority = 1.0
+        # running max of the priorities (replay_buffer.py:98,191) lives on the device so that the resident train loop
+        # never reads it back; the host attribute `_max_priority` is a view that synchronises only when somebody asks
         self._maxp_dev = torch.ones(1, dtype=torch.float64, device=dev)
         self._arange = torch.arange(self._stage_cap, dtype=torch.int64, device=dev)
         self._new_val = torch.zeros(self._stage_cap, dtype=torch.float64, device=dev)
+
+    @property
+    def _max_priority(self):
+        return float(self._maxp_dev.item())
+
+    @_max_priority.setter
+    def _max_priority(self, v):
+        self._maxp_dev.fill_(float(v))
 
     def _set_priorities(self, idx_t, vals_t):
         ops.tree_set(self._it_sum, self._it_min, self._cap, idx_t, vals_t)
@@ -163,13 +172,13 @@ class PrioritizedReplayBuffer(ReplayBuffer):
         return super().add(*args, **kwargs)
 
     def _on_flush_range(self, lo, n):
-        self._new_val[:n].fill_(self._max_priority ** self._alpha)
-        self._set_priorities(self._arange[:n] + lo, self._new_val[:n])
+        torch.pow(self._maxp_dev, self._alpha, out=self._new_val[:1])          # scalar bookkeeping, stays on the device
+        self._set_priorities(self._arange[:n] + lo, self._new_val[:1].expand(n).contiguous())
 
     def add_batch(self, *args, **kwargs):
         idx = super().add_batch(*args, **kwargs)
         it = torch.from_numpy(np.asarray(idx, dtype=np.int64)).to(self.device)
-        vals = torch.full((len(idx),), self._max_priority ** self._alpha, dtype=torch.float64, device=self.device)
+        vals = torch.pow(self._maxp_dev, self._alpha).expand(len(idx)).contiguous()
         self._set_priorities(it, vals)
         return idx
 
@@ -204,7 +213,6 @@ class PrioritizedReplayBuffer(ReplayBuffer):
         vals = torch.as_tensor(np.array([p ** self._alpha for p in pr], dtype=np.float64)).to(self.device)
         self._set_priorities(it, vals)
         self._max_priority = max(self._max_priority, max(pr))
-        self._maxp_dev[0] = self._max_priority
 
     def update_priorities_device(self, idx, td_errors, eps):
         """new_priorities = |td| + eps (deepq.py:302); p ** alpha and the running max are computed on device."""
@@ -212,4 +220,3 @@ class PrioritizedReplayBuffer(ReplayBuffer):
         powered = torch.empty(idx.numel(), dtype=torch.float64, device=self.device)
         ops.per_priorities(td_errors, eps, self._alpha, powered, self._maxp_dev)
         self._set_priorities(idx, powered)
-        self._max_priority = float(self._maxp_dev.item())

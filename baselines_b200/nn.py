@@ -496,7 +496,7 @@ class Tower:
                 omap = (0, c.OH * c.OW * c.nf, c.OW * c.nf, c.nf, 0, 0)
             ops.conv_shift_fwd(cur, B, g["Hg"], g["Wg"], g["Cg"], c.w_fwd, c.Kp, c.nf, g["shifts"], c.OH, c.OW,
                                self.hconv[i], omap, bias=c.b, act=c.act, tag="fwd." + c.name,
-                               u8=self._u8 if i == 0 else None, bits_out=self.hbits[i])
+                               u8=self._u8 if i == 0 else None, bits_out=self.hbits[i], useful_rows=B * c.OH * c.OW)
             cur = self.hconv[i]
         return cur, self.flat
 
@@ -509,7 +509,7 @@ class Tower:
             xin = self.x16 if i == 0 else self.hconv[i - 1]
             ops.conv_shift_wgrad(xin, rows, g["Cg"], self.dY[i], c.nf, g["shifts"], c.gw, c.nf,
                                  alpha=alpha * c.in_scale, tag="wgrad." + c.name, gbias=c.gb, alpha_b=alpha,
-                                 u8=self._u8 if i == 0 else None)
+                                 u8=self._u8 if i == 0 else None, useful_rows=B * c.OH * c.OW)
             if i == 0:
                 break
             # dX_i (= dY_{i-1} after the ReLU mask) as a shift-GEMM over dY_i with negative shifts
@@ -519,7 +519,7 @@ class Tower:
             ops.conv_shift_fwd(self.dY[i], B, g["Hg"], g["Wg"], c.nf, self.wd[i], g["k"] * g["k"] * c.nf, g["Cg"],
                                [-sft for sft in g["shifts"]], g["Hg"], g["Wg"], self.dY[i - 1], omap,
                                saved=self.hconv[i - 1], smap=smap, act=ops.ACT_RELU, dact=True, tag="dgrad." + c.name,
-                               saved_bits=self.hbits[i - 1])
+                               saved_bits=self.hbits[i - 1], useful_rows=B * c.OH * c.OW)
 
     def refresh(self):
         for l in self.layers:

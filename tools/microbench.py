@@ -183,8 +183,9 @@ def run(only=None, quick=False):
     out = {"l2_flush": "512 MB write between iterations"}
     Ms = [8192, 131072] if not quick else [131072]
     cases = [
+        # cfg-2 size (L2-resident), cfg-3 size (142 MB ~ L2), and 4x L2 (570 MB: a DRAM steady-state measurement)
         ("gae", "gae", lambda: [gae_case(128, 4096, -1, flush), gae_case(512, 16384, 1, flush),
-                                gae_case(512, 16384, 0, flush)]),
+                                gae_case(512, 16384, 0, flush), gae_case(2048, 16384, 1, flush)]),
         ("fc1", "fc1", lambda: [fc1_case(M, k, flush) for M in Ms for k in ("fwd", "dgrad", "wgrad")]),
         ("gae", "gae_cpu", lambda: [gae_cpu_case(128, 4096), gae_cpu_case(512, 16384)]),
         ("per", "per", lambda: per_case(flush)),
