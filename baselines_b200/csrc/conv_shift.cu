@@ -228,8 +228,9 @@ struct ShiftParams {
   FastDiv fwg, fhg;        // epilogue row -> (n, y, x)
   long long M;             // grid rows = B*Hg*Wg
   int Hg, Wg;              // grid
-  int N;                   // output channels of the GEMM
-  int taps;
+  int N;                   // output channels of the conv (the MMA's N is KX * N when the x-taps are folded)
+  int taps;                // taps the MMA loop accumulates over (KX > 1: the ky row-taps only)
+  int tstep;               // output rows per tile: 128 - (KX - 1)
   int shift[SH_MAX_TAPS];  // row shift of tap t, relative to min_shift (>= 0)
   int min_shift;           // smallest absolute shift (negative for dgrad)
   int vy, vx;              // rows with y < vy && x < vx produce an output
@@ -246,14 +247,23 @@ struct ShiftParams {
 };
 
 // ------------------------------------------------------------------------------------------------ forward / dgrad
-template <int BN, int KH, bool DACT, bool U8>
+// KX > 1 ("x-fold"): the KX horizontally adjacent filter taps of one filter row are folded into the MMA's N
+// dimension -- D[m, (b, n)] = sum_{a, c} X[m + a*Wg, c] * W[(a, b), c, n] -- so every A slab is fetched from shared
+// memory once per filter ROW instead of once per tap (tcgen05 SS operand fetch is 128 B/clk and is the bound of
+// these N <= 64 kernels, profiles/r2_mma_probe.jsonl).  The epilogue finishes the sum across lanes:
+// out[m, n] = sum_b D[m + b, b*N + n] (warp shuffle by b lanes; the last b lanes of a warp take the rows from the next
+// warp through a tiny smem exchange; tiles overlap by KX - 1 rows so nothing crosses a tile).
+template <int BN, int KH, bool DACT, bool U8, int KX>
 __global__ void __launch_bounds__(SH_FWD_THREADS + (U8 ? U8_THREADS : 0), 1)
 conv_shift_fwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW,
                       const __grid_constant__ ShiftParams p) {
+  static_assert(KX == 1 || !DACT, "the data gradient keeps one MMA group per tap");
+  constexpr int NO = BN / KX;                        // output channels
+  constexpr int TSTEP = SH_BM - (KX - 1);
   constexpr int STAGE_BYTES = KH * SH_ABYTES;
   constexpr int STAGES = (KH == 1) ? 6 : 3;
   constexpr int W_SUB = BN * 128;                    // one (tap, half) weight sub-tile
-  constexpr int TMEM_COLS = (2 * BN <= 64) ? 64 : (2 * BN <= 128) ? 128 : 256;
+  constexpr int TMEM_COLS = (2 * BN <= 64) ? 64 : (2 * BN <= 128) ? 128 : (2 * BN <= 256) ? 256 : 512;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* wres = smem + STAGES * STAGE_BYTES;       // resident weights: taps*KH sub-tiles
@@ -265,9 +275,13 @@ conv_shift_fwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_cons
   uint64_t* w_bar = bars + 2 * STAGES + 4;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 5);
 
-  __shared__ float s_bias[BN];
+  __shared__ float s_bias[NO];
+  // x-fold halo exchange: [accumulator stage][parity][warp][halo row slot][column of the current chunk]
+  constexpr int XG = (KX == 1) ? 1 : (NO >= 64 ? 2 : NO / 16);        // 16-column chunks combined per exchange round
+  constexpr int XROWS = (KX * (KX - 1)) / 2;                          // sum_b b halo rows per warp
+  __shared__ float s_xch[(KX > 1) ? 2 : 1][2][4][(KX > 1) ? XROWS : 1][16 * XG];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  if (threadIdx.x < BN) s_bias[threadIdx.x] = (p.bias && (int)threadIdx.x < p.N) ? p.bias[threadIdx.x] : 0.0f;
+  if (threadIdx.x < NO) s_bias[threadIdx.x] = (p.bias && (int)threadIdx.x < p.N) ? p.bias[threadIdx.x] : 0.0f;
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmX);
     tma_prefetch_desc(&tmW);
@@ -301,7 +315,7 @@ conv_shift_fwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_cons
         if (elect_one()) {
           uint8_t* sa = smem + s * STAGE_BYTES;
           mbar_arrive_expect_tx(&full_bar[s], (uint32_t)STAGE_BYTES);
-          const int row0 = tile * SH_BM + p.min_shift;                  // may be negative: TMA zero-fills
+          const int row0 = tile * TSTEP + p.min_shift;                  // may be negative: TMA zero-fills
 #pragma unroll
           for (int h = 0; h < KH; ++h) tma_load_2d(sa + h * SH_ABYTES, &tmX, &full_bar[s], h * 64, row0);
         }
@@ -315,7 +329,7 @@ conv_shift_fwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_cons
     const int ntiles = first < p.num_tiles ? (p.num_tiles - first + step - 1) / step : 0;
     const int min_shift = p.min_shift;
     u8_producer_loop<SH_AROWS, STAGES>(
-        p.u8, p.M, ntiles, [=](int seq) { return (long long)(first + seq * step) * SH_BM + min_shift; }, smem,
+        p.u8, p.M, ntiles, [=](int seq) { return (long long)(first + seq * step) * TSTEP + min_shift; }, smem,
         STAGE_BYTES, full_bar, empty_bar, wres + 16384, warp - 12, lane);
   } else if (warp == 1) {
     constexpr uint32_t IDESC = (1u << 4) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(SH_BM >> 4) << 24);
@@ -360,95 +374,175 @@ conv_shift_fwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_cons
     const int ew = warp & 3;
     const int as = (warp - 4) >> 2;
     uint32_t aph = 0;
-    constexpr int G = (BN >= 64) ? 4 : BN / 16;       // 16-column chunks handled together (loads in flight)
-    for (int tile = blockIdx.x + as * (int)gridDim.x; tile < p.num_tiles; tile += 2 * (int)gridDim.x) {
-      const uint32_t m = (uint32_t)tile * SH_BM + ew * 32 + lane;       // M < 2^31 (checked on the host)
-      const uint32_t t2 = p.fwg.div(m);
-      const int x = (int)(m - t2 * (uint32_t)p.Wg);
-      const int n = (int)p.fhg.div(t2);
-      const int y = (int)(t2 - (uint32_t)n * (uint32_t)p.Hg);
-      const bool ok = ((long long)m < p.M) && (y < p.vy) && (x < p.vx);
-      const long long obase = map_rowbase(p.omap, n, y, x);
-      const long long sbase = p.saved ? map_rowbase(p.smap, n, y, x) : 0;
-      const bool masked = DACT && p.saved != nullptr;
-      // branch-free activation: relu(x) = max(x, 0), identity = max(x, -inf); relu'(h) = (h > 0), 1 = (h > -inf).
-      // (The epilogue is instruction-FETCH bound when its unrolled body outgrows the L0 / L1.5 I-caches, so it is
-      // kept small: no tanh here, no per-element mode switches.)
-      const float lo = (p.act == ACT_RELU) ? 0.0f : -INFINITY;
-      mbar_wait(&tfull_bar[as], aph);
-      tc_fence_after();
-      const uint32_t taddr0 = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(as * BN);
+    if constexpr (KX > 1) {
+      uint32_t par = 0;
+      for (int tile = blockIdx.x + as * (int)gridDim.x; tile < p.num_tiles; tile += 2 * (int)gridDim.x) {
+        const int ml = ew * 32 + lane;
+        const uint32_t m = (uint32_t)tile * TSTEP + ml;
+        const uint32_t t2 = p.fwg.div(m);
+        const int x = (int)(m - t2 * (uint32_t)p.Wg);
+        const int n = (int)p.fhg.div(t2);
+        const int y = (int)(t2 - (uint32_t)n * (uint32_t)p.Hg);
+        const bool ok = (ml < TSTEP) && ((long long)m < p.M) && (y < p.vy) && (x < p.vx);
+        const long long obase = map_rowbase(p.omap, n, y, x);
+        const float lo = (p.act == ACT_RELU) ? 0.0f : -INFINITY;
+        mbar_wait(&tfull_bar[as], aph);
+        tc_fence_after();
+        const uint32_t taddr0 = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(as * BN);
 #pragma unroll 1
-      for (int c0 = 0; c0 < BN; c0 += 16 * G) {
-        uint32_t sv[G][8];
-        if (DACT) {
-          if (masked && ok && p.saved_bits != nullptr) {
-            // 1 bit per element instead of the fp16 activation: 2 B instead of 32 B of HBM traffic per 16 columns;
-            // expanded to the half2 words {1.0 | 0.0} the mask code below expects
-            uint32_t bw[G];
+        for (int c0 = 0; c0 < NO; c0 += 16 * XG) {
+          uint32_t r[KX][XG][16];
 #pragma unroll
-            for (int j = 0; j < G; ++j)
-              bw[j] = __ldg(p.saved_bits + ((sbase + map_coloff(p.smap, c0 + 16 * j)) >> 4));
+          for (int b = 0; b < KX; ++b)
 #pragma unroll
-            for (int j = 0; j < G; ++j)
+            for (int j = 0; j < XG; ++j) tmem_ld16(taddr0 + b * NO + c0 + 16 * j, r[b][j]);
+          tmem_ld_wait();
+          // rows this warp's first lanes hold are the halo of the previous warp: publish them
 #pragma unroll
-              for (int i = 0; i < 8; ++i)
-                sv[j][i] = (((bw[j] >> (2 * i)) & 1u) ? 0x3c00u : 0u) | (((bw[j] >> (2 * i + 1)) & 1u) ? 0x3c000000u : 0u);
-          } else if (masked && ok) {
+          for (int b = 1; b < KX; ++b) {
+            if (lane < b) {
+              float* dst = s_xch[as][par][ew][(b * (b - 1)) / 2 + lane];
 #pragma unroll
-            for (int j = 0; j < G; ++j) {
-              ldg256(p.saved + sbase + map_coloff(p.smap, c0 + 16 * j), sv[j]);
+              for (int j = 0; j < XG; ++j)
+#pragma unroll
+                for (int i = 0; i < 16; ++i) dst[16 * j + i] = __uint_as_float(r[b][j][i]);
             }
-          } else {
-#pragma unroll
-            for (int j = 0; j < G; ++j)
-#pragma unroll
-              for (int i = 0; i < 8; ++i) sv[j][i] = 0x3c003c00u;
           }
-        }
-        uint32_t r[G][16];
+          asm volatile("bar.sync %0, 128;" ::"r"(1 + as) : "memory");
 #pragma unroll
-        for (int j = 0; j < G; ++j) tmem_ld16(taddr0 + c0 + 16 * j, r[j]);
-        tmem_ld_wait();
-        if (ok) {
+          for (int b = 1; b < KX; ++b) {
+            const bool halo = lane >= 32 - b;
+            const float* src = s_xch[as][par][(ew + 1) & 3][(b * (b - 1)) / 2 + (halo ? lane - (32 - b) : 0)];
 #pragma unroll
-          for (int j = 0; j < G; ++j) {
-            const int c = c0 + 16 * j;
-            uint32_t packed[8];
-            if (DACT) {
+            for (int j = 0; j < XG; ++j)
+#pragma unroll
+              for (int i = 0; i < 16; ++i) {
+                float v = __shfl_down_sync(0xffffffffu, __uint_as_float(r[b][j][i]), b);
+                if (halo) v = (ew < 3) ? src[16 * j + i] : 0.0f;
+                r[0][j][i] = __float_as_uint(__uint_as_float(r[0][j][i]) + v);
+              }
+          }
+          par ^= 1;
+          if (ok) {
+#pragma unroll
+            for (int j = 0; j < XG; ++j) {
+              const int c = c0 + 16 * j;
+              uint32_t packed[8];
 #pragma unroll
               for (int i = 0; i < 8; ++i) {
-                const float2 h = __half22float2(*reinterpret_cast<const __half2*>(&sv[j][i]));
-                const float a = (h.x > lo) ? __uint_as_float(r[j][2 * i]) * p.alpha : 0.0f;
-                const float b = (h.y > lo) ? __uint_as_float(r[j][2 * i + 1]) * p.alpha : 0.0f;
-                const __half2 o = __floats2half2_rn(a, b);
+                const float a = fmaxf(fmaf(__uint_as_float(r[0][j][2 * i]), p.alpha, s_bias[c + 2 * i]), lo);
+                const float b2 = fmaxf(fmaf(__uint_as_float(r[0][j][2 * i + 1]), p.alpha, s_bias[c + 2 * i + 1]), lo);
+                const __half2 o = __floats2half2_rn(a, b2);
                 packed[i] = *reinterpret_cast<const uint32_t*>(&o);
+              }
+              const long long eo = obase + map_coloff(p.omap, c);
+              stg256(p.out + eo, packed);
+              if (p.bits_out != nullptr) {
+                uint32_t bits = 0;
+#pragma unroll
+                for (int i = 0; i < 8; ++i)
+                  bits |= (((packed[i] & 0x7fffu) != 0u) ? (1u << (2 * i)) : 0u) |
+                          (((packed[i] & 0x7fff0000u) != 0u) ? (2u << (2 * i)) : 0u);
+                p.bits_out[eo >> 4] = (uint16_t)bits;
+              }
+            }
+          }
+        }
+        tc_fence_before();
+        mbar_arrive(&tempty_bar[as]);
+        aph ^= 1;
+      }
+    } else {
+      constexpr int G = (BN >= 64) ? 4 : BN / 16;       // 16-column chunks handled together (loads in flight)
+      for (int tile = blockIdx.x + as * (int)gridDim.x; tile < p.num_tiles; tile += 2 * (int)gridDim.x) {
+        const uint32_t m = (uint32_t)tile * SH_BM + ew * 32 + lane;       // M < 2^31 (checked on the host)
+        const uint32_t t2 = p.fwg.div(m);
+        const int x = (int)(m - t2 * (uint32_t)p.Wg);
+        const int n = (int)p.fhg.div(t2);
+        const int y = (int)(t2 - (uint32_t)n * (uint32_t)p.Hg);
+        const bool ok = ((long long)m < p.M) && (y < p.vy) && (x < p.vx);
+        const long long obase = map_rowbase(p.omap, n, y, x);
+        const long long sbase = p.saved ? map_rowbase(p.smap, n, y, x) : 0;
+        const bool masked = DACT && p.saved != nullptr;
+        // branch-free activation: relu(x) = max(x, 0), identity = max(x, -inf); relu'(h) = (h > 0), 1 = (h > -inf).
+        // (The epilogue is instruction-FETCH bound when its unrolled body outgrows the L0 / L1.5 I-caches, so it is
+        // kept small: no tanh here, no per-element mode switches.)
+        const float lo = (p.act == ACT_RELU) ? 0.0f : -INFINITY;
+        mbar_wait(&tfull_bar[as], aph);
+        tc_fence_after();
+        const uint32_t taddr0 = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(as * BN);
+  #pragma unroll 1
+        for (int c0 = 0; c0 < BN; c0 += 16 * G) {
+          uint32_t sv[G][8];
+          if (DACT) {
+            if (masked && ok && p.saved_bits != nullptr) {
+              // 1 bit per element instead of the fp16 activation: 2 B instead of 32 B of HBM traffic per 16 columns;
+              // expanded to the half2 words {1.0 | 0.0} the mask code below expects
+              uint32_t bw[G];
+  #pragma unroll
+              for (int j = 0; j < G; ++j)
+                bw[j] = __ldg(p.saved_bits + ((sbase + map_coloff(p.smap, c0 + 16 * j)) >> 4));
+  #pragma unroll
+              for (int j = 0; j < G; ++j)
+  #pragma unroll
+                for (int i = 0; i < 8; ++i)
+                  sv[j][i] = (((bw[j] >> (2 * i)) & 1u) ? 0x3c00u : 0u) | (((bw[j] >> (2 * i + 1)) & 1u) ? 0x3c000000u : 0u);
+            } else if (masked && ok) {
+  #pragma unroll
+              for (int j = 0; j < G; ++j) {
+                ldg256(p.saved + sbase + map_coloff(p.smap, c0 + 16 * j), sv[j]);
               }
             } else {
-#pragma unroll
-              for (int i = 0; i < 8; ++i) {
-                const float a = fmaxf(fmaf(__uint_as_float(r[j][2 * i]), p.alpha, s_bias[c + 2 * i]), lo);
-                const float b = fmaxf(fmaf(__uint_as_float(r[j][2 * i + 1]), p.alpha, s_bias[c + 2 * i + 1]), lo);
-                const __half2 o = __floats2half2_rn(a, b);
-                packed[i] = *reinterpret_cast<const uint32_t*>(&o);
-              }
+  #pragma unroll
+              for (int j = 0; j < G; ++j)
+  #pragma unroll
+                for (int i = 0; i < 8; ++i) sv[j][i] = 0x3c003c00u;
             }
-            const long long eo = obase + map_coloff(p.omap, c);
-            stg256(p.out + eo, packed);
-            if (!DACT && p.bits_out != nullptr) {
-              uint32_t bits = 0;
-#pragma unroll
-              for (int i = 0; i < 8; ++i)
-                bits |= (((packed[i] & 0x7fffu) != 0u) ? (1u << (2 * i)) : 0u) |
-                        (((packed[i] & 0x7fff0000u) != 0u) ? (2u << (2 * i)) : 0u);
-              p.bits_out[eo >> 4] = (uint16_t)bits;
+          }
+          uint32_t r[G][16];
+  #pragma unroll
+          for (int j = 0; j < G; ++j) tmem_ld16(taddr0 + c0 + 16 * j, r[j]);
+          tmem_ld_wait();
+          if (ok) {
+  #pragma unroll
+            for (int j = 0; j < G; ++j) {
+              const int c = c0 + 16 * j;
+              uint32_t packed[8];
+              if (DACT) {
+  #pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                  const float2 h = __half22float2(*reinterpret_cast<const __half2*>(&sv[j][i]));
+                  const float a = (h.x > lo) ? __uint_as_float(r[j][2 * i]) * p.alpha : 0.0f;
+                  const float b = (h.y > lo) ? __uint_as_float(r[j][2 * i + 1]) * p.alpha : 0.0f;
+                  const __half2 o = __floats2half2_rn(a, b);
+                  packed[i] = *reinterpret_cast<const uint32_t*>(&o);
+                }
+              } else {
+  #pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                  const float a = fmaxf(fmaf(__uint_as_float(r[j][2 * i]), p.alpha, s_bias[c + 2 * i]), lo);
+                  const float b = fmaxf(fmaf(__uint_as_float(r[j][2 * i + 1]), p.alpha, s_bias[c + 2 * i + 1]), lo);
+                  const __half2 o = __floats2half2_rn(a, b);
+                  packed[i] = *reinterpret_cast<const uint32_t*>(&o);
+                }
+              }
+              const long long eo = obase + map_coloff(p.omap, c);
+              stg256(p.out + eo, packed);
+              if (!DACT && p.bits_out != nullptr) {
+                uint32_t bits = 0;
+  #pragma unroll
+                for (int i = 0; i < 8; ++i)
+                  bits |= (((packed[i] & 0x7fffu) != 0u) ? (1u << (2 * i)) : 0u) |
+                          (((packed[i] & 0x7fff0000u) != 0u) ? (2u << (2 * i)) : 0u);
+                p.bits_out[eo >> 4] = (uint16_t)bits;
+              }
             }
           }
         }
+        tc_fence_before();
+        mbar_arrive(&tempty_bar[as]);
+        aph ^= 1;
       }
-      tc_fence_before();
-      mbar_arrive(&tempty_bar[as]);
-      aph ^= 1;
     }
   }
   tc_fence_before();
@@ -474,15 +568,22 @@ struct ShiftWgradParams {
   int kb_total, kb_per_cta;
 };
 
-template <int BN, int KH, bool U8>
+// KX > 1 ("x-fold", see the forward kernel): the accumulator holds G for one filter row a and all KX taps b of it,
+//   D[(a, h, c), (j, n)] = sum_m' X[m' + a*Wg, h*64 + c] * dY[m' - (KX-1-j), n]         (b = KX - 1 - j)
+// i.e. the MMA's N dimension is KX copies of the dY tile, each starting ONE ROW earlier (descriptor LBO = one row of
+// the tile), so the X slab is fetched once per filter row instead of once per tap.  BN stays the number of dY channels.
+template <int BN, int KH, bool U8, int KX>
 __global__ void __launch_bounds__(SH_THREADS + (U8 ? U8_THREADS : 0), 1)
 conv_shift_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmD,
                         const __grid_constant__ ShiftWgradParams p) {
   constexpr int BROWB = (BN >= 64) ? 128 : BN * 2;            // dY row bytes in smem
   constexpr uint32_t LAYOUT_B = (BROWB == 64) ? 4u : 2u;
-  constexpr int B_BYTES = 64 * BROWB;
-  constexpr int STAGE_BYTES = KH * SH_WABYTES + 8192;         // A halves + B (<= 8 KB), keeps 1024 B alignment
-  constexpr int STAGES = (KH == 1) ? 8 : 6;
+  constexpr int BROWS = 64 + (KX - 1);                        // dY rows per stage (halo of KX - 1 rows in front)
+  constexpr int B_BYTES = BROWS * BROWB;
+  constexpr int B_REGION = (B_BYTES + 1023) & ~1023;
+  constexpr int STAGE_BYTES = KH * SH_WABYTES + B_REGION;     // A halves + B, keeps 1024 B alignment
+  constexpr int STAGES = (KH == 1) ? 8 : (KX == 1 ? 6 : 5);
+  constexpr int NW = KX * BN;                                 // MMA N
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
@@ -494,7 +595,7 @@ conv_shift_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_co
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int kb0 = blockIdx.x * p.kb_per_cta;
   const int kb1 = min(kb0 + p.kb_per_cta, p.kb_total);
-  const int nchunks = p.taps * KH;                  // 64-row chunks of the output matrix G
+  const int nchunks = p.taps * KH;                  // 64-row chunks of the accumulator rows
   const int n_mt = (nchunks + 1) / 2;               // 128-row accumulator tiles
 
   if (warp == 0 && lane == 0) {
@@ -527,7 +628,7 @@ conv_shift_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_co
 #pragma unroll
           for (int h = 0; h < KH; ++h) tma_load_2d(sa + h * SH_WABYTES, &tmX, &full_bar[s], h * 64, kb * 64);
         }
-        tma_load_2d(sa + KH * SH_WABYTES, &tmD, &full_bar[s], 0, kb * 64);
+        tma_load_2d(sa + KH * SH_WABYTES, &tmD, &full_bar[s], 0, kb * 64 - (KX - 1));   // negative rows: zero fill
       }
       __syncwarp();
       if (++s == STAGES) { s = 0; ph ^= 1; }
@@ -537,7 +638,7 @@ conv_shift_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_co
         p.u8, p.M, kb1 - kb0, [=](int seq) { return (long long)(kb0 + seq) * 64; }, smem, STAGE_BYTES, full_bar,
         empty_bar, smem + STAGES * STAGE_BYTES + 256, warp - 8, lane);
   } else if (warp == 1) {
-    constexpr uint32_t IDESC = (1u << 4) | (1u << 15) | (1u << 16) | ((uint32_t)(BN >> 3) << 17) |
+    constexpr uint32_t IDESC = (1u << 4) | (1u << 15) | (1u << 16) | ((uint32_t)(NW >> 3) << 17) |
                                ((uint32_t)(SH_BM >> 4) << 24);
     {
       int s = 0;
@@ -548,14 +649,15 @@ conv_shift_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_co
         if (elect_one()) {
         const uint32_t a_addr = smem_u32(smem + s * STAGE_BYTES);
         const uint32_t b_addr = a_addr + KH * SH_WABYTES;
-        const uint64_t bdesc0 = make_sdesc(b_addr, 64 * BROWB, 8 * BROWB, LAYOUT_B);
+        // KX == 1: one chunk (LBO unused).  KX > 1: N-chunk j of the dY operand starts j rows further into the tile
+        const uint64_t bdesc0 = make_sdesc(b_addr, KX == 1 ? 64 * BROWB : BROWB, 8 * BROWB, LAYOUT_B);
         for (int j = 0; j < n_mt; ++j) {
           const int q0 = 2 * j, q1 = 2 * j + 1;
           const uint32_t st0 = a_addr + (q0 % KH) * SH_WABYTES + p.shift[q0 / KH] * 128;
           uint32_t lbo = 128;
           if (q1 < nchunks) lbo = (a_addr + (q1 % KH) * SH_WABYTES + p.shift[q1 / KH] * 128) - st0;
           const uint64_t adesc0 = make_sdesc(st0, lbo, 1024, 2u);
-          const uint32_t td = tmem_base + (uint32_t)(j * BN);
+          const uint32_t td = tmem_base + (uint32_t)(j * NW);
 #pragma unroll
           for (int k = 0; k < 4; ++k)
             umma_f16(td, adesc0 + (uint64_t)(k * (16 * 128 / 16)), bdesc0 + (uint64_t)(k * (16 * BROWB / 16)), IDESC,
@@ -587,7 +689,7 @@ conv_shift_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_co
         mbar_wait(&full_bar[s], ph);
         const uint8_t* sb = smem + s * STAGE_BYTES + KH * SH_WABYTES;
 #pragma unroll 8
-        for (int r = rg; r < 64; r += RG) {
+        for (int r = rg + (KX - 1); r < 64 + (KX - 1); r += RG) {           // the halo rows belong to the previous block
           const int sw = (BROWB == 128) ? (r & 7) : ((r >> 1) & 3);
           const uint2 w = *reinterpret_cast<const uint2*>(sb + r * BROWB + ((chunk ^ sw) << 4) + within);
           a[0] += __half2float(__ushort_as_half((unsigned short)(w.x & 0xffffu)));
@@ -613,17 +715,22 @@ conv_shift_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_co
       tc_fence_after();
       const int mrows = nchunks * 64;
       for (int j = 0; j < n_mt; ++j) {
-        const int row = j * 128 + ew * 32 + lane;
+        const int row = j * 128 + ew * 32 + lane;               // accumulator row = (a, h, c): chunk q = row / 64
+        // G row of accumulator row (q, c) and N-chunk jb: tap (a, b = KX-1-jb) -> ((a*KX + b)*KH + h)*64 + c
+        const int q = row >> 6, cc = row & 63;
+        const int ta = q / KH, th = q - ta * KH;
 #pragma unroll 1
-        for (int c = 0; c < BN; c += 16) {
+        for (int c = 0; c < NW; c += 16) {
           uint32_t r[16];
-          tmem_ld16(tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(j * BN + c), r);
+          tmem_ld16(tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(j * NW + c), r);
           tmem_ld_wait();
-          if (row < mrows && c < p.N) {
-            float* out = p.G + (long long)row * p.ldg + c;
+          const int jb = c / BN, cn = c - jb * BN;
+          if (row < mrows && cn < p.N) {
+            const long long grow = (long long)((ta * KX + (KX - 1 - jb)) * KH + th) * 64 + cc;
+            float* out = p.G + grow * p.ldg + cn;
 #pragma unroll
             for (int i = 0; i < 16; ++i)
-              if (c + i < p.N) atomicAdd(out + i, __uint_as_float(r[i]) * p.alpha);
+              if (cn + i < p.N) atomicAdd(out + i, __uint_as_float(r[i]) * p.alpha);
           }
         }
       }
@@ -652,12 +759,12 @@ static U8Src make_u8src(const void* x, const long long* idx, int H, int W, int C
   return u;
 }
 
-template <int BN, int KH, bool DACT, bool U8 = false>
+template <int BN, int KH, bool DACT, bool U8 = false, int KX = 1>
 static int launch_fwd(const CUtensorMap& tmX, const CUtensorMap& tmW, const ShiftParams& p, cudaStream_t st) {
   constexpr int STAGES = (KH == 1) ? 6 : 3;
   constexpr int SMEM = STAGES * KH * SH_ABYTES + 80 * 1024 + 1024 + 256;
   static bool attr = false;
-  auto kern = conv_shift_fwd_kernel<BN, KH, DACT, U8>;
+  auto kern = conv_shift_fwd_kernel<BN, KH, DACT, U8, KX>;
   if (!attr) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
     if (e != cudaSuccess) {
@@ -671,14 +778,16 @@ static int launch_fwd(const CUtensorMap& tmX, const CUtensorMap& tmW, const Shif
   return check_launch("conv_shift_fwd_kernel");
 }
 
-template <int BN, int KH, bool U8 = false>
+template <int BN, int KH, bool U8 = false, int KX = 1>
 static int launch_wgrad(const CUtensorMap& tmX, const CUtensorMap& tmD, const ShiftWgradParams& p, int grid,
                         cudaStream_t st) {
-  constexpr int STAGES = (KH == 1) ? 8 : 6;
-  constexpr int SMEM = STAGES * (KH * SH_WABYTES + 8192) + 1024 + 256 +
-                       (U8 ? U8_RING_BYTES : 0);
+  constexpr int STAGES = (KH == 1) ? 8 : (KX == 1 ? 6 : 5);
+  constexpr int BROWB = (BN >= 64) ? 128 : BN * 2;
+  constexpr int B_REGION = ((64 + KX - 1) * BROWB + 1023) & ~1023;
+  constexpr int SMEM = STAGES * (KH * SH_WABYTES + B_REGION) + 1024 + 256 + (U8 ? U8_RING_BYTES : 0);
+  static_assert(SMEM <= 227 * 1024, "conv_shift_wgrad: shared memory budget");
   static bool attr = false;
-  auto kern = conv_shift_wgrad_kernel<BN, KH, U8>;
+  auto kern = conv_shift_wgrad_kernel<BN, KH, U8, KX>;
   if (!attr) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
     if (e != cudaSuccess) {
@@ -707,8 +816,10 @@ int conv_shift_fwd_impl(const void* X, long long B, int Hg, int Wg, int C, const
                         int taps, const int* shifts, int vy, int vx, void* out, const long long* omap,
                         const void* saved, const long long* smap, const float* bias, int act, int dact, float alpha,
                         const void* u8_x, const long long* u8_idx, int u8_H, int u8_W, int u8_C, int u8_s,
-                        void* bits_out, const void* saved_bits, cudaStream_t stream) {
+                        void* bits_out, const void* saved_bits, int kx, cudaStream_t stream) {
   B200RL_REQUIRE((X || u8_x) && W && out && omap && B > 0, "conv_shift_fwd: null operand");
+  if (kx < 1) kx = 1;
+  B200RL_REQUIRE(kx <= 3 && (kx == 1 || !dact), "conv_shift_fwd: kx must be 1..3 (forward only)");
   B200RL_REQUIRE(!(bits_out && dact) && !(saved_bits && !(dact && smap)), "conv_shift_fwd: bits_out is a forward output, saved_bits a dact input (with smap)");
   if (u8_x) {
     B200RL_REQUIRE(C == 64 && u8_s * u8_C == 16 && u8_s == 4 && u8_H == Hg * u8_s && u8_W == Wg * u8_s && !dact &&
@@ -718,7 +829,7 @@ int conv_shift_fwd_impl(const void* X, long long B, int Hg, int Wg, int C, const
   B200RL_REQUIRE(C == 64 || C == 128, "conv_shift_fwd: C must be 64 or 128 (got %d)", C);
   B200RL_REQUIRE(N == 32 || N == 64 || N == 128, "conv_shift_fwd: N must be 32, 64 or 128 (got %d)", N);
   B200RL_REQUIRE(taps >= 1 && taps <= SH_MAX_TAPS, "conv_shift_fwd: 1..%d taps", SH_MAX_TAPS);
-  B200RL_REQUIRE((long long)taps * (C / 64) * N * 128 <= 80 * 1024, "conv_shift_fwd: weights do not fit in smem");
+  B200RL_REQUIRE((long long)taps * (C / 64) * kx * N * 128 <= 80 * 1024, "conv_shift_fwd: weights do not fit in smem");
   ShiftParams p = {};
   int lo = shifts[0], hi = shifts[0];
   for (int t = 1; t < taps; ++t) { lo = shifts[t] < lo ? shifts[t] : lo; hi = shifts[t] > hi ? shifts[t] : hi; }
@@ -741,21 +852,31 @@ int conv_shift_fwd_impl(const void* X, long long B, int Hg, int Wg, int C, const
     B200RL_REQUIRE(((smap[1] | smap[2] | smap[3]) & 15) == 0 && (reinterpret_cast<uintptr_t>(saved) & 31) == 0,
                    "conv_shift_fwd: saved strides must be multiples of 16 elements, base 32-byte aligned");
   p.bias = bias; p.act = act; p.dact = dact; p.alpha = alpha;
-  p.num_tiles = (int)((p.M + SH_BM - 1) / SH_BM);
+  p.tstep = SH_BM - (kx - 1);
+  p.num_tiles = (int)((p.M + p.tstep - 1) / p.tstep);
   p.u8 = make_u8src(u8_x, u8_idx, u8_H, u8_W, u8_C, u8_s);
   B200RL_REQUIRE(Hg >= 2 && Wg >= 2, "conv_shift_fwd: grid must be at least 2x2");
   p.fwg = make_fastdiv((uint32_t)Wg);
   p.fhg = make_fastdiv((uint32_t)Hg);
   CUtensorMap tmX, tmW;
   int rc;
-  if (u8_x) {
-    if ((rc = make_tmap_2d_f16(&tmW, W, N, (long long)taps * C, ldw, 64, N)) != 0) return rc;
-    return launch_fwd<32, 1, false, true>(tmW, tmW, p, stream);      // tmX unused: A tiles come from the producers
+  B200RL_REQUIRE(act == ACT_NONE || act == ACT_RELU, "conv_shift_fwd: activation must be none or relu");
+  if ((rc = make_tmap_2d_f16(&tmW, W, (long long)kx * N, (long long)taps * C, ldw, 64, kx * N)) != 0) return rc;
+  if (u8_x) {                                                          // tmX unused: A tiles come from the producers
+    if (kx == 2) return launch_fwd<64, 1, false, true, 2>(tmW, tmW, p, stream);
+    B200RL_REQUIRE(kx == 1, "conv_shift_fwd: the uint8-fed first layer supports kx = 1 or 2");
+    return launch_fwd<32, 1, false, true>(tmW, tmW, p, stream);
   }
   if ((rc = make_tmap_2d_f16(&tmX, X, p.M, C, C, 64, SH_AROWS)) != 0) return rc;
-  if ((rc = make_tmap_2d_f16(&tmW, W, N, (long long)taps * C, ldw, 64, N)) != 0) return rc;
   const int KH = C / 64;
-  B200RL_REQUIRE(act == ACT_NONE || act == ACT_RELU, "conv_shift_fwd: activation must be none or relu");
+  if (kx > 1) {
+    if (kx == 2 && N == 32 && KH == 1) return launch_fwd<64, 1, false, false, 2>(tmX, tmW, p, stream);
+    if (kx == 2 && N == 64 && KH == 2) return launch_fwd<128, 2, false, false, 2>(tmX, tmW, p, stream);
+    if (kx == 2 && N == 64 && KH == 1) return launch_fwd<128, 1, false, false, 2>(tmX, tmW, p, stream);
+    if (kx == 3 && N == 64 && KH == 1) return launch_fwd<192, 1, false, false, 3>(tmX, tmW, p, stream);
+    set_last_error("conv_shift_fwd: no x-folded kernel for kx=%d N=%d C=%d", kx, N, C);
+    return B200RL_ERR_UNSUPPORTED;
+  }
 #define SHIFT_FWD_CASE(bn)                                                                                    \
   if (N == bn) {                                                                                              \
     if (dact) return KH == 1 ? launch_fwd<bn, 1, true>(tmX, tmW, p, stream) : launch_fwd<bn, 2, true>(tmX, tmW, p, stream); \
@@ -772,8 +893,10 @@ int conv_shift_fwd_impl(const void* X, long long B, int Hg, int Wg, int C, const
 int conv_shift_wgrad_impl(const void* X, long long rows, int C, const void* dY, int N, int taps, const int* shifts,
                           float* G, long long ldg, float alpha, float* gbias, float alpha_b, int max_ctas,
                           const void* u8_x, const long long* u8_idx, int u8_H, int u8_W, int u8_C, int u8_s,
-                          cudaStream_t stream) {
+                          int kx, cudaStream_t stream) {
   B200RL_REQUIRE((X || u8_x) && dY && G && rows > 0, "conv_shift_wgrad: null operand");
+  if (kx < 1) kx = 1;
+  B200RL_REQUIRE(kx <= 3, "conv_shift_wgrad: kx must be 1..3");
   if (u8_x)
     B200RL_REQUIRE(C == 64 && u8_s == 4 && u8_s * u8_C == 16 && N == 32 && u8_H % 4 == 0 && u8_W % 4 == 0 &&
                        (reinterpret_cast<uintptr_t>(u8_x) & 15) == 0,
@@ -783,7 +906,7 @@ int conv_shift_wgrad_impl(const void* X, long long rows, int C, const void* dY, 
   B200RL_REQUIRE(taps >= 1 && taps <= SH_MAX_TAPS, "conv_shift_wgrad: 1..%d taps", SH_MAX_TAPS);
   const int KH = C / 64;
   const int n_mt = (taps * KH + 1) / 2;
-  B200RL_REQUIRE(n_mt * N <= 512, "conv_shift_wgrad: accumulators exceed TMEM");
+  B200RL_REQUIRE(n_mt * kx * N <= 512, "conv_shift_wgrad: accumulators exceed TMEM");
   ShiftWgradParams p = {};
   for (int t = 0; t < taps; ++t) {
     B200RL_REQUIRE(shifts[t] >= 0 && shifts[t] <= SH_WROWS_K - 64, "conv_shift_wgrad: shift %d out of range", shifts[t]);
@@ -801,9 +924,21 @@ int conv_shift_wgrad_impl(const void* X, long long rows, int C, const void* dY, 
   p.u8 = make_u8src(u8_x, u8_idx, u8_H, u8_W, u8_C, u8_s);
   CUtensorMap tmX, tmD;
   int rc;
-  if ((rc = make_tmap_2d_f16(&tmD, dY, rows, N, N, N < 64 ? N : 64, 64)) != 0) return rc;
-  if (u8_x) return launch_wgrad<32, 1, true>(tmD, tmD, p, grid, stream);
+  if ((rc = make_tmap_2d_f16(&tmD, dY, rows, N, N, N < 64 ? N : 64, 64 + kx - 1)) != 0) return rc;
+  if (u8_x) {
+    if (kx == 2) return launch_wgrad<32, 1, true, 2>(tmD, tmD, p, grid, stream);
+    B200RL_REQUIRE(kx == 1, "conv_shift_wgrad: the uint8-fed first layer supports kx = 1 or 2");
+    return launch_wgrad<32, 1, true>(tmD, tmD, p, grid, stream);
+  }
   if ((rc = make_tmap_2d_f16(&tmX, X, rows, C, C, 64, SH_WROWS_K)) != 0) return rc;
+  if (kx > 1) {
+    if (kx == 2 && N == 32 && KH == 1) return launch_wgrad<32, 1, false, 2>(tmX, tmD, p, grid, stream);
+    if (kx == 2 && N == 64 && KH == 2) return launch_wgrad<64, 2, false, 2>(tmX, tmD, p, grid, stream);
+    if (kx == 2 && N == 64 && KH == 1) return launch_wgrad<64, 1, false, 2>(tmX, tmD, p, grid, stream);
+    if (kx == 3 && N == 64 && KH == 1) return launch_wgrad<64, 1, false, 3>(tmX, tmD, p, grid, stream);
+    set_last_error("conv_shift_wgrad: no x-folded kernel for kx=%d N=%d C=%d", kx, N, C);
+    return B200RL_ERR_UNSUPPORTED;
+  }
   if (N == 32) return KH == 1 ? launch_wgrad<32, 1>(tmX, tmD, p, grid, stream) : launch_wgrad<32, 2>(tmX, tmD, p, grid, stream);
   return KH == 1 ? launch_wgrad<64, 1>(tmX, tmD, p, grid, stream) : launch_wgrad<64, 2>(tmX, tmD, p, grid, stream);
 }

@@ -443,10 +443,17 @@ class Tower:
     def _materialize_shift(self, f16):
         cap, cv = self.cap, self.convs
         self.sg = []                                   # per layer: dict(Hg, Wg, Cg, k, shifts, s)
+        import os
+        xfold = os.environ.get("B200RL_NO_XFOLD", "0") != "1"
         for c in cv:
             s_, k = c.stride, c.rf // c.stride
             Hg, Wg, Cg = c.H // s_, c.W // s_, c.C * s_ * s_
-            self.sg.append(dict(Hg=Hg, Wg=Wg, Cg=Cg, k=k, s=s_, shifts=[a * Wg + b for a in range(k) for b in range(k)]))
+            # x-fold (csrc/conv_shift.cu): the k taps of a filter row ride in the MMA's N dimension; kernels exist for
+            # (k, nf, Cg) in {(2, 32, 64), (2, 64, 64), (2, 64, 128), (3, 64, 64)}
+            kx = k if (xfold and (k, c.nf, Cg) in ((2, 32, 64), (2, 64, 64), (2, 64, 128), (3, 64, 64))) else 1
+            self.sg.append(dict(Hg=Hg, Wg=Wg, Cg=Cg, k=k, s=s_, kx=kx,
+                                shifts=[a * Wg + b for a in range(k) for b in range(k)],
+                                yshifts=[a * Wg for a in range(k)]))
         c0, g0 = cv[0], self.sg[0]
         import os
         # first layer straight from the uint8 images (producer warps gather + cast + space-to-depth in smem)
@@ -467,10 +474,20 @@ class Tower:
         self.dY = [torch.zeros(cap, g["Hg"] * g["Wg"] * c.nf, **f16) for c, g in zip(cv, self.sg)]
         # data-gradient weight operands [N' = Cg, taps * nf] (tap blocks of the master weight side by side)
         self.wd = [None] + [torch.zeros(g["Cg"], g["k"] * g["k"] * c.nf, **f16) for c, g in zip(cv[1:], self.sg[1:])]
+        # x-folded forward operands [kx * nf, ky * Cg]: row b*nf + n, column a*Cg + c = tap (a, b)
+        self.wfold = [torch.zeros(g["kx"] * c.nf, g["k"] * g["Cg"], **f16) if g["kx"] > 1 else None
+                      for c, g in zip(cv, self.sg)]
         self.flat = cv[-1].OH * cv[-1].OW * cv[-1].nf
 
     def _refresh_shift(self):
         for i, (c, g) in enumerate(zip(self.convs, self.sg)):
+            if g["kx"] > 1:
+                k, Cg, nf = g["k"], g["Cg"], c.nf
+                for a in range(k):
+                    for b in range(k):
+                        t = a * k + b
+                        ops.cast_transpose(c.w[t * Cg:(t + 1) * Cg], Cg, nf, None, 0,
+                                           self.wfold[i][b * nf:(b + 1) * nf, a * Cg:], k * Cg, scale=c.in_scale)
             if i == 0:
                 continue
             taps, Cg, nf = g["k"] * g["k"], g["Cg"], c.nf
@@ -494,9 +511,16 @@ class Tower:
                 omap = (2, Hn * Wn * Cn, Wn * Cn, Cn, c.nf, sn)
             else:
                 omap = (0, c.OH * c.OW * c.nf, c.OW * c.nf, c.nf, 0, 0)
-            ops.conv_shift_fwd(cur, B, g["Hg"], g["Wg"], g["Cg"], c.w_fwd, c.Kp, c.nf, g["shifts"], c.OH, c.OW,
-                               self.hconv[i], omap, bias=c.b, act=c.act, tag="fwd." + c.name,
-                               u8=self._u8 if i == 0 else None, bits_out=self.hbits[i], useful_rows=B * c.OH * c.OW)
+            if g["kx"] > 1:
+                ops.conv_shift_fwd(cur, B, g["Hg"], g["Wg"], g["Cg"], self.wfold[i], g["k"] * g["Cg"], c.nf,
+                                   g["yshifts"], c.OH, c.OW, self.hconv[i], omap, bias=c.b, act=c.act,
+                                   tag="fwd." + c.name, u8=self._u8 if i == 0 else None, bits_out=self.hbits[i],
+                                   useful_rows=B * c.OH * c.OW, kx=g["kx"])
+            else:
+                ops.conv_shift_fwd(cur, B, g["Hg"], g["Wg"], g["Cg"], c.w_fwd, c.Kp, c.nf, g["shifts"], c.OH, c.OW,
+                                   self.hconv[i], omap, bias=c.b, act=c.act, tag="fwd." + c.name,
+                                   u8=self._u8 if i == 0 else None, bits_out=self.hbits[i],
+                                   useful_rows=B * c.OH * c.OW)
             cur = self.hconv[i]
         return cur, self.flat
 
@@ -507,9 +531,10 @@ class Tower:
             c, g = cv[i], sg[i]
             rows = B * g["Hg"] * g["Wg"]
             xin = self.x16 if i == 0 else self.hconv[i - 1]
-            ops.conv_shift_wgrad(xin, rows, g["Cg"], self.dY[i], c.nf, g["shifts"], c.gw, c.nf,
-                                 alpha=alpha * c.in_scale, tag="wgrad." + c.name, gbias=c.gb, alpha_b=alpha,
-                                 u8=self._u8 if i == 0 else None, useful_rows=B * c.OH * c.OW)
+            ops.conv_shift_wgrad(xin, rows, g["Cg"], self.dY[i], c.nf, g["yshifts"] if g["kx"] > 1 else g["shifts"],
+                                 c.gw, c.nf, alpha=alpha * c.in_scale, tag="wgrad." + c.name, gbias=c.gb,
+                                 alpha_b=alpha, u8=self._u8 if i == 0 else None, useful_rows=B * c.OH * c.OW,
+                                 kx=g["kx"])
             if i == 0:
                 break
             # dX_i (= dY_{i-1} after the ReLU mask) as a shift-GEMM over dY_i with negative shifts

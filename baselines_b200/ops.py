@@ -91,7 +91,7 @@ def _u8_args(u8):
 
 def conv_shift_fwd(X, B, Hg, Wg, C, W, ldw, N, shifts, vy, vx, out, omap, *, saved=None, smap=None, bias=None,
                    act=ACT_NONE, dact=False, alpha=1.0, tag=None, u8=None, bits_out=None, saved_bits=None,
-                   useful_rows=None):
+                   useful_rows=None, kx=1):
     """Shift-GEMM convolution (forward, or data gradient with dact=True).  omap / smap: 6-tuples
     (mode, sN, sY, sX, Cq, s).  useful_rows (accounting only): positions that are real conv outputs -- the kernel
     also computes (and discards) the grid positions that are not; reported flops / bytes count the useful ones."""
@@ -113,12 +113,12 @@ def conv_shift_fwd(X, B, Hg, Wg, C, W, ldw, N, shifts, vy, vx, out, omap, *, sav
         nbytes = (1.0 if u8 is not None else 2.0) * rows * C + 2.0 * useful * N + (0.125 * useful * N if bits_out is not None else 0.0)
     _lib.call("b200rl_conv_shift_fwd", _ptr(X), int(B), Hg, Wg, C, _ptr(W), int(ldw), int(N), len(shifts), sh, vy, vx,
               _ptr(out), om, _ptr(saved), sm, _ptr(bias), int(act), int(bool(dact)), float(alpha), *u8a,
-              _ptr(bits_out), _ptr(saved_bits), _stream(),
-              label="convs." + (tag or "fwd"), flops=2.0 * useful * N * len(shifts) * C, nbytes=nbytes)
+              _ptr(bits_out), _ptr(saved_bits), int(kx), _stream(),
+              label="convs." + (tag or "fwd"), flops=2.0 * useful * N * len(shifts) * kx * C, nbytes=nbytes)
 
 
 def conv_shift_wgrad(X, rows, C, dY, N, shifts, G, ldg, alpha=1.0, max_ctas=0, tag=None, gbias=None, alpha_b=1.0,
-                     u8=None, useful_rows=None):
+                     u8=None, useful_rows=None, kx=1):
     _chk(X, torch.float16, "X")
     _chk(dY, torch.float16, "dY")
     _chk(G, torch.float32, "G")
@@ -126,9 +126,9 @@ def conv_shift_wgrad(X, rows, C, dY, N, shifts, G, ldg, alpha=1.0, max_ctas=0, t
     _chk(gbias, torch.float32, "gbias")
     u8a = _u8_args(u8)
     _lib.call("b200rl_conv_shift_wgrad", _ptr(X), int(rows), C, _ptr(dY), int(N), len(shifts), sh, _ptr(G), int(ldg),
-              float(alpha), _ptr(gbias), float(alpha_b), int(max_ctas), *u8a, _stream(),
+              float(alpha), _ptr(gbias), float(alpha_b), int(max_ctas), *u8a, int(kx), _stream(),
               label="convs." + (tag or "wgrad"),
-              flops=2.0 * (float(useful_rows) if useful_rows is not None else rows) * N * len(shifts) * C,
+              flops=2.0 * (float(useful_rows) if useful_rows is not None else rows) * N * len(shifts) * kx * C,
               nbytes=rows * (1.0 if u8 is not None else 2.0) * C +
               2.0 * N * (float(useful_rows) if useful_rows is not None else rows))
 

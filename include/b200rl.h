@@ -67,7 +67,7 @@ int b200rl_conv_shift_fwd(const void* X, long long B, int Hg, int Wg, int C, con
                           int taps, const int* shifts, int vy, int vx, void* out, const long long* omap,
                           const void* saved, const long long* smap, const float* bias, int act, int dact, float alpha,
                           const void* u8_x, const long long* u8_idx, int u8_H, int u8_W, int u8_C, int u8_s,
-                          void* act_bits_out, const void* saved_bits, void* stream);
+                          void* act_bits_out, const void* saved_bits, int kx, void* stream);
 /* act_bits_out (forward, optional): uint16[numel(out)/16]; bit k of word e/16 is set iff out element e+k > 0 (e = the
  * element offset the output map produces, always a multiple of 16).  saved_bits (dact, optional): the same array for
  * the saved activation; it is read instead of `saved` (1 bit instead of 16 per element of backward HBM traffic).
@@ -76,7 +76,12 @@ int b200rl_conv_shift_fwd(const void* X, long long B, int Hg, int Wg, int C, con
 int b200rl_conv_shift_wgrad(const void* X, long long rows, int C, const void* dY, int N, int taps, const int* shifts,
                             float* G, long long ldg, float alpha, float* gbias, float alpha_b, int max_ctas,
                             const void* u8_x, const long long* u8_idx, int u8_H, int u8_W, int u8_C, int u8_s,
-                            void* stream);   /* gbias != NULL: gbias[n] += alpha_b * sum_m dY[m, n] (fused) */
+                            int kx, void* stream);
+/* kx > 1 ("x-fold", forward and wgrad): the filter is ky rows of kx horizontally adjacent taps (row shift of tap
+ * (a, b) = a*Wg + b).  `shifts` then lists only the ky row shifts a*Wg, and the kx taps of a filter row ride in the
+ * MMA's N dimension, so every X slab is fetched from shared memory once per filter row instead of once per tap.
+ *   fwd  : W is [kx*N, ky*C] with row b*N + n, column a*C + c = filter tap (a, b), input channel c, output channel n
+ *   wgrad: G keeps its [(a*kx + b)*C + c, n] row order. */   /* gbias != NULL: gbias[n] += alpha_b * sum_m dY[m, n] (fused) */
 
 /* Implicit-GEMM convolution (tf.nn.conv2d a2c/utils.py:56 and its gradients): the A operand is read
  * straight from the NHWC fp16 activation x[B,H,W,C] by TMA im2col mode (C = 16, 32 or 64 channels per tap).

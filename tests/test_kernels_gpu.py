@@ -795,3 +795,102 @@ def test_frame_stack_kernel_atari_shape_vs_oracle(ops):
     ops.frame_stack(torch.from_numpy(prev).cuda(), torch.from_numpy(frames).cuda(),
                     torch.from_numpy(news.astype(np.uint8)).cuda(), out2, 4, 1)
     assert np.array_equal(out2.cpu().numpy(), want)
+
+
+# ------------------------------------------------------------------------------------------ x-folded shift-GEMM
+XFOLD_CASES = [("c1", 67, 21, 21, 64, 2, 32), ("c2", 90, 10, 10, 128, 2, 64), ("c3", 130, 9, 9, 64, 3, 64),
+               ("k2c64", 9, 12, 7, 64, 2, 64)]
+
+
+@pytest.mark.parametrize("name,B,Hg,Wg,C,R,N", XFOLD_CASES)
+def test_conv_shift_xfold_forward_and_wgrad(ops, name, B, Hg, Wg, C, R, N):
+    """kx = R: the R taps of a filter row ride in the MMA's N dimension (forward: cross-lane sum in the epilogue incl.
+    the cross-warp halo and the R-1 row tile overlap; wgrad: N-chunks of the dY tile one row apart).  Checked against
+    explicit patch matrices in fp32 AND against the un-folded kernels; several tiles per CTA and tile / warp / image
+    boundaries at arbitrary phases (rows per image not a multiple of anything)."""
+    torch.manual_seed(len(name) * 7 + B)
+    OH, OW = Hg - R + 1, Wg - R + 1
+    taps, K = R * R, R * R * C
+    shifts = [r * Wg + s for r in range(R) for s in range(R)]
+    yshifts = [r * Wg for r in range(R)]
+    x = (torch.randn(B, Hg, Wg, C, device="cuda") * 0.5).half()
+    wt = (torch.randn(N, K, device="cuda") * 0.1).half()                  # [n, (a, b, c)]
+    bias = torch.randn(N, device="cuda")
+    wf = torch.zeros(R * N, R * C, dtype=torch.float16, device="cuda")     # [(b, n), (a, c)]
+    for a in range(R):
+        for b in range(R):
+            t = a * R + b
+            wf[b * N:(b + 1) * N, a * C:(a + 1) * C] = wt[:, t * C:(t + 1) * C]
+    P = _patches(x.float(), R, R, 1, 1, 0, 0, OH, OW)
+    want = torch.relu(P @ wt.float().t() + bias).view(B, OH, OW, N)
+    omap = (0, OH * OW * N, OW * N, N, 0, 0)
+    out_f = torch.full((B, OH, OW, N), 7.0, dtype=torch.float16, device="cuda")
+    bits_f = torch.zeros(B * OH * OW * N // 16, dtype=torch.int16, device="cuda")
+    ops.conv_shift_fwd(x, B, Hg, Wg, C, wf, R * C, N, yshifts, OH, OW, out_f, omap, bias=bias, act=ops.ACT_RELU,
+                       bits_out=bits_f, kx=R)
+    out_u = torch.full((B, OH, OW, N), 7.0, dtype=torch.float16, device="cuda")
+    ops.conv_shift_fwd(x, B, Hg, Wg, C, wt, K, N, shifts, OH, OW, out_u, omap, bias=bias, act=ops.ACT_RELU)
+    torch.cuda.synchronize()
+    err = float((out_f.float() - want).abs().max())
+    assert torch.allclose(out_f.float(), want, atol=3e-2, rtol=5e-3), (name, "fold fwd", err)
+    # same products, different fp32 summation order: at most one fp16 ulp apart
+    assert float((out_f.float() - out_u.float()).abs().max()) <= 2e-2, (name, "fold vs unfolded")
+    want_bits = ((out_f.reshape(-1, 16) > 0).to(torch.int32) << torch.arange(16, device="cuda", dtype=torch.int32)
+                 ).sum(1).to(torch.int16)
+    assert torch.equal(bits_f, want_bits), (name, "fold fwd bits")
+    # ---- wgrad
+    dz = torch.zeros(B, Hg, Wg, N, dtype=torch.float16, device="cuda")
+    dzv = (torch.randn(B, OH, OW, N, device="cuda") * 0.5).half()
+    dz[:, :OH, :OW] = dzv
+    G = torch.ones(K, N, dtype=torch.float32, device="cuda")
+    gb = torch.ones(N, dtype=torch.float32, device="cuda")
+    ops.conv_shift_wgrad(x, B * Hg * Wg, C, dz, N, yshifts, G, N, alpha=0.5, gbias=gb, alpha_b=0.25, kx=R)
+    torch.cuda.synchronize()
+    want_gb = 1.0 + 0.25 * dzv.float().reshape(-1, N).sum(0)
+    assert torch.allclose(gb, want_gb, atol=2e-2, rtol=1e-3), (name, "fold gbias", float((gb - want_gb).abs().max()))
+    wantG = 1.0 + 0.5 * (P.t() @ dzv.float().reshape(-1, N))
+    err = float((G - wantG).abs().max())
+    assert torch.allclose(G, wantG, atol=3e-3 * (B * OH * OW) ** 0.5, rtol=3e-3), (name, "fold wgrad", err)
+
+
+@pytest.mark.parametrize("B,gather", [(5, False), (300, True)])
+def test_conv_shift_xfold_fused_uint8_source(ops, B, gather):
+    """conv1 with the x-fold straight from uint8 frames == the same folded kernels fed by s2d_gather (forward bit-exact;
+    wgrad to float-atomic order)."""
+    torch.manual_seed(B)
+    H = W = 84
+    C, s, Hg, Wg, N = 4, 4, 21, 21, 32
+    pool = 2 * B + 5
+    frames = torch.randint(0, 256, (pool, H, W, C), dtype=torch.uint8, device="cuda")
+    idx = torch.randperm(pool, device="cuda")[:B].contiguous() if gather else None
+    x16 = torch.empty(B, Hg * Wg * 64, dtype=torch.float16, device="cuda")
+    ops.s2d_gather(frames, x16, B, H, W, C, s, src_idx=idx)
+    yshifts = [0, Wg]
+    wf = (torch.randn(2 * N, 128, device="cuda") * 0.01).half()
+    bias = torch.randn(N, device="cuda")
+    omap = (2, 100 * 4 * N, 10 * 4 * N, 4 * N, N, 2)
+    h_ref = torch.zeros(B, 10, 10, 4 * N, dtype=torch.float16, device="cuda")
+    h_u8 = torch.zeros_like(h_ref)
+    ops.conv_shift_fwd(x16, B, Hg, Wg, 64, wf, 128, N, yshifts, 20, 20, h_ref, omap, bias=bias, act=ops.ACT_RELU, kx=2)
+    u8 = (frames, idx, H, W, C, s)
+    ops.conv_shift_fwd(None, B, Hg, Wg, 64, wf, 128, N, yshifts, 20, 20, h_u8, omap, bias=bias, act=ops.ACT_RELU, u8=u8,
+                       kx=2)
+    torch.cuda.synchronize()
+    assert float(h_ref.float().abs().max()) > 0 and torch.equal(h_ref, h_u8)
+    dz = torch.zeros(B, Hg, Wg, N, dtype=torch.float16, device="cuda")
+    dz[:, :20, :20] = (torch.randn(B, 20, 20, N, device="cuda") * 0.5).half()
+    G_ref = torch.zeros(256, N, dtype=torch.float32, device="cuda")
+    G_u8 = torch.zeros_like(G_ref)
+    G_old = torch.zeros_like(G_ref)
+    gb_ref = torch.zeros(N, dtype=torch.float32, device="cuda")
+    gb_u8 = torch.zeros_like(gb_ref)
+    rows = B * Hg * Wg
+    ops.conv_shift_wgrad(x16, rows, 64, dz, N, yshifts, G_ref, N, alpha=1.0 / 255, gbias=gb_ref, alpha_b=1.0, kx=2)
+    ops.conv_shift_wgrad(None, rows, 64, dz, N, yshifts, G_u8, N, alpha=1.0 / 255, gbias=gb_u8, alpha_b=1.0, u8=u8, kx=2)
+    ops.conv_shift_wgrad(x16, rows, 64, dz, N, [0, 1, Wg, Wg + 1], G_old, N, alpha=1.0 / 255)
+    torch.cuda.synchronize()
+    scale = float(G_ref.abs().max())
+    assert scale > 0
+    assert float((G_ref - G_u8).abs().max()) <= 1e-5 * scale + 1e-3
+    assert float((G_ref - G_old).abs().max()) <= 1e-5 * scale + 1e-3          # folded == un-folded wgrad
+    assert torch.allclose(gb_ref, gb_u8, atol=1e-3, rtol=1e-5)
