@@ -26,15 +26,17 @@ SIGNATURES = {
     "b200rl_frame_stack": [_p, _p, _p, _p, _ll, _ll, _i, _i, _p],
     "b200rl_col2im": [_p, _p, _p, _ll, _i, _i, _i, _i, _i, _i, _i, _p],
     "b200rl_colsum": [_p, _p, _ll, _i, _ll, _f, _p],
-    "b200rl_cat_step": [_p, _ll, _i, _p, _ll, _p, _ull, _ull, _p, _p, _p, _ll, _p],
-    "b200rl_gauss_step": [_p, _ll, _p, _i, _p, _ll, _p, _ull, _ull, _p, _p, _p, _ll, _p],
+    "b200rl_cat_step": [_p, _ll, _i, _p, _ll, _p, _ull, _ull, _p, _p, _p, _p, _ll, _p],
+    "b200rl_gauss_step": [_p, _ll, _p, _i, _p, _ll, _p, _ull, _ull, _p, _p, _p, _p, _ll, _p],
+    "b200rl_set_scalars": [_p, _i, _f, _f, _f, _f, _p],
+    "b200rl_counter_add": [_p, _ull, _p],
     "b200rl_adv_stats": [_p, _p, _p, _ll, _p, _p],
-    "b200rl_cat_loss": [_p, _ll, _i, _p, _ll, _p, _p, _p, _p, _p, _p, _f, _f, _f, _p, _ll, _p, _ll, _p, _ll, _p],
+    "b200rl_cat_loss": [_p, _ll, _i, _p, _ll, _p, _p, _p, _p, _p, _p, _f, _f, _f, _p, _ll, _p, _ll, _p, _ll, _p, _p],
     "b200rl_gauss_loss": [_p, _ll, _p, _i, _p, _ll, _p, _p, _p, _p, _p, _p, _f, _f, _f, _p, _ll, _p, _ll, _p, _f,
-                          _p, _ll, _p],
+                          _p, _ll, _p, _p],
     "b200rl_sumsq": [_p, _ll, _p, _p],
     "b200rl_seg_sumsq": [_p, _p, _i, _p, _p],
-    "b200rl_clip_adam": [_p, _p, _p, _p, _ll, _f, _f, _f, _f, _f, _p, _p, _i, _p],
+    "b200rl_clip_adam": [_p, _p, _p, _p, _ll, _f, _f, _f, _f, _f, _p, _p, _i, _p, _p],
     "b200rl_clip_accumulate": [_p, _p, _ll, _f, _f, _p, _p],
     "b200rl_cast_transpose": [_p, _i, _i, _p, _ll, _p, _ll, _f, _p],
     "b200rl_cast_f32_f16": [_p, _p, _ll, _i, _ll, _ll, _f, _p],
@@ -45,7 +47,7 @@ SIGNATURES = {
     "b200rl_per_priorities": [_p, _i, _d, _d, _p, _p, _p],
     "b200rl_dqn_td": [_p, _ll, _p, _ll, _p, _ll, _p, _ll, _p, _ll, _p, _ll, _i, _p, _p, _p, _p, _p, _f, _i, _p, _p,
                       _ll, _p, _ll, _p, _i, _p],
-    "b200rl_dqn_act": [_p, _ll, _p, _ll, _i, _f, _ull, _ull, _p, _i, _p],
+    "b200rl_dqn_act": [_p, _ll, _p, _ll, _i, _f, _ull, _ull, _p, _p, _p, _i, _p],
 }
 
 _lib = None
@@ -73,7 +75,8 @@ def load():
     return lib
 
 
-LAUNCHES = 0          # C-ABI kernel-launching calls made by this process (bench.py reports the delta)
+LAUNCHES = 0          # library kernels launched by this process, eagerly or inside graph replays (bench.py reports the delta)
+REPLAYS = 0           # CUDA-graph replays (graphs.py)
 _prof = None          # list of (label, start_event, end_event, flops, bytes) while profiling
 phase = ""            # profile-label suffix ("@act" / "@train"): the same kernel runs at two very different sizes
 

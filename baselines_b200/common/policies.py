@@ -152,6 +152,8 @@ class PolicyNet:
             self.g_logstd = self.store.gviews["pi/logstd"].view(-1)
         self.adv_st = torch.zeros(2, dtype=torch.float64, device=dev)
         self.stats = torch.zeros(5, dtype=torch.float64, device=dev)
+        self.clip_dev = torch.zeros(1, dtype=torch.float32, device=dev)      # clip range of the current update
+        self.rng_ctr = torch.zeros(1, dtype=torch.int64, device=dev)         # sampler stream position (Philox offset)
 
     def set_obs_rms(self, values=None):
         """Install RunningMeanStd variables (mpi_running_mean_std.py:29-30: mean = sum/count,
@@ -213,36 +215,44 @@ class PolicyNet:
         if self.head is not None:
             self.head.forward(lat, ldl, B, self.headout, self.ld_ho, mode=ops.MODE_F32_STORE)
         else:
-            latv, ldlv = self.tower_vf.forward(x, B, src_idx)
+            # the value tower of value_network='copy' reads the same observations: encode them once
+            enc = self.tower_pi.x0 if self.tower_pi.kind == "mlp" else None
+            latv, ldlv = self.tower_vf.forward(x, B, src_idx, encoded=enc)
             self._lat_vf, self._ld_lat_vf = latv, ldlv
             self.head_pi.forward(lat, ldl, B, self.pi_out, self.ld_pi, mode=ops.MODE_F32_STORE)
             self.head_vf.forward(latv, ldlv, B, self.v_out, self.ld_v, mode=ops.MODE_F32_STORE)
 
-    def act(self, x, B, actions, values, neglogp, noise=None, seed=0, offset=0):
-        """PolicyWithValue.step (policies.py:77-96) into caller-provided device tensors."""
+    def act(self, x, B, actions, values, neglogp, noise=None, seed=0):
+        """PolicyWithValue.step (policies.py:77-96) into caller-provided device tensors.  The sampler's stream position
+        is a device counter advanced after every pass, so the sequence can be replayed from a CUDA graph."""
         _lib.phase = "@act"
         self.forward(x, B)
         if self.discrete:
             ops.cat_step(self.pi_out, self.ld_pi, self.nout, self.v_out, self.ld_v, actions, values, neglogp, B,
-                         uniforms=noise, seed=seed, offset=offset)
+                         uniforms=noise, seed=seed, offset_dev=self.rng_ctr)
         else:
             ops.gauss_step(self.pi_out, self.ld_pi, self.logstd, self.nout, self.v_out, self.ld_v, actions, values,
-                           neglogp, B, normals=noise, seed=seed, offset=offset)
+                           neglogp, B, normals=noise, seed=seed, offset_dev=self.rng_ctr)
+        ops.counter_add(self.rng_ctr, 1)
 
     def loss_backward(self, x, B, src_idx, actions, returns, old_values, old_neglogp, cliprange, ent_coef, vf_coef,
                       inv_M):
         """One chunk of ppo2/model.py:57-114: forward, loss statistics, full backward into store.grads
-        (gradients of the MEAN loss: every wgrad carries alpha = 1/M)."""
+        (gradients of the MEAN loss: every wgrad carries alpha = 1/M).  cliprange None: read it from `clip_dev`
+        (written with ops.set_scalars by the caller) -- the form a captured launch sequence uses."""
+        clip_dev = self.clip_dev if cliprange is None else None
+        cliprange = 0.0 if cliprange is None else cliprange
         _lib.phase = "@train"
         self.forward(x, B, src_idx)
         if self.discrete:
             ops.cat_loss(self.pi_out, self.ld_pi, self.nout, self.v_out, self.ld_v, actions, src_idx, returns,
                          old_values, old_neglogp, self.adv_st, cliprange, ent_coef, vf_coef, self.dpi, self.ld_dpi,
-                         self.dv, self.ld_dv, self.stats, B)
+                         self.dv, self.ld_dv, self.stats, B, cliprange_dev=clip_dev)
         else:
             ops.gauss_loss(self.pi_out, self.ld_pi, self.logstd, self.nout, self.v_out, self.ld_v, actions, src_idx,
                            returns, old_values, old_neglogp, self.adv_st, cliprange, ent_coef, vf_coef, self.dpi,
-                           self.ld_dpi, self.dv, self.ld_dv, self.g_logstd, inv_M, self.stats, B)
+                           self.ld_dpi, self.dv, self.ld_dv, self.g_logstd, inv_M, self.stats, B,
+                           cliprange_dev=clip_dev)
         tp = self.tower_pi
         if self.head is not None:
             self.head.wgrad(self._lat_pi, self._ld_lat_pi, self.dhead, self.ld_dh, B, inv_M)

@@ -35,20 +35,23 @@ int frame_stack_impl(const void*, const void*, const void*, void*, long long, lo
 int col2im_impl(const void*, const void*, void*, long long, int, int, int, int, int, int, int, cudaStream_t);
 int colsum_impl(const void*, float*, long long, int, long long, float, cudaStream_t);
 int cat_step_impl(const float*, long long, int, const float*, long long, const float*, unsigned long long,
-                  unsigned long long, long long*, float*, float*, long long, cudaStream_t);
+                  unsigned long long, const unsigned long long*, long long*, float*, float*, long long, cudaStream_t);
 int gauss_step_impl(const float*, long long, const float*, int, const float*, long long, const float*,
-                    unsigned long long, unsigned long long, float*, float*, float*, long long, cudaStream_t);
+                    unsigned long long, unsigned long long, const unsigned long long*, float*, float*, float*,
+                    long long, cudaStream_t);
+int set_scalars_impl(float*, int, float, float, float, float, cudaStream_t);
+int counter_add_impl(unsigned long long*, unsigned long long, cudaStream_t);
 int adv_stats_impl(const float*, const float*, const long long*, long long, double*, cudaStream_t);
 int cat_loss_impl(const float*, long long, int, const float*, long long, const long long*, const long long*,
                   const float*, const float*, const float*, const double*, float, float, float, void*, long long,
-                  void*, long long, double*, long long, cudaStream_t);
+                  void*, long long, double*, long long, const float*, cudaStream_t);
 int gauss_loss_impl(const float*, long long, const float*, int, const float*, long long, const float*,
                     const long long*, const float*, const float*, const float*, const double*, float, float, float,
-                    void*, long long, void*, long long, float*, float, double*, long long, cudaStream_t);
+                    void*, long long, void*, long long, float*, float, double*, long long, const float*, cudaStream_t);
 int sumsq_impl(const float*, long long, double*, cudaStream_t);
 int seg_sumsq_impl(const float*, const long long*, int, double*, cudaStream_t);
 int clip_adam_impl(float*, const float*, float*, float*, long long, float, float, float, float, float, const double*,
-                   const long long*, int, cudaStream_t);
+                   const long long*, int, const float*, cudaStream_t);
 int clip_accumulate_impl(const float*, float*, long long, float, float, const double*, cudaStream_t);
 int cast_transpose_impl(const float*, int, int, void*, long long, void*, long long, float, cudaStream_t);
 int cast_f32_f16_impl(const float*, void*, long long, int, long long, long long, float, cudaStream_t);
@@ -64,7 +67,7 @@ int dqn_td_impl(const float*, long long, const float*, long long, const float*, 
                 const float*, const float*, const float*, float, int, float*, void*, long long, void*, long long,
                 double*, int, cudaStream_t);
 int dqn_act_impl(const float*, long long, const float*, long long, int, float, unsigned long long,
-                 unsigned long long, long long*, int, cudaStream_t);
+                 unsigned long long, const float*, const unsigned long long*, long long*, int, cudaStream_t);
 
 }  // namespace b200rl
 
@@ -141,15 +144,24 @@ int b200rl_colsum(const void* dz, float* db, long long rows, int C, long long ld
 }
 
 int b200rl_cat_step(const float* logits, long long ld, int nA, const float* vpred, long long ldv,
-                    const float* uniforms, unsigned long long seed, unsigned long long offset, long long* actions,
-                    float* values, float* neglogp, long long B, void* stream) {
-  return cat_step_impl(logits, ld, nA, vpred, ldv, uniforms, seed, offset, actions, values, neglogp, B, S(stream));
+                    const float* uniforms, unsigned long long seed, unsigned long long offset,
+                    const unsigned long long* offset_dev, long long* actions, float* values, float* neglogp,
+                    long long B, void* stream) {
+  return cat_step_impl(logits, ld, nA, vpred, ldv, uniforms, seed, offset, offset_dev, actions, values, neglogp, B,
+                       S(stream));
+}
+int b200rl_set_scalars(float* dst, int n, float a, float b, float c, float d, void* stream) {
+  return set_scalars_impl(dst, n, a, b, c, d, S(stream));
+}
+int b200rl_counter_add(unsigned long long* ctr, unsigned long long inc, void* stream) {
+  return counter_add_impl(ctr, inc, S(stream));
 }
 int b200rl_gauss_step(const float* mean, long long ld, const float* logstd, int d, const float* vpred,
                       long long ldv, const float* normals, unsigned long long seed, unsigned long long offset,
-                      float* actions, float* values, float* neglogp, long long B, void* stream) {
-  return gauss_step_impl(mean, ld, logstd, d, vpred, ldv, normals, seed, offset, actions, values, neglogp, B,
-                         S(stream));
+                      const unsigned long long* offset_dev, float* actions, float* values, float* neglogp,
+                      long long B, void* stream) {
+  return gauss_step_impl(mean, ld, logstd, d, vpred, ldv, normals, seed, offset, offset_dev, actions, values, neglogp,
+                         B, S(stream));
 }
 int b200rl_adv_stats(const float* returns, const float* values, const long long* src_idx, long long M, double* out,
                      void* stream) {
@@ -159,18 +171,19 @@ int b200rl_cat_loss(const float* logits, long long ld, int nA, const float* vpre
                     const long long* actions, const long long* src_idx, const float* returns,
                     const float* old_values, const float* old_neglogp, const double* adv_stats, float cliprange,
                     float ent_coef, float vf_coef, void* dlogits, long long ld_dl, void* dv, long long ld_dv,
-                    double* stats, long long B, void* stream) {
+                    double* stats, long long B, const float* cliprange_dev, void* stream) {
   return cat_loss_impl(logits, ld, nA, vpred, ldv, actions, src_idx, returns, old_values, old_neglogp, adv_stats,
-                       cliprange, ent_coef, vf_coef, dlogits, ld_dl, dv, ld_dv, stats, B, S(stream));
+                       cliprange, ent_coef, vf_coef, dlogits, ld_dl, dv, ld_dv, stats, B, cliprange_dev, S(stream));
 }
 int b200rl_gauss_loss(const float* mean, long long ld, const float* logstd, int d, const float* vpred,
                       long long ldv, const float* actions, const long long* src_idx, const float* returns,
                       const float* old_values, const float* old_neglogp, const double* adv_stats, float cliprange,
                       float ent_coef, float vf_coef, void* dmean, long long ld_dm, void* dv, long long ld_dv,
-                      float* dlogstd, float inv_M, double* stats, long long B, void* stream) {
+                      float* dlogstd, float inv_M, double* stats, long long B, const float* cliprange_dev,
+                      void* stream) {
   return gauss_loss_impl(mean, ld, logstd, d, vpred, ldv, actions, src_idx, returns, old_values, old_neglogp,
                          adv_stats, cliprange, ent_coef, vf_coef, dmean, ld_dm, dv, ld_dv, dlogstd, inv_M, stats, B,
-                         S(stream));
+                         cliprange_dev, S(stream));
 }
 
 int b200rl_sumsq(const float* g, long long n, double* out, void* stream) { return sumsq_impl(g, n, out, S(stream)); }
@@ -178,8 +191,9 @@ int b200rl_seg_sumsq(const float* g, const long long* seg_off, int nseg, double*
   return seg_sumsq_impl(g, seg_off, nseg, out, S(stream));
 }
 int b200rl_clip_adam(float* p, const float* g, float* m, float* v, long long n, float lr_t, float beta1, float beta2,
-                     float eps, float clip, const double* sumsq, const long long* seg_off, int nseg, void* stream) {
-  return clip_adam_impl(p, g, m, v, n, lr_t, beta1, beta2, eps, clip, sumsq, seg_off, nseg, S(stream));
+                     float eps, float clip, const double* sumsq, const long long* seg_off, int nseg,
+                     const float* lr_t_dev, void* stream) {
+  return clip_adam_impl(p, g, m, v, n, lr_t, beta1, beta2, eps, clip, sumsq, seg_off, nseg, lr_t_dev, S(stream));
 }
 int b200rl_clip_accumulate(const float* g, float* acc, long long n, float clip, float weight, const double* sumsq,
                            void* stream) {
@@ -229,8 +243,9 @@ int b200rl_dqn_td(const float* a_t, long long lda_t, const float* s_t, long long
                      rewards, dones, weights, gamma, double_q, td_out, d_a, ld_da, d_s, ld_ds, loss_sum, B, S(stream));
 }
 int b200rl_dqn_act(const float* a, long long lda, const float* s, long long lds, int nA, float eps,
-                   unsigned long long seed, unsigned long long step, long long* actions, int B, void* stream) {
-  return dqn_act_impl(a, lda, s, lds, nA, eps, seed, step, actions, B, S(stream));
+                   unsigned long long seed, unsigned long long step, const float* eps_dev,
+                   const unsigned long long* step_dev, long long* actions, int B, void* stream) {
+  return dqn_act_impl(a, lda, s, lds, nA, eps, seed, step, eps_dev, step_dev, actions, B, S(stream));
 }
 
 }  // extern "C"

@@ -72,7 +72,8 @@ __device__ __forceinline__ void adam1(float& p, float g, float& m, float& v, con
 __global__ void __launch_bounds__(256)
 clip_adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
                  long long n, AdamArgs a, const double* __restrict__ sumsq, const long long* __restrict__ seg_off,
-                 int nseg) {
+                 int nseg, const float* __restrict__ lr_t_dev) {
+  if (lr_t_dev) a.lr_t = *lr_t_dev;                // step size kept on the device (CUDA-graph replays)
   float gscale = 1.0f;
   if (a.clip > 0.0f && seg_off == nullptr) {
     const float norm = (float)sqrt(sumsq[0]);
@@ -187,12 +188,31 @@ int seg_sumsq_impl(const float* g, const long long* seg_off, int nseg, double* o
 
 int clip_adam_impl(float* p, const float* g, float* m, float* v, long long n, float lr_t, float beta1, float beta2,
                    float eps, float clip, const double* sumsq, const long long* seg_off, int nseg,
-                   cudaStream_t stream) {
+                   const float* lr_t_dev, cudaStream_t stream) {
   B200RL_REQUIRE(p && g && m && v && n > 0, "clip_adam: bad args");
   B200RL_REQUIRE(clip <= 0.0f || sumsq != nullptr, "clip_adam: clipping needs the device sumsq");
   AdamArgs a{lr_t, beta1, beta2, eps, clip};
-  clip_adam_kernel<<<grid_for(n, 256, 8), 256, 0, stream>>>(p, g, m, v, n, a, sumsq, seg_off, nseg);
+  clip_adam_kernel<<<grid_for(n, 256, 8), 256, 0, stream>>>(p, g, m, v, n, a, sumsq, seg_off, nseg, lr_t_dev);
   return check_launch("clip_adam_kernel");
+}
+
+__global__ void set_scalars_kernel(float* dst, float a, float b, float c, float d, int n) {
+  const float v[4] = {a, b, c, d};
+  if (threadIdx.x < n) dst[threadIdx.x] = v[threadIdx.x];
+}
+__global__ void counter_add_kernel(unsigned long long* ctr, unsigned long long inc) { *ctr += inc; }
+
+// dst[0..n) = {a, b, c, d}[0..n): scalars that change between replays of a captured launch sequence (Adam step size,
+// clip range) travel as kernel arguments of this one-thread kernel, so no host buffer can be overwritten too early
+int set_scalars_impl(float* dst, int n, float a, float b, float c, float d, cudaStream_t stream) {
+  B200RL_REQUIRE(dst && n >= 1 && n <= 4, "set_scalars: 1..4 values");
+  set_scalars_kernel<<<1, 32, 0, stream>>>(dst, a, b, c, d, n);
+  return check_launch("set_scalars_kernel");
+}
+int counter_add_impl(unsigned long long* ctr, unsigned long long inc, cudaStream_t stream) {
+  B200RL_REQUIRE(ctr != nullptr, "counter_add: null counter");
+  counter_add_kernel<<<1, 1, 0, stream>>>(ctr, inc);
+  return check_launch("counter_add_kernel");
 }
 
 int clip_accumulate_impl(const float* g, float* acc, long long n, float clip, float weight, const double* sumsq,

@@ -36,10 +36,12 @@ __device__ __forceinline__ float u01_open(uint32_t x) { return ((float)(x >> 8) 
 // ---------------------------------------------------------------- categorical: act
 __global__ void __launch_bounds__(256)
 cat_step_kernel(const float* __restrict__ logits, long long ld, int nA, const float* __restrict__ vpred, long long ldv,
-                const float* __restrict__ uniforms, uint64_t seed, uint64_t offset, long long* __restrict__ actions,
+                const float* __restrict__ uniforms, uint64_t seed, uint64_t offset,
+                const unsigned long long* __restrict__ offset_dev, long long* __restrict__ actions,
                 float* __restrict__ values, float* __restrict__ neglogp, long long B) {
   const long long b = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= B) return;
+  if (offset_dev) offset = *offset_dev;            // stream position kept on the device (CUDA-graph replays)
   const float* l = logits + b * ld;
   float m = -INFINITY;
   for (int j = 0; j < nA; ++j) m = fmaxf(m, l[j]);
@@ -68,10 +70,11 @@ cat_step_kernel(const float* __restrict__ logits, long long ld, int nA, const fl
 __global__ void __launch_bounds__(256)
 gauss_step_kernel(const float* __restrict__ mean, long long ld, const float* __restrict__ logstd, int d,
                   const float* __restrict__ vpred, long long ldv, const float* __restrict__ normals, uint64_t seed,
-                  uint64_t offset, float* __restrict__ actions, float* __restrict__ values,
-                  float* __restrict__ neglogp, long long B) {
+                  uint64_t offset, const unsigned long long* __restrict__ offset_dev, float* __restrict__ actions,
+                  float* __restrict__ values, float* __restrict__ neglogp, long long B) {
   const long long b = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= B) return;
+  if (offset_dev) offset = *offset_dev;
   float q = 0.0f, sl = 0.0f;
   uint32_t rnd[4];
   float z0 = 0.f, z1 = 0.f;
@@ -101,24 +104,32 @@ gauss_step_kernel(const float* __restrict__ mean, long long ld, const float* __r
   values[b] = vpred[b * ldv];
 }
 
-// ---------------------------------------------------------------- advantage moments (one block, fp64)
-// One block keeps the summation order fixed (deterministic).  The gathers are dependent loads (index -> returns,
-// values), so each thread keeps 8 of them in flight; sum and sum of squares are accumulated together in fp64
-// (inputs are fp32 differences of O(1): E[x^2] - mean^2 in fp64 loses nothing that fp32 numpy would have kept).
-__global__ void __launch_bounds__(1024)
+// ---------------------------------------------------------------- advantage moments (fp64, deterministic)
+// ADV_BLOCKS blocks each reduce a FIXED contiguous slice in a fixed order; the block that finishes last adds the
+// partials in index order, so the result does not depend on scheduling (same bits on every run).  The gathers are
+// dependent loads (index -> returns, values): each thread keeps 8 in flight.  Sum and sum of squares are accumulated
+// together in fp64 (inputs are fp32 differences of O(1): E[x^2] - mean^2 in fp64 loses nothing fp32 numpy would keep).
+static constexpr int ADV_BLOCKS = 128;
+__device__ double g_adv_part[2 * ADV_BLOCKS];
+__device__ unsigned int g_adv_done = 0;
+
+__global__ void __launch_bounds__(512)
 adv_stats_kernel(const float* __restrict__ returns, const float* __restrict__ values,
                  const long long* __restrict__ src_idx, long long M, double* __restrict__ out) {
-  __shared__ double red[2][32];
+  __shared__ double red[2][16];
+  __shared__ bool last;
   const int tid = threadIdx.x;
   constexpr int U = 8;
+  const long long per = (M + gridDim.x - 1) / gridDim.x;
+  const long long lo = (long long)blockIdx.x * per, hi = (lo + per < M) ? lo + per : M;
   double s1 = 0.0, s2 = 0.0;
-  for (long long i0 = tid; i0 < M; i0 += (long long)blockDim.x * U) {
+  for (long long i0 = lo + tid; i0 < hi; i0 += (long long)blockDim.x * U) {
     float d[U];
 #pragma unroll
     for (int u = 0; u < U; ++u) {
       const long long i = i0 + (long long)u * blockDim.x;
       d[u] = 0.0f;
-      if (i < M) {
+      if (i < hi) {
         const long long s = src_idx ? src_idx[i] : i;
         d[u] = __fsub_rn(returns[s], values[s]);                 // float32 subtraction (model.py:136)
       }
@@ -133,17 +144,27 @@ adv_stats_kernel(const float* __restrict__ returns, const float* __restrict__ va
   s2 = warp_sum_d(s2);
   if ((tid & 31) == 0) { red[0][tid >> 5] = s1; red[1][tid >> 5] = s2; }
   __syncthreads();
-  if (tid < 32) {
-    double a = (tid < (blockDim.x >> 5)) ? red[0][tid] : 0.0;
-    double b = (tid < (blockDim.x >> 5)) ? red[1][tid] : 0.0;
-    a = warp_sum_d(a);
-    b = warp_sum_d(b);
-    if (tid == 0) {
-      const double mean = a / (double)M;
-      const double var = fmax(b / (double)M - mean * mean, 0.0);
-      out[0] = mean;
-      out[1] = sqrt(var);                                          // population std (numpy default ddof=0)
+  if (tid == 0) {
+    double a = 0.0, b = 0.0;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) { a += red[0][w]; b += red[1][w]; }
+    g_adv_part[2 * blockIdx.x] = a;
+    g_adv_part[2 * blockIdx.x + 1] = b;
+    __threadfence();
+    last = (atomicAdd(&g_adv_done, 1u) == gridDim.x - 1);
+  }
+  __syncthreads();
+  if (last && tid == 0) {
+    __threadfence();
+    double a = 0.0, b = 0.0;
+    for (int k = 0; k < (int)gridDim.x; ++k) {
+      a += *((volatile double*)&g_adv_part[2 * k]);
+      b += *((volatile double*)&g_adv_part[2 * k + 1]);
     }
+    const double mean = a / (double)M;
+    const double var = fmax(b / (double)M - mean * mean, 0.0);
+    out[0] = mean;
+    out[1] = sqrt(var);                                          // population std (numpy default ddof=0)
+    g_adv_done = 0;
   }
 }
 
@@ -156,6 +177,7 @@ struct PpoCommon {
   const double* adv_stats;        // {mean, std}
   float cliprange, ent_coef, vf_coef;
   double* stats;                  // [5] sums: pg, vf, entropy, approxkl, clipfrac
+  const float* cliprange_dev;     // optional: read the clip range from device memory (CUDA-graph replays)
 };
 
 __device__ __forceinline__ void block_accumulate5(double (&v)[5], double* stats) {
@@ -228,8 +250,9 @@ cat_loss_kernel(const float* __restrict__ logits, long long ld, int nA, const fl
     const float adv_raw = __fsub_rn(R, oldv);
     const float adv = (float)(((double)adv_raw - pc.adv_stats[0]) / (pc.adv_stats[1] + 1e-8));
     float pgl, kl, cf, vl;
-    const float g_nlp = pg_loss_grad(nlp, pc.old_neglogp[s], adv, pc.cliprange, pgl, kl, cf);
-    const float g_v = value_loss_grad(vpred[b * ldv], oldv, R, pc.cliprange, pc.vf_coef, vl);
+    const float clip = pc.cliprange_dev ? *pc.cliprange_dev : pc.cliprange;
+    const float g_nlp = pg_loss_grad(nlp, pc.old_neglogp[s], adv, clip, pgl, kl, cf);
+    const float g_v = value_loss_grad(vpred[b * ldv], oldv, R, clip, pc.vf_coef, vl);
     for (int j = 0; j < nA; ++j) {
       const float a0 = l[j] - m;
       const float pj = expf(a0) / z;
@@ -255,8 +278,11 @@ gauss_loss_kernel(const float* __restrict__ mean, long long ld, const float* __r
   __syncthreads();
   const long long b = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   double st[5] = {0, 0, 0, 0, 0};
+  float g_nlp = 0.0f;
+  long long srow = 0;
   if (b < B) {
     const long long s = pc.src_idx ? pc.src_idx[b] : b;
+    srow = s;
     float q = 0.0f, sl = 0.0f;
     for (int j = 0; j < d; ++j) {
       const float ls = logstd[j];
@@ -270,17 +296,24 @@ gauss_loss_kernel(const float* __restrict__ mean, long long ld, const float* __r
     const float adv_raw = __fsub_rn(R, oldv);
     const float adv = (float)(((double)adv_raw - pc.adv_stats[0]) / (pc.adv_stats[1] + 1e-8));
     float pgl, kl, cf, vl;
-    const float g_nlp = pg_loss_grad(nlp, pc.old_neglogp[s], adv, pc.cliprange, pgl, kl, cf);
-    const float g_v = value_loss_grad(vpred[b * ldv], oldv, R, pc.cliprange, pc.vf_coef, vl);
-    for (int j = 0; j < d; ++j) {
-      const float sd = expf(logstd[j]);
-      const float t = (actions[s * d + j] - mean[b * ld + j]) / sd;
-      dmean[b * ld_dm + j] = __float2half_rn(g_nlp * (-t / sd));      // d nlp/d mu = -(x-mu)/sigma^2
-      // d nlp/d logstd = 1 - t^2 ; d(-ent_coef*H)/d logstd = -ent_coef
-      atomicAdd(&s_dls[j], g_nlp * (1.0f - t * t) - pc.ent_coef);
-    }
+    const float clip = pc.cliprange_dev ? *pc.cliprange_dev : pc.cliprange;
+    g_nlp = pg_loss_grad(nlp, pc.old_neglogp[s], adv, clip, pgl, kl, cf);
+    const float g_v = value_loss_grad(vpred[b * ldv], oldv, R, clip, pc.vf_coef, vl);
     dv[b * ld_dv] = __float2half_rn(g_v);
     st[0] = pgl; st[1] = vl; st[2] = H; st[3] = kl; st[4] = cf;
+  }
+  // every lane takes part in the warp reductions of dL/dlogstd (inactive rows contribute 0): one shared-memory
+  // atomic per warp and action dimension instead of one per sample
+  for (int j = 0; j < d; ++j) {
+    float gl = 0.0f;
+    if (b < B) {
+      const float sd = expf(logstd[j]);
+      const float t = (actions[srow * d + j] - mean[b * ld + j]) / sd;
+      dmean[b * ld_dm + j] = __float2half_rn(g_nlp * (-t / sd));      // d nlp/d mu = -(x-mu)/sigma^2
+      gl = g_nlp * (1.0f - t * t) - pc.ent_coef;   // d nlp/d logstd = 1 - t^2 ; d(-ent_coef*H)/d logstd = -ent_coef
+    }
+    gl = warp_sum(gl);
+    if ((threadIdx.x & 31) == 0) atomicAdd(&s_dls[j], gl);
   }
   __syncthreads();
   for (int j = threadIdx.x; j < d; j += blockDim.x) atomicAdd(dlogstd + j, s_dls[j] * inv_M);
@@ -289,27 +322,29 @@ gauss_loss_kernel(const float* __restrict__ mean, long long ld, const float* __r
 
 // ---------------------------------------------------------------- launchers
 int cat_step_impl(const float* logits, long long ld, int nA, const float* vpred, long long ldv, const float* uniforms,
-                  unsigned long long seed, unsigned long long offset, long long* actions, float* values,
-                  float* neglogp, long long B, cudaStream_t stream) {
+                  unsigned long long seed, unsigned long long offset, const unsigned long long* offset_dev,
+                  long long* actions, float* values, float* neglogp, long long B, cudaStream_t stream) {
   B200RL_REQUIRE(logits && vpred && actions && values && neglogp && B > 0 && nA > 0, "cat_step: bad args");
   cat_step_kernel<<<(int)ceil_div_ll(B, 256), 256, 0, stream>>>(logits, ld, nA, vpred, ldv, uniforms, seed, offset,
-                                                                 actions, values, neglogp, B);
+                                                                 offset_dev, actions, values, neglogp, B);
   return check_launch("cat_step_kernel");
 }
 
 int gauss_step_impl(const float* mean, long long ld, const float* logstd, int d, const float* vpred, long long ldv,
-                    const float* normals, unsigned long long seed, unsigned long long offset, float* actions,
-                    float* values, float* neglogp, long long B, cudaStream_t stream) {
+                    const float* normals, unsigned long long seed, unsigned long long offset,
+                    const unsigned long long* offset_dev, float* actions, float* values, float* neglogp, long long B,
+                    cudaStream_t stream) {
   B200RL_REQUIRE(mean && logstd && vpred && actions && values && neglogp && B > 0 && d > 0, "gauss_step: bad args");
   gauss_step_kernel<<<(int)ceil_div_ll(B, 256), 256, 0, stream>>>(mean, ld, logstd, d, vpred, ldv, normals, seed,
-                                                                   offset, actions, values, neglogp, B);
+                                                                   offset, offset_dev, actions, values, neglogp, B);
   return check_launch("gauss_step_kernel");
 }
 
 int adv_stats_impl(const float* returns, const float* values, const long long* src_idx, long long M, double* out,
                    cudaStream_t stream) {
   B200RL_REQUIRE(returns && values && out && M > 0, "adv_stats: bad args");
-  adv_stats_kernel<<<1, 1024, 0, stream>>>(returns, values, src_idx, M, out);
+  const int blocks = (int)((M + 4095) / 4096 < ADV_BLOCKS ? (M + 4095) / 4096 : ADV_BLOCKS);
+  adv_stats_kernel<<<blocks, 512, 0, stream>>>(returns, values, src_idx, M, out);
   return check_launch("adv_stats_kernel");
 }
 
@@ -317,11 +352,11 @@ int cat_loss_impl(const float* logits, long long ld, int nA, const float* vpred,
                   const long long* actions, const long long* src_idx, const float* returns, const float* old_values,
                   const float* old_neglogp, const double* adv_stats, float cliprange, float ent_coef, float vf_coef,
                   void* dlogits, long long ld_dl, void* dv, long long ld_dv, double* stats, long long B,
-                  cudaStream_t stream) {
+                  const float* cliprange_dev, cudaStream_t stream) {
   B200RL_REQUIRE(logits && vpred && actions && returns && old_values && old_neglogp && adv_stats && dlogits && dv &&
                      stats && B > 0,
                  "cat_loss: bad args");
-  PpoCommon pc{src_idx, returns, old_values, old_neglogp, adv_stats, cliprange, ent_coef, vf_coef, stats};
+  PpoCommon pc{src_idx, returns, old_values, old_neglogp, adv_stats, cliprange, ent_coef, vf_coef, stats, cliprange_dev};
   cat_loss_kernel<<<(int)ceil_div_ll(B, 256), 256, 0, stream>>>(logits, ld, nA, vpred, ldv, actions, pc,
                                                                  reinterpret_cast<__half*>(dlogits), ld_dl,
                                                                  reinterpret_cast<__half*>(dv), ld_dv, B);
@@ -332,11 +367,11 @@ int gauss_loss_impl(const float* mean, long long ld, const float* logstd, int d,
                     const float* actions, const long long* src_idx, const float* returns, const float* old_values,
                     const float* old_neglogp, const double* adv_stats, float cliprange, float ent_coef, float vf_coef,
                     void* dmean, long long ld_dm, void* dv, long long ld_dv, float* dlogstd, float inv_M,
-                    double* stats, long long B, cudaStream_t stream) {
+                    double* stats, long long B, const float* cliprange_dev, cudaStream_t stream) {
   B200RL_REQUIRE(mean && logstd && vpred && actions && returns && old_values && old_neglogp && adv_stats && dmean &&
                      dv && dlogstd && stats && B > 0,
                  "gauss_loss: bad args");
-  PpoCommon pc{src_idx, returns, old_values, old_neglogp, adv_stats, cliprange, ent_coef, vf_coef, stats};
+  PpoCommon pc{src_idx, returns, old_values, old_neglogp, adv_stats, cliprange, ent_coef, vf_coef, stats, cliprange_dev};
   gauss_loss_kernel<<<(int)ceil_div_ll(B, 256), 256, d * sizeof(float), stream>>>(
       mean, ld, logstd, d, vpred, ldv, actions, pc, reinterpret_cast<__half*>(dmean), ld_dm,
       reinterpret_cast<__half*>(dv), ld_dv, dlogstd, inv_M, B);

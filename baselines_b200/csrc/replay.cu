@@ -192,9 +192,12 @@ dqn_td_kernel(QHead qt, QHead q1_online, QHead q1_target, int nA, const long lon
 
 // epsilon-greedy action selection (build_graph.py:184-191) with counter-based randomness
 __global__ void dqn_act_kernel(QHead q, int nA, float eps, unsigned long long seed, unsigned long long step,
+                               const float* __restrict__ eps_dev, const unsigned long long* __restrict__ step_dev,
                                long long* __restrict__ actions, int B) {
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= B) return;
+  if (eps_dev) eps = *eps_dev;                       // exploration rate / stream position kept on the device
+  if (step_dev) step = *step_dev;                    // (CUDA-graph replays of the acting pass)
   const float m = mean_adv(q, b, nA);
   int arg = 0;
   float bq = -INFINITY;
@@ -271,10 +274,11 @@ int dqn_td_impl(const float* a_t, long long lda_t, const float* s_t, long long l
 }
 
 int dqn_act_impl(const float* a, long long lda, const float* s, long long lds, int nA, float eps,
-                 unsigned long long seed, unsigned long long step, long long* actions, int B, cudaStream_t stream) {
+                 unsigned long long seed, unsigned long long step, const float* eps_dev, const unsigned long long* step_dev, long long* actions, int B,
+                 cudaStream_t stream) {
   B200RL_REQUIRE(a && actions && B > 0 && nA > 0, "dqn_act: bad args");
   QHead q{a, lda, s, lds};
-  dqn_act_kernel<<<ceil_div(B, 128), 128, 0, stream>>>(q, nA, eps, seed, step, actions, B);
+  dqn_act_kernel<<<ceil_div(B, 128), 128, 0, stream>>>(q, nA, eps, seed, step, eps_dev, step_dev, actions, B);
   return check_launch("dqn_act_kernel");
 }
 

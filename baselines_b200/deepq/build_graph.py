@@ -12,7 +12,7 @@ argmax and the target network (:399-408), Huber loss (tf_util.py:39-45) weighted
 import numpy as np
 import torch
 
-from .. import nn, ops
+from .. import graphs, nn, ops
 
 
 def _fc_name(j):
@@ -182,9 +182,16 @@ class DQNModel:
             self.td = torch.zeros(batch_cap, dtype=torch.float32, device=dev)
             self.loss = torch.zeros(1, dtype=torch.float64, device=dev)
             self._act = torch.zeros(batch_cap, dtype=torch.int64, device=dev)
+            # fixed homes for per-step inputs and scalars, so that a step is a replayable launch sequence (graphs.py)
+            self._idx_buf = torch.zeros(batch_cap, dtype=torch.int64, device=dev)
+            self._w_buf = torch.zeros(batch_cap, dtype=torch.float32, device=dev)
+            self._eps_dev = torch.zeros(1, dtype=torch.float32, device=dev)
+            self._step_dev = torch.zeros(1, dtype=torch.int64, device=dev)
+            self._act_obs = None
+        self.graphs = graphs.GraphCache()
+        self.batch_cap = batch_cap
         self.eps = 0.0
         self._seed = int(np.random.randint(0, 2 ** 31 - 1))
-        self._step = 0
         self.update_target()
 
     def update_target(self):
@@ -193,10 +200,25 @@ class DQNModel:
         self.qt.refresh()
 
     def act_device(self, obs_dev, B, eps):
-        self._step += 1
-        out = self.q.forward(obs_dev, B)
-        S = out[:, self.nA:] if self.q.dueling else None
-        ops.dqn_act(out, self.q.ld_out, S, self.q.ld_out, self.nA, eps, self._seed, self._step, self._act, B)
+        """build_graph.py:184-192 on B observations.  The observations are staged in a fixed buffer, eps and the
+        random-stream position live on the device, so the pass is captured once per B and replayed."""
+        if B > self.batch_cap:
+            raise ValueError(f"act batch {B} exceeds batch_cap {self.batch_cap}")
+        if self._act_obs is None or self._act_obs.shape[1:] != obs_dev.shape[1:] or self._act_obs.dtype != obs_dev.dtype:
+            self._act_obs = torch.zeros((self.batch_cap,) + tuple(obs_dev.shape[1:]), dtype=obs_dev.dtype,
+                                        device=self.device)
+            self.graphs.clear()
+        self._act_obs[:B].copy_(obs_dev)
+        ops.set_scalars(self._eps_dev, eps)
+        x = self._act_obs[:B]
+
+        def body():
+            out = self.q.forward(x, B)
+            S = out[:, self.nA:] if self.q.dueling else None
+            ops.dqn_act(out, self.q.ld_out, S, self.q.ld_out, self.nA, 0.0, self._seed, 0, self._act, B,
+                        eps_dev=self._eps_dev, step_dev=self._step_dev)
+            ops.counter_add(self._step_dev, 1)
+        self.graphs.run(("act", B), body)
         return self._act[:B]
 
     def q_values(self, obs):
@@ -211,23 +233,38 @@ class DQNModel:
 
     def train_device(self, obs_t, obs_tp1, actions, rewards, dones, weights, idx, B, lr=None):
         """One step of build_graph.py:380-444 on device-resident arrays.  obs_* / actions / rewards / dones are the
-        replay storage (gathered through idx) or already-gathered batches (idx None).  Returns td_error[B]."""
+        replay storage (gathered through idx) or already-gathered batches (idx None).  Returns td_error[B].
+        With idx (the resident replay path) the step is a fixed launch sequence: indices and weights are copied into
+        fixed buffers, Adam's step size goes to the device, and the sequence is captured once and replayed."""
         q, qt, nA = self.q, self.qt, self.nA
         with torch.cuda.device(self.device):
+            self.opt.begin_step(self.lr if lr is None else lr)
+            replay = idx is not None
+            if replay:
+                self._idx_buf[:B].copy_(idx)
+                self._w_buf[:B].copy_(weights)
+                idx, weights = self._idx_buf[:B], self._w_buf[:B]
             ld = q.ld_out
             sp = (lambda o: o[:, nA:]) if q.dueling else (lambda o: None)
-            if self.double_q:
-                q.forward(obs_tp1, B, idx, out=self.on_out)            # online q(s')  (first: it reuses q's workspace)
-            qt.forward(obs_tp1, B, idx)                                # target q(s')
-            q.forward(obs_t, B, idx)                                   # online q(s)   (last: activations kept for bwd)
-            q.store.grads.zero_()
-            self.loss.zero_()
-            ops.dqn_td(q.out, ld, sp(q.out), ld, self.on_out, ld, sp(self.on_out), ld, qt.out, ld, sp(qt.out), ld, nA,
-                       idx, actions, rewards, dones, weights, self.gamma, self.double_q, self.td, q.dout, q.ld_dout,
-                       q.dout[:, q.s_col:] if q.dueling else None, q.ld_dout, self.loss, B)
-            q.backward(B, 1.0 / B)
-            self.opt.step(self.lr if lr is None else lr)
-            q.refresh()
+
+            def body():
+                if self.double_q:
+                    q.forward(obs_tp1, B, idx, out=self.on_out)        # online q(s')  (first: it reuses q's workspace)
+                qt.forward(obs_tp1, B, idx)                            # target q(s')
+                q.forward(obs_t, B, idx)                               # online q(s)   (last: activations kept for bwd)
+                q.store.grads.zero_()
+                self.loss.zero_()
+                ops.dqn_td(q.out, ld, sp(q.out), ld, self.on_out, ld, sp(self.on_out), ld, qt.out, ld, sp(qt.out), ld,
+                           nA, idx, actions, rewards, dones, weights, self.gamma, self.double_q, self.td, q.dout,
+                           q.ld_dout, q.dout[:, q.s_col:] if q.dueling else None, q.ld_dout, self.loss, B)
+                q.backward(B, 1.0 / B)
+                self.opt.apply()
+                q.refresh()
+            if replay:
+                self.graphs.run(("train", B, obs_t.data_ptr(), obs_tp1.data_ptr(), actions.data_ptr(),
+                                 rewards.data_ptr(), dones.data_ptr()), body)
+            else:
+                body()
             return self.td[:B]
 
 

@@ -553,7 +553,8 @@ class Tower:
             self._refresh_shift()
 
     # x: uint8 [*,H,W,C] images (cnn) or fp16 [*, in_pad] rows (mlp); src_idx gathers samples from it
-    def forward(self, x, B, src_idx=None):
+    def forward(self, x, B, src_idx=None, encoded=None):
+        """encoded (mlp only): operand rows another tower already produced from the same observations."""
         assert B <= self.cap
         if self.convs and self.shift_mode:
             h, ldh = self._forward_shift(x, B, src_idx)
@@ -581,10 +582,12 @@ class Tower:
         else:
             # float32 rows (optionally gathered through src_idx) -> encoded fp16 [hi | lo] operand rows
             nm = self.obs_norm
-            ops.obs_encode(x, self.x0, B, self.raw_dim, self.in_dim, self.in_pad, src_idx=src_idx,
-                           mean=nm[0] if nm else None, inv_std=nm[1] if nm else None,
-                           clip=(nm[2], nm[3]) if nm else (0.0, 0.0), onehot_n=self.onehot_n)
-            h, ldh = self.x0, 2 * self.in_pad
+            if encoded is None:
+                ops.obs_encode(x, self.x0, B, self.raw_dim, self.in_dim, self.in_pad, src_idx=src_idx,
+                               mean=nm[0] if nm else None, inv_std=nm[1] if nm else None,
+                               clip=(nm[2], nm[3]) if nm else (0.0, 0.0), onehot_n=self.onehot_n)
+                encoded = self.x0
+            h, ldh = encoded, 2 * self.in_pad
             self._mlp_in = h
         for i, l in enumerate(self.fcs):
             l.forward(h, ldh, B, self.hfc[i], l.Np)
@@ -649,18 +652,30 @@ class Optimizer:
         self.nseg = nseg
         self.sumsq = torch.zeros(nseg, dtype=torch.float64, device=store.device)
         self.seg_off = torch.from_numpy(store.segment_offsets()).to(store.device) if per_variable else None
+        self.lr_dev = torch.zeros(1, dtype=torch.float32, device=store.device)    # lr_t of the current step
 
-    def step(self, lr, clip=True):
-        """clip=False: the gradient buffer already holds clipped gradients (MicrobatchedModel)."""
-        s = self.store
+    def begin_step(self, lr):
+        """Host half of a step: advance t and hand the bias-corrected step size lr*sqrt(1-b2^t)/(1-b1^t)
+        (mpi_adam.py:37) to the device.  Separate from `apply` so that `apply` is a fixed launch sequence."""
         self.t += 1
         lr_t = lr * math.sqrt(1.0 - self.beta2 ** self.t) / (1.0 - self.beta1 ** self.t)
+        ops.set_scalars(self.lr_dev, lr_t)
+        return lr_t
+
+    def apply(self, clip=True):
+        """Device half: norm(s) + clip + Adam, reading the step size written by begin_step."""
+        s = self.store
         clip = self.clip if (self.clip is not None and clip) else 0.0
         if clip > 0:
             if self.per_variable:
                 ops.seg_sumsq(s.grads, self.seg_off, self.nseg, self.sumsq)
             else:
                 ops.sumsq(s.grads, self.sumsq)
-        ops.clip_adam(s.params, s.grads, s.m, s.v, lr_t, self.beta1, self.beta2, self.eps, clip,
+        ops.clip_adam(s.params, s.grads, s.m, s.v, 0.0, self.beta1, self.beta2, self.eps, clip,
                       self.sumsq if clip > 0 else None, self.seg_off if (clip > 0 and self.per_variable) else None,
-                      self.nseg if self.per_variable else 0)
+                      self.nseg if self.per_variable else 0, lr_t_dev=self.lr_dev)
+
+    def step(self, lr, clip=True):
+        """clip=False: the gradient buffer already holds clipped gradients (MicrobatchedModel)."""
+        self.begin_step(lr)
+        self.apply(clip)

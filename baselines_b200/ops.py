@@ -193,20 +193,36 @@ def colsum(dz, db, rows, C, ld, alpha=1.0):
               label="colsum", nbytes=2.0 * rows * C)
 
 
-def cat_step(logits, ld, nA, vpred, ldv, actions, values, neglogp, B, uniforms=None, seed=0, offset=0):
+def cat_step(logits, ld, nA, vpred, ldv, actions, values, neglogp, B, uniforms=None, seed=0, offset=0,
+             offset_dev=None):
     _chk(logits, torch.float32, "logits")
     _chk(actions, torch.int64, "actions")
     _chk(uniforms, torch.float32, "uniforms")
+    _chk(offset_dev, torch.int64, "offset_dev")
     _lib.call("b200rl_cat_step", _ptr(logits), int(ld), int(nA), _ptr(vpred), int(ldv), _ptr(uniforms), int(seed),
-              int(offset), _ptr(actions), _ptr(values), _ptr(neglogp), int(B), _stream())
+              int(offset), _ptr(offset_dev), _ptr(actions), _ptr(values), _ptr(neglogp), int(B), _stream())
 
 
-def gauss_step(mean, ld, logstd, d, vpred, ldv, actions, values, neglogp, B, normals=None, seed=0, offset=0):
+def gauss_step(mean, ld, logstd, d, vpred, ldv, actions, values, neglogp, B, normals=None, seed=0, offset=0,
+               offset_dev=None):
     _chk(mean, torch.float32, "mean")
     _chk(actions, torch.float32, "actions")
     _chk(normals, torch.float32, "normals")
+    _chk(offset_dev, torch.int64, "offset_dev")
     _lib.call("b200rl_gauss_step", _ptr(mean), int(ld), _ptr(logstd), int(d), _ptr(vpred), int(ldv), _ptr(normals),
-              int(seed), int(offset), _ptr(actions), _ptr(values), _ptr(neglogp), int(B), _stream())
+              int(seed), int(offset), _ptr(offset_dev), _ptr(actions), _ptr(values), _ptr(neglogp), int(B), _stream())
+
+
+def set_scalars(dst, *vals):
+    """dst[0..len(vals)) = vals (float32 device tensor): values travel as kernel arguments."""
+    _chk(dst, torch.float32, "dst")
+    v = [float(x) for x in vals] + [0.0] * (4 - len(vals))
+    _lib.call("b200rl_set_scalars", _ptr(dst), len(vals), v[0], v[1], v[2], v[3], _stream())
+
+
+def counter_add(ctr, inc=1):
+    _chk(ctr, torch.int64, "ctr")
+    _lib.call("b200rl_counter_add", _ptr(ctr), int(inc), _stream())
 
 
 def adv_stats(returns, values, src_idx, M, out):
@@ -216,21 +232,22 @@ def adv_stats(returns, values, src_idx, M, out):
 
 
 def cat_loss(logits, ld, nA, vpred, ldv, actions, src_idx, returns, old_values, old_neglogp, adv_st, cliprange,
-             ent_coef, vf_coef, dlogits, ld_dl, dv, ld_dv, stats, B):
+             ent_coef, vf_coef, dlogits, ld_dl, dv, ld_dv, stats, B, cliprange_dev=None):
     _chk(actions, torch.int64, "actions")
     _chk(stats, torch.float64, "stats")
     _lib.call("b200rl_cat_loss", _ptr(logits), int(ld), int(nA), _ptr(vpred), int(ldv), _ptr(actions), _ptr(src_idx),
               _ptr(returns), _ptr(old_values), _ptr(old_neglogp), _ptr(adv_st), float(cliprange), float(ent_coef),
-              float(vf_coef), _ptr(dlogits), int(ld_dl), _ptr(dv), int(ld_dv), _ptr(stats), int(B), _stream())
+              float(vf_coef), _ptr(dlogits), int(ld_dl), _ptr(dv), int(ld_dv), _ptr(stats), int(B), _ptr(cliprange_dev),
+              _stream())
 
 
 def gauss_loss(mean, ld, logstd, d, vpred, ldv, actions, src_idx, returns, old_values, old_neglogp, adv_st,
-               cliprange, ent_coef, vf_coef, dmean, ld_dm, dv, ld_dv, dlogstd, inv_M, stats, B):
+               cliprange, ent_coef, vf_coef, dmean, ld_dm, dv, ld_dv, dlogstd, inv_M, stats, B, cliprange_dev=None):
     _chk(actions, torch.float32, "actions")
     _lib.call("b200rl_gauss_loss", _ptr(mean), int(ld), _ptr(logstd), int(d), _ptr(vpred), int(ldv), _ptr(actions),
               _ptr(src_idx), _ptr(returns), _ptr(old_values), _ptr(old_neglogp), _ptr(adv_st), float(cliprange),
               float(ent_coef), float(vf_coef), _ptr(dmean), int(ld_dm), _ptr(dv), int(ld_dv), _ptr(dlogstd),
-              float(inv_M), _ptr(stats), int(B), _stream())
+              float(inv_M), _ptr(stats), int(B), _ptr(cliprange_dev), _stream())
 
 
 def sumsq(g, out):
@@ -244,12 +261,12 @@ def seg_sumsq(g, seg_off, nseg, out):
     _lib.call("b200rl_seg_sumsq", _ptr(g), _ptr(seg_off), int(nseg), _ptr(out), _stream())
 
 
-def clip_adam(p, g, m, v, lr_t, beta1, beta2, eps, clip, sumsq_buf, seg_off=None, nseg=0):
+def clip_adam(p, g, m, v, lr_t, beta1, beta2, eps, clip, sumsq_buf, seg_off=None, nseg=0, lr_t_dev=None):
     for t, nm in ((p, "p"), (g, "g"), (m, "m"), (v, "v")):
         _chk(t, torch.float32, nm)
     _lib.call("b200rl_clip_adam", _ptr(p), _ptr(g), _ptr(m), _ptr(v), p.numel(), float(lr_t), float(beta1),
               float(beta2), float(eps), float(clip if clip else 0.0), _ptr(sumsq_buf), _ptr(seg_off), int(nseg),
-              _stream(), label="clip_adam", nbytes=28.0 * p.numel())
+              _ptr(lr_t_dev), _stream(), label="clip_adam", nbytes=28.0 * p.numel())
 
 
 def clip_accumulate(g, acc, clip, weight, sumsq_buf):
@@ -318,6 +335,8 @@ def dqn_td(a_t, lda_t, s_t, lds_t, a_on, lda_on, s_on, lds_on, a_tg, lda_tg, s_t
               int(ld_da), _ptr(d_s), int(ld_ds), _ptr(loss_sum), int(B), _stream())
 
 
-def dqn_act(a, lda, s, lds, nA, eps, seed, step, actions, B):
+def dqn_act(a, lda, s, lds, nA, eps, seed, step, actions, B, eps_dev=None, step_dev=None):
+    _chk(eps_dev, torch.float32, "eps_dev")
+    _chk(step_dev, torch.int64, "step_dev")
     _lib.call("b200rl_dqn_act", _ptr(a), int(lda), _ptr(s), int(lds), int(nA), float(eps), int(seed), int(step),
-              _ptr(actions), int(B), _stream())
+              _ptr(eps_dev), _ptr(step_dev), _ptr(actions), int(B), _stream())

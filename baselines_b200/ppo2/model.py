@@ -11,7 +11,7 @@ import os
 import numpy as np
 import torch
 
-from .. import ops
+from .. import graphs, ops
 from ..common.policies import PolicyNet
 from ..common import dist_util
 
@@ -43,7 +43,9 @@ class Model(object):
         self.initial_state = None
         self.act_model = self.train_model = self
         self._rng_seed = int(np.random.randint(0, 2 ** 31 - 1))
-        self._rng_offset = 0
+        self.graphs = graphs.GraphCache()
+        self._mb_idx = None                       # fixed home of the current minibatch's indices (graph replays)
+        self._stats_out = torch.zeros(5, dtype=torch.float64, device=self.device)
         self.comm = comm
         self.dist = dist_util.DataParallel(comm, mpi_rank_weight)
         self._train_calls = 0
@@ -51,16 +53,27 @@ class Model(object):
         self.net.refresh()
 
     # ------------------------------------------------------------------------------------ act path
-    def step_device(self, obs_dev, actions, values, neglogp, noise=None):
-        """PolicyWithValue.step (policies.py:77-96) on device tensors; obs_dev as produced by net.encode_obs."""
+    def step_device(self, obs_dev, actions, values, neglogp, noise=None, persistent=False):
+        """PolicyWithValue.step (policies.py:77-96) on device tensors; obs_dev as produced by net.encode_obs.
+        persistent=True: the caller passes the same buffers on every call (the Runner's rollout slots), so the launch
+        sequence is captured once per slot and replayed."""
         B = obs_dev.shape[0]
-        self._rng_offset += 1
-        self.net.act(obs_dev, B, actions, values, neglogp, noise=noise, seed=self._rng_seed, offset=self._rng_offset)
+        if persistent and noise is None:
+            key = ("act", obs_dev.data_ptr(), actions.data_ptr(), values.data_ptr(), neglogp.data_ptr(), B)
+            self.graphs.run(key, lambda: self.net.act(obs_dev, B, actions, values, neglogp, seed=self._rng_seed))
+        else:
+            self.net.act(obs_dev, B, actions, values, neglogp, noise=noise, seed=self._rng_seed)
 
-    def value_device(self, obs_dev, values):
+    def value_device(self, obs_dev, values, persistent=False):
         B = obs_dev.shape[0]
-        self.net.forward(obs_dev, B)
-        values.copy_(self.net.v_out[:B, 0] if self.net.v_out.dim() == 2 else self.net.v_out[:B])
+
+        def body():
+            self.net.forward(obs_dev, B)
+            values.copy_(self.net.v_out[:B, 0] if self.net.v_out.dim() == 2 else self.net.v_out[:B])
+        if persistent:
+            self.graphs.run(("value", obs_dev.data_ptr(), values.data_ptr(), B), body)
+        else:
+            body()
 
     def step(self, observation, S=None, M=None, noise=None, **_):
         """numpy in / numpy out, like the reference: (actions, values, states=None, neglogpacs)."""
@@ -100,26 +113,53 @@ class Model(object):
         net, store = self.net, self.net.store
         M = int(src_idx.numel()) if src_idx is not None else int(returns.numel())
         with torch.cuda.device(self.device):
-            store.grads.zero_()
-            net.stats.zero_()
-            ops.adv_stats(returns, values, src_idx, M, net.adv_st)       # per-MINIBATCH moments (model.py:139)
+            # scalars that change from call to call go to device memory first; everything after that is a fixed launch
+            # sequence for a given (rollout buffers, M), captured once and replayed (graphs.py)
+            ops.set_scalars(net.clip_dev, cliprange)
+            self.opt.begin_step(lr)
+            idx_all = None
+            if src_idx is not None:
+                if self._mb_idx is None or self._mb_idx.numel() < M:
+                    self._mb_idx = torch.empty(max(M, self.nbatch_train), dtype=torch.int64, device=self.device)
+                self._mb_idx[:M].copy_(src_idx)
+                idx_all = self._mb_idx
             inv_M = 1.0 / M
-            for s in range(0, M, self.chunk):
-                B = min(self.chunk, M - s)
-                if src_idx is not None:
-                    idx = src_idx[s:s + B]
-                    net.loss_backward(obs, B, idx, actions, returns, values, neglogpacs, cliprange, self.ent_coef,
-                                      self.vf_coef, inv_M)
+
+            def grads():
+                store.grads.zero_()
+                net.stats.zero_()
+                ops.adv_stats(returns, values, None if idx_all is None else idx_all[:M], M, net.adv_st)  # model.py:139
+                for s in range(0, M, self.chunk):
+                    B = min(self.chunk, M - s)
+                    if idx_all is not None:
+                        net.loss_backward(obs, B, idx_all[s:s + B], actions, returns, values, neglogpacs, None,
+                                          self.ent_coef, self.vf_coef, inv_M)
+                    else:
+                        sl = slice(s, s + B)
+                        net.loss_backward(obs[sl], B, None, actions[sl], returns[sl], values[sl], neglogpacs[sl],
+                                          None, self.ent_coef, self.vf_coef, inv_M)
+                net.freeze_identity()
+
+            def update():
+                self.opt.apply()                                         # model.py:107 clip -> :114 Adam
+                net.refresh()
+                self._stats_out.copy_(net.stats)
+
+            if idx_all is None:                                          # caller-owned temporaries: run eagerly
+                grads()
+                self.dist.average_gradients(store)
+                update()
+            else:
+                key = ("train", M, obs.data_ptr(), actions.data_ptr(), returns.data_ptr(), values.data_ptr(),
+                       neglogpacs.data_ptr())
+                if self.dist.active:
+                    self.graphs.run(key + ("grads",), grads)
+                    self.dist.average_gradients(store)                   # mpi_adam_optimizer.py:39-40, BEFORE the clip
+                    self.graphs.run(key + ("update",), update)
                 else:
-                    sl = slice(s, s + B)
-                    net.loss_backward(obs[sl], B, None, actions[sl], returns[sl], values[sl], neglogpacs[sl],
-                                      cliprange, self.ent_coef, self.vf_coef, inv_M)
-            net.freeze_identity()
-            self.dist.average_gradients(store)                           # mpi_adam_optimizer.py:39-40, BEFORE the clip
-            self.opt.step(lr)                                            # model.py:107 clip -> :114 Adam
-            net.refresh()
+                    self.graphs.run(key, lambda: (grads(), update()))
             self._after_train_call()
-            return net.stats / M
+            return self._stats_out / M
 
     def _after_train_call(self):
         """mpi_adam_optimizer.py:41-42: every 100th compute_gradients call checks that the ranks still hold identical

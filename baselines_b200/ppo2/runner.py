@@ -178,7 +178,7 @@ class Runner:
                 if not self.fs:
                     self._upload_obs(ro.obs[t])
                 model.step_device(ro.obs[t], ro.actions[t], ro.values[t], ro.neglogpacs[t],
-                                  noise=None if nz is None else nz[t])
+                                  noise=None if nz is None else nz[t], persistent=True)
                 if self.device_env:
                     ro.dones[t].copy_(self._dev_dones)
                     self._dev_obs, rew, self._dev_dones = self.env.step_device(ro.actions[t])
@@ -204,7 +204,7 @@ class Runner:
             # bootstrap value of the final observation (runner.py:50)
             if not self.fs:
                 self._upload_obs(self._cur)
-            model.value_device(self._cur, ro.last_values)
+            model.value_device(self._cur, ro.last_values, persistent=True)
             if self.device_env:
                 ro.last_dones.copy_(self._dev_dones)
             else:

@@ -337,7 +337,7 @@ def run_ppo2(cfg, args, steps, warmup, with_profile, with_e2e, dist_ctx):
             update(model, runner)
         torch.cuda.synchronize()
         if profile:
-            _lib.profile_begin()
+            _lib.profile_begin()                                 # per-call events: graphs.py falls back to eager launches
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()

@@ -119,11 +119,19 @@ int b200rl_colsum(const void* dz, float* db, long long rows, int C, long long ld
 /* act path: PolicyWithValue.step common/policies.py:77-96; CategoricalPd.sample/neglogp
  * common/distributions.py:164-201; DiagGaussianPd :238-248.  noise == NULL -> counter-based Philox. */
 int b200rl_cat_step(const float* logits, long long ld, int nA, const float* vpred, long long ldv,
-                    const float* uniforms, unsigned long long seed, unsigned long long offset, long long* actions,
-                    float* values, float* neglogp, long long B, void* stream);
+                    const float* uniforms, unsigned long long seed, unsigned long long offset,
+                    const unsigned long long* offset_dev, long long* actions, float* values, float* neglogp,
+                    long long B, void* stream);
 int b200rl_gauss_step(const float* mean, long long ld, const float* logstd, int d, const float* vpred,
                       long long ldv, const float* normals, unsigned long long seed, unsigned long long offset,
-                      float* actions, float* values, float* neglogp, long long B, void* stream);
+                      const unsigned long long* offset_dev, float* actions, float* values, float* neglogp,
+                      long long B, void* stream);
+/* Scalars that change between replays of a CUDA-graph-captured launch sequence live in device memory:
+ *   *_dev arguments (offset_dev of the samplers, cliprange_dev of the losses, lr_t_dev of clip_adam), when non-NULL,
+ *   override the by-value argument; set_scalars writes up to 4 floats from its own kernel arguments (no host staging
+ *   buffer to race with); counter_add advances the sampler's stream position after each acting pass. */
+int b200rl_set_scalars(float* dst, int n, float a, float b, float c, float d, void* stream);
+int b200rl_counter_add(unsigned long long* ctr, unsigned long long inc, void* stream);
 
 /* per-minibatch advantage moments: ppo2/model.py:136-139.  out = {mean, std} (float64). */
 int b200rl_adv_stats(const float* returns, const float* values, const long long* src_idx, long long M, double* out,
@@ -135,19 +143,21 @@ int b200rl_cat_loss(const float* logits, long long ld, int nA, const float* vpre
                     const long long* actions, const long long* src_idx, const float* returns,
                     const float* old_values, const float* old_neglogp, const double* adv_stats, float cliprange,
                     float ent_coef, float vf_coef, void* dlogits, long long ld_dl, void* dv, long long ld_dv,
-                    double* stats, long long B, void* stream);
+                    double* stats, long long B, const float* cliprange_dev, void* stream);
 int b200rl_gauss_loss(const float* mean, long long ld, const float* logstd, int d, const float* vpred,
                       long long ldv, const float* actions, const long long* src_idx, const float* returns,
                       const float* old_values, const float* old_neglogp, const double* adv_stats, float cliprange,
                       float ent_coef, float vf_coef, void* dmean, long long ld_dm, void* dv, long long ld_dv,
-                      float* dlogstd, float inv_M, double* stats, long long B, void* stream);
+                      float* dlogstd, float inv_M, double* stats, long long B, const float* cliprange_dev,
+                      void* stream);
 
 /* optimiser: tf.clip_by_global_norm ppo2/model.py:105-107, tf.clip_by_norm deepq/build_graph.py:416-421,
  * tf.train.AdamOptimizer ppo2/model.py:100 == common/mpi_adam.py:37-42. lr_t = lr*sqrt(1-b2^t)/(1-b1^t). */
 int b200rl_sumsq(const float* g, long long n, double* out, void* stream);
 int b200rl_seg_sumsq(const float* g, const long long* seg_off, int nseg, double* out, void* stream);
 int b200rl_clip_adam(float* p, const float* g, float* m, float* v, long long n, float lr_t, float beta1, float beta2,
-                     float eps, float clip, const double* sumsq, const long long* seg_off, int nseg, void* stream);
+                     float eps, float clip, const double* sumsq, const long long* seg_off, int nseg,
+                     const float* lr_t_dev, void* stream);
 /* acc += g * clip/max(||g||, clip) * weight (clip <= 0: no clipping): the clipped per-microbatch gradients that
  * ppo2/microbatched_model.py:60-70 sums and averages before one apply_gradients. */
 int b200rl_clip_accumulate(const float* g, float* acc, long long n, float clip, float weight, const double* sumsq,
@@ -188,7 +198,8 @@ int b200rl_dqn_td(const float* a_t, long long lda_t, const float* s_t, long long
                   float* td_out, void* d_a, long long ld_da, void* d_s, long long ld_ds, double* loss_sum, int B,
                   void* stream);
 int b200rl_dqn_act(const float* a, long long lda, const float* s, long long lds, int nA, float eps,
-                   unsigned long long seed, unsigned long long step, long long* actions, int B, void* stream);
+                   unsigned long long seed, unsigned long long step, const float* eps_dev,
+                   const unsigned long long* step_dev, long long* actions, int B, void* stream);
 
 #ifdef __cplusplus
 }

@@ -551,3 +551,87 @@ def test_reference_layout_checkpoint_fixture_and_adam_step_recovery(tmp_path):
     joblib.dump(ck, path)
     model2.load(path)
     assert model2.opt.t >= 10 ** 5
+
+
+# ----------------------------------------------------------------------------------------------- graph replay
+def test_cuda_graph_replay_equals_eager_launch_sequence():
+    """graphs.py: acting passes, the bootstrap value pass and whole train minibatches are captured once and replayed;
+    scalars that change between replays (Adam step size with its bias correction, the annealed clip range, the sampler's
+    stream position, the minibatch indices) live in device memory.  Three updates with annealed lr / cliprange must give
+    the same actions (bit-exact: the acting forward has no atomics) and the same parameters (float-atomic order) as the
+    eager sequence, and the second and third update must actually run from graphs."""
+    from baselines_b200 import _lib
+    from baselines_b200.common.vec_env import DeviceSyntheticVecEnv
+    from baselines_b200.ppo2.ppo2 import run_epochs
+    from baselines_b200.ppo2.runner import Runner
+    case = CASES["cnn_cat"]
+    T, N, nmb, nep = 8, 64, 2, 2
+    out = {}
+    for mode in ("eager", "graphs"):
+        if mode == "eager":
+            os.environ["B200RL_NO_GRAPHS"] = "1"
+        try:
+            env, model, _ = _mk(nenv=N, nsteps=T, nminibatches=nmb, **case)
+            model._rng_seed = 1234
+            denv = DeviceSyntheticVecEnv(N, (84, 84, 4), np.uint8, n_actions=6, seed=3)
+            runner = Runner(env=denv, model=model, nsteps=T, gamma=0.99, lam=0.95)
+            rng = np.random.RandomState(0)
+            acts, replays0 = [], _lib.REPLAYS
+            for upd in range(3):
+                ro, _ = runner.run_device()
+                acts.append(ro.actions.cpu().numpy().copy())
+                perms = [rng.permutation(T * N) for _ in range(nep)]
+                frac = 1.0 - upd / 3.0
+                st = run_epochs(model, ro, 2.5e-4 * frac, 0.1 * frac, T * N, T * N // nmb, nep, model.device, perms=perms)
+            torch.cuda.synchronize()
+            out[mode] = (acts, model.get_params(), torch.stack(st).cpu().numpy(), _lib.REPLAYS - replays0, model.opt.t)
+        finally:
+            os.environ.pop("B200RL_NO_GRAPHS", None)
+    assert out["eager"][3] == 0 and out["graphs"][3] >= 2 * (T + 1) + nmb * nep     # updates 2 and 3 ran from graphs
+    assert out["eager"][4] == out["graphs"][4] == 3 * nmb * nep
+    for a, b in zip(out["eager"][0], out["graphs"][0]):
+        assert np.array_equal(a, b)
+    assert np.allclose(out["eager"][2], out["graphs"][2], atol=1e-6)
+    for k in out["eager"][1]:
+        assert np.allclose(out["eager"][1][k], out["graphs"][1][k], atol=2e-6), k
+
+
+def test_dqn_graph_replay_equals_eager():
+    from baselines_b200 import _lib
+    from baselines_b200.common import spaces
+    from baselines_b200.deepq.build_graph import DQNModel, build_act
+    from baselines_b200.deepq.replay_buffer import PrioritizedReplayBuffer
+    res = {}
+    for mode in ("eager", "graphs"):
+        if mode == "eager":
+            os.environ["B200RL_NO_GRAPHS"] = "1"
+        try:
+            np.random.seed(0)
+            random.seed(0)
+            model = DQNModel(spaces.Box(0, 255, (84, 84, 4), np.uint8), 6, "cnn", lr=1e-4, gamma=0.99,
+                             grad_norm_clipping=10, batch_cap=64, seed=2, hiddens=(256,), dueling=True)
+            model._seed = 99
+            rb = PrioritizedReplayBuffer(4096, 0.6)
+            g = torch.Generator(device="cuda").manual_seed(1)
+            o = torch.randint(0, 256, (4096, 84, 84, 4), dtype=torch.uint8, device="cuda", generator=g)
+            rb.add_batch(o, torch.randint(0, 6, (4096,), device="cuda", generator=g),
+                         torch.randn(4096, device="cuda", generator=g), o.flip(0), torch.zeros(4096, device="cuda"))
+            act = build_act(model)
+            r0 = _lib.REPLAYS
+            tds, acts = [], []
+            for it in range(5):
+                acts.append(act(o[it:it + 1].cpu().numpy(), update_eps=0.5).copy())
+                idx, w32, _ = rb.sample_device(64, beta=0.4)
+                td = model.train_device(rb._obs_t, rb._obs_tp1, rb._actions, rb._rewards, rb._dones, w32, idx, 64)
+                rb.update_priorities_device(idx, td, 1e-6)
+                tds.append(td.cpu().numpy().copy())
+            res[mode] = (tds, acts, model.q.store.export_tf("params"), _lib.REPLAYS - r0)
+        finally:
+            os.environ.pop("B200RL_NO_GRAPHS", None)
+    assert res["eager"][3] == 0 and res["graphs"][3] >= 6
+    for a, b in zip(res["eager"][1], res["graphs"][1]):
+        assert np.array_equal(a, b)
+    for a, b in zip(res["eager"][0], res["graphs"][0]):
+        assert np.allclose(a, b, atol=1e-4)
+    for k in res["eager"][2]:
+        assert np.allclose(res["eager"][2][k], res["graphs"][2][k], atol=1e-5), k

@@ -46,7 +46,7 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
 // MODE 0: SS K-major (A [M rows x 128 B], B [N rows x 128 B], SWIZZLE_128B)
 // MODE 1: TS (A in TMEM), B as above
 // MODE 2: SS MN-major both (the wgrad form): A [16 K-rows x 128 M], B [16 K-rows x N]
-template <int M, int N, int MODE, bool LSU, int NMMA>
+template <int M, int N, int MODE, bool LSU, int NMMA, int AOFF = 0>
 __global__ void __launch_bounds__(384, 1) probe_kernel(Result* out) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -84,7 +84,7 @@ __global__ void __launch_bounds__(384, 1) probe_kernel(Result* out) {
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
           if (MODE == 0) {
-            const uint64_t ad = make_sdesc(a_addr + ((i >> 2) & 1) * 16384 + k * 32, 16, 1024, 2u);
+            const uint64_t ad = make_sdesc(a_addr + AOFF * 128 + ((i >> 2) & 1) * 8192 + k * 32, 16, 1024, 2u);   // AOFF rows: the shifted-tap start
             const uint64_t bd = make_sdesc(b_addr + ((i >> 2) & 1) * 32768 + k * 32, 16, 1024, 2u);
             umma_f16(tmem_base, ad, bd, IDESC, 1);
           } else if (MODE == 1) {
@@ -153,11 +153,11 @@ __global__ void __launch_bounds__(384, 1) probe_kernel(Result* out) {
   }
 }
 
-template <int M, int N, int MODE, bool LSU>
+template <int M, int N, int MODE, bool LSU, int AOFF = 0>
 static void run(const char* name, int ctas) {
   constexpr int NMMA = 4096;
   constexpr int SMEM = 161 * 1024 + 1024;
-  auto kern = probe_kernel<M, N, MODE, LSU, NMMA>;
+  auto kern = probe_kernel<M, N, MODE, LSU, NMMA, AOFF>;
   cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
   Result* d;
   cudaMalloc(&d, sizeof(Result) * ctas);
@@ -207,5 +207,15 @@ int main(int argc, char** argv) {
   run<128, 64, 2, false>("mn_n64", ctas);
   run<128, 128, 2, false>("mn_n128", ctas);
   run<128, 32, 0, false>("ss_n32_1cta", 1);
+  // A operand starting at a row that is not a multiple of 8 (the shifted filter taps of csrc/conv_shift.cu)
+  run<128, 32, 0, false, 1>("ss_n32_aoff1", ctas);
+  run<128, 32, 0, false, 21>("ss_n32_aoff21", ctas);
+  run<128, 64, 0, false, 1>("ss_n64_aoff1", ctas);
+  run<128, 64, 0, false, 21>("ss_n64_aoff21", ctas);
+  run<128, 64, 0, false, 8>("ss_n64_aoff8", ctas);
+  run<128, 128, 0, false, 10>("ss_n128_aoff10", ctas);
+  run<128, 192, 0, false, 0>("ss_n192", ctas);
+  run<128, 192, 0, false, 9>("ss_n192_aoff9", ctas);
+  run<128, 256, 0, false, 5>("ss_n256_aoff5", ctas);
   return 0;
 }
