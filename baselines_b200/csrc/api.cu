@@ -17,7 +17,7 @@ void set_last_error(const char* fmt, ...) {
 }
 
 int gemm_f16_impl(const void*, const void*, void*, const float*, const void*, int, int, int, long long, long long,
-                  long long, long long, int, int, int, float, int, int, int, int, int, cudaStream_t);
+                  long long, long long, int, int, int, float, int, int, int, int, int, const void*, cudaStream_t);
 int conv_shift_fwd_impl(const void*, long long, int, int, int, const void*, long long, int, int, const int*, int, int,
                         void*, const long long*, const void*, const long long*, const float*, int, int, float,
                         const void*, const long long*, int, int, int, int, void*, const void*, int, cudaStream_t);
@@ -88,9 +88,10 @@ int b200rl_gae_scan(const float* rewards, const float* values, const uint8_t* do
 
 int b200rl_gemm_f16(const void* A, const void* B, void* C, const float* bias, const void* saved, int M, int N, int K,
                     long long lda, long long ldb, long long ldc, long long ld_saved, int mn_major, int mode, int act,
-                    float alpha, int split_k, int max_ctas, int rm_C, int rm_OW, int rm_Wg, void* stream) {
+                    float alpha, int split_k, int max_ctas, int rm_C, int rm_OW, int rm_Wg, const void* saved_bits,
+                    void* stream) {
   return gemm_f16_impl(A, B, C, bias, saved, M, N, K, lda, ldb, ldc, ld_saved, mn_major, mode, act, alpha, split_k,
-                       max_ctas, rm_C, rm_OW, rm_Wg, S(stream));
+                       max_ctas, rm_C, rm_OW, rm_Wg, saved_bits, S(stream));
 }
 
 int b200rl_conv_shift_fwd(const void* X, long long B, int Hg, int Wg, int C, const void* W, long long ldw, int N,

@@ -31,7 +31,12 @@ namespace b200rl {
 
 static constexpr int SH_BM = 128;
 static constexpr int SH_THREADS = 256;             // wgrad: TMA, MMA, TMEM alloc, spare, 4 epilogue warps
-static constexpr int SH_FWD_THREADS = 384;         // forward: two epilogue warp sets (one per accumulator stage)
+// forward: the epilogue is latency-bound per warp (a dependent chain tcgen05.ld -> math -> pack -> store of ~150
+// instructions per 16 columns at an IPC of ~0.25), so it gets SH_CG column groups of 4 warps per accumulator stage:
+// 2 stages x SH_CG groups x 4 lane quadrants
+static constexpr int SH_CG = 2;
+static constexpr int SH_EPI_WARPS = 2 * SH_CG * 4;
+static constexpr int SH_FWD_THREADS = 128 + SH_EPI_WARPS * 32;
 static constexpr int SH_MAX_TAPS = 16;
 static constexpr int SH_AROWS = 160;                 // 128 + max shift span (<= 32)
 static constexpr int SH_ABYTES = SH_AROWS * 128;     // one 64-channel half of an A stage
@@ -277,9 +282,11 @@ conv_shift_fwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_cons
 
   __shared__ float s_bias[NO];
   // x-fold halo exchange: [accumulator stage][parity][warp][halo row slot][column of the current chunk]
-  constexpr int XG = (KX == 1) ? 1 : (NO >= 64 ? 2 : NO / 16);        // 16-column chunks combined per exchange round
+  constexpr int NCG = NO / SH_CG;                                     // output columns per epilogue column group
+  static_assert(NCG % 16 == 0, "column groups are whole 16-column chunks");
+  constexpr int XG = (KX == 2 && NCG >= 32) ? 2 : 1;                  // 16-column chunks combined per exchange round
   constexpr int XROWS = (KX * (KX - 1)) / 2;                          // sum_b b halo rows per warp
-  __shared__ float s_xch[(KX > 1) ? 2 : 1][2][4][(KX > 1) ? XROWS : 1][16 * XG];
+  __shared__ float s_xch[(KX > 1) ? 2 * SH_CG : 1][2][4][(KX > 1) ? XROWS : 1][16 * XG];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x < NO) s_bias[threadIdx.x] = (p.bias && (int)threadIdx.x < p.N) ? p.bias[threadIdx.x] : 0.0f;
   if (warp == 0 && lane == 0) {
@@ -288,7 +295,7 @@ conv_shift_fwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_cons
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], U8 ? SH_AROWS / 32 : 1); mbar_init(&empty_bar[s], 1); }
-    for (int s = 0; s < 2; ++s) { mbar_init(&tfull_bar[s], 1); mbar_init(&tempty_bar[s], 128); }
+    for (int s = 0; s < 2; ++s) { mbar_init(&tfull_bar[s], 1); mbar_init(&tempty_bar[s], 128 * SH_CG); }
     mbar_init(w_bar, 1);
     fence_barrier_init();
   }
@@ -323,14 +330,14 @@ conv_shift_fwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_cons
         if (++s == STAGES) { s = 0; ph ^= 1; }
       }
     }
-  } else if (U8 && warp >= 12) {
+  } else if (U8 && warp >= 4 + SH_EPI_WARPS) {
     // uint8 producer warps (the cp.async ring lives in the unused 64 KB of the weight area)
     const int step = gridDim.x, first = blockIdx.x;
     const int ntiles = first < p.num_tiles ? (p.num_tiles - first + step - 1) / step : 0;
     const int min_shift = p.min_shift;
     u8_producer_loop<SH_AROWS, STAGES>(
         p.u8, p.M, ntiles, [=](int seq) { return (long long)(first + seq * step) * TSTEP + min_shift; }, smem,
-        STAGE_BYTES, full_bar, empty_bar, wres + 16384, warp - 12, lane);
+        STAGE_BYTES, full_bar, empty_bar, wres + 16384, warp - (4 + SH_EPI_WARPS), lane);
   } else if (warp == 1) {
     constexpr uint32_t IDESC = (1u << 4) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(SH_BM >> 4) << 24);
     int s = 0, as = 0;
@@ -368,11 +375,12 @@ conv_shift_fwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_cons
       if (++s == STAGES) { s = 0; ph ^= 1; }
       if (++as == 2) { as = 0; aph ^= 1; }
     }
-  } else if (warp >= 4 && warp < 12) {
-    // warps 4-7 drain accumulator stage 0 (even tiles), warps 8-11 stage 1 (odd tiles): a warp reaches TMEM lane
-    // quadrant warp % 4 only, and one set per stage gives every tile two tile-times of epilogue
+  } else if (warp >= 4 && warp < 4 + SH_EPI_WARPS) {
+    // epilogue warp e = warp - 4: accumulator stage as = e / (4*SH_CG) (even / odd tiles), column group
+    // cg = (e / 4) % SH_CG, TMEM lane quadrant ew = warp % 4 (a warp reaches only that quadrant)
     const int ew = warp & 3;
-    const int as = (warp - 4) >> 2;
+    const int as = (warp - 4) / (4 * SH_CG);
+    const int cg = ((warp - 4) >> 2) % SH_CG;
     uint32_t aph = 0;
     if constexpr (KX > 1) {
       uint32_t par = 0;
@@ -390,7 +398,7 @@ conv_shift_fwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_cons
         tc_fence_after();
         const uint32_t taddr0 = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(as * BN);
 #pragma unroll 1
-        for (int c0 = 0; c0 < NO; c0 += 16 * XG) {
+        for (int c0 = cg * NCG; c0 < (cg + 1) * NCG; c0 += 16 * XG) {
           uint32_t r[KX][XG][16];
 #pragma unroll
           for (int b = 0; b < KX; ++b)
@@ -401,18 +409,18 @@ conv_shift_fwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_cons
 #pragma unroll
           for (int b = 1; b < KX; ++b) {
             if (lane < b) {
-              float* dst = s_xch[as][par][ew][(b * (b - 1)) / 2 + lane];
+              float* dst = s_xch[as * SH_CG + cg][par][ew][(b * (b - 1)) / 2 + lane];
 #pragma unroll
               for (int j = 0; j < XG; ++j)
 #pragma unroll
                 for (int i = 0; i < 16; ++i) dst[16 * j + i] = __uint_as_float(r[b][j][i]);
             }
           }
-          asm volatile("bar.sync %0, 128;" ::"r"(1 + as) : "memory");
+          asm volatile("bar.sync %0, 128;" ::"r"(1 + as * SH_CG + cg) : "memory");
 #pragma unroll
           for (int b = 1; b < KX; ++b) {
             const bool halo = lane >= 32 - b;
-            const float* src = s_xch[as][par][(ew + 1) & 3][(b * (b - 1)) / 2 + (halo ? lane - (32 - b) : 0)];
+            const float* src = s_xch[as * SH_CG + cg][par][(ew + 1) & 3][(b * (b - 1)) / 2 + (halo ? lane - (32 - b) : 0)];
 #pragma unroll
             for (int j = 0; j < XG; ++j)
 #pragma unroll
@@ -453,7 +461,8 @@ conv_shift_fwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_cons
         aph ^= 1;
       }
     } else {
-      constexpr int G = (BN >= 64) ? 4 : BN / 16;       // 16-column chunks handled together (loads in flight)
+      // 16-column chunks handled together (loads in flight); the masked data gradient also holds the mask words
+      constexpr int G = DACT ? ((NCG >= 32) ? 2 : 1) : ((NCG >= 64) ? 4 : NCG / 16);
       for (int tile = blockIdx.x + as * (int)gridDim.x; tile < p.num_tiles; tile += 2 * (int)gridDim.x) {
         const uint32_t m = (uint32_t)tile * SH_BM + ew * 32 + lane;       // M < 2^31 (checked on the host)
         const uint32_t t2 = p.fwg.div(m);
@@ -472,7 +481,7 @@ conv_shift_fwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_cons
         tc_fence_after();
         const uint32_t taddr0 = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(as * BN);
   #pragma unroll 1
-        for (int c0 = 0; c0 < BN; c0 += 16 * G) {
+        for (int c0 = cg * NCG; c0 < (cg + 1) * NCG; c0 += 16 * G) {
           uint32_t sv[G][8];
           if (DACT) {
             if (masked && ok && p.saved_bits != nullptr) {

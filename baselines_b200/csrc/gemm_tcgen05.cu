@@ -32,7 +32,11 @@ namespace b200rl {
 static constexpr int BM = 128;
 static constexpr int BK = 64;          // elements of the reduction dimension per pipeline stage
 static constexpr int UMMA_K = 16;
-static constexpr int NUM_THREADS = 384;   // TMA, MMA, TMEM alloc, spare + two epilogue warp sets (one per accumulator stage)
+// TMA, MMA, TMEM alloc, spare + epilogue warps: 2 accumulator stages x GEMM_CG column groups x 4 lane quadrants.  The
+// epilogue is a latency-bound dependent chain per warp (tcgen05.ld -> math -> pack -> store), so the columns of a tile
+// are split over GEMM_CG warps per quadrant.
+static constexpr int GEMM_CG = 2;
+static constexpr int NUM_THREADS = 128 + 2 * GEMM_CG * 128;
 
 
 struct ConvCoords {       // im2col traversal of the A operand (all zero for plain GEMMs)
@@ -53,6 +57,7 @@ struct GemmParams {
   long long ldc;
   const float* bias;
   const __half* saved;     // saved activation for MODE_F16_DACT / SHUFFLE masks
+  const uint16_t* saved_bits;   // MODE_F16_DACT alternative: 1 bit per element (activation > 0), word (row*ld_saved + col)/16
   long long ld_saved;
   float alpha;
   int mode, act;
@@ -125,7 +130,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tfull_bar[s], 1);
-      mbar_init(&tempty_bar[s], 128);
+      mbar_init(&tempty_bar[s], 128 * GEMM_CG);
     }
     mbar_init(bres_bar, 1);
     fence_barrier_init();
@@ -275,19 +280,40 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     }
   } else if (warp >= 4) {
     // ------------------------------------------------------------------ epilogue
-    // warps 4-7 drain accumulator stage 0 (even work items of this CTA), warps 8-11 stage 1 (odd ones)
-    const int ew = warp & 3;            // TMEM lane quarter this warp may access
+    // warp e = warp - 4: accumulator stage as = e / (4*GEMM_CG) (even / odd work items of this CTA), column group
+    // cg = (e / 4) % GEMM_CG, TMEM lane quarter ew = warp % 4
+    const int ew = warp & 3;
     const int mode = (TMODE >= 0) ? TMODE : p.mode;
-    const int as = (warp - 4) >> 2;
+    const int as = (warp - 4) / (4 * GEMM_CG);
+    const int cg = ((warp - 4) >> 2) % GEMM_CG;
+    constexpr int NCG = (BN / GEMM_CG >= 16) ? BN / GEMM_CG : 16;         // columns per group (BN = 16*k)
+    constexpr int NCH = NCG / 16;
+    constexpr int PF = (NCH > 4) ? 4 : NCH;                               // mask chunks prefetched ahead
+    const bool active = cg * NCG < BN;
     uint32_t aph = 0;
     for (int work = blockIdx.x + as * (int)gridDim.x; work < total_work; work += 2 * (int)gridDim.x) {
       const int n_tile = work % p.n_tiles;
       const int t2 = work / p.n_tiles;
       const int m_tile = t2 % p.m_tiles;
-      mbar_wait(&tfull_bar[as], aph);
-      tc_fence_after();
       const int row = m_tile * BM + ew * 32 + lane;
       const bool row_ok = row < p.M;
+      // the activation mask of a data gradient does not depend on the accumulator: fetch it while the MMAs run
+      uint32_t sv[PF][8];
+      const bool dact_vec = (mode == MODE_F16_DACT) && p.vec32 && row_ok && active;
+      const bool use_bits = (mode == MODE_F16_DACT) && p.saved_bits != nullptr;
+      auto prefetch = [&](int k, int slot) {
+        const int col0 = n_tile * BN + cg * NCG + 16 * k;
+        if (dact_vec && col0 + 16 <= p.N) {
+          if (use_bits) sv[slot][0] = __ldg(p.saved_bits + (((long long)row * p.ld_saved + col0) >> 4));
+          else ldg256(p.saved + (long long)row * p.ld_saved + col0, sv[slot]);
+        }
+      };
+      if (mode == MODE_F16_DACT) {
+#pragma unroll
+        for (int k = 0; k < PF; ++k) prefetch(k, k);
+      }
+      mbar_wait(&tfull_bar[as], aph);
+      tc_fence_after();
       int sh_n = 0, sh_i = 0, sh_j = 0;
       if (mode == MODE_F16_SHUFFLE) {
         sh_j = row % p.cv.OW;
@@ -295,13 +321,17 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         sh_i = t3 % p.cv.OH;
         sh_n = t3 / p.cv.OH;
       }
-      const uint32_t taddr0 = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(as * BN);
+      const uint32_t taddr0 = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(as * BN + cg * NCG);
+      if (active) {
 #pragma unroll 1
-      for (int c = 0; c < BN; c += 16) {
+      for (int k0 = 0; k0 < NCH; k0 += PF) {
+#pragma unroll
+      for (int kk = 0; kk < PF; ++kk) {
+        const int k = k0 + kk;
         uint32_t r[16];
-        tmem_ld16(taddr0 + c, r);
+        tmem_ld16(taddr0 + 16 * k, r);
         tmem_ld_wait();
-        const int col0 = n_tile * BN + c;
+        const int col0 = n_tile * BN + cg * NCG + 16 * k;
         if (row_ok && col0 < p.N) {
           float v[16];
 #pragma unroll
@@ -342,7 +372,22 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                 for (int i = 0; i < 16; ++i) v[i] = fmaxf(v[i], lo);
               }
             } else {  // MODE_F16_DACT: dX = (dY W^T) * act'(saved activation)
-              mask16(v, p.saved + (long long)row * p.ld_saved + col0, full && p.vec32, nvalid, p.act);
+              if (full && p.vec32) {
+                if (use_bits) {                    // 1 bit per element: relu'(h) = (h > 0)
+                  const uint32_t bw = sv[kk][0];
+#pragma unroll
+                  for (int i = 0; i < 16; ++i) v[i] = ((bw >> i) & 1u) ? v[i] : 0.0f;
+                } else {
+#pragma unroll
+                  for (int i = 0; i < 8; ++i) {
+                    const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&sv[kk][i]));
+                    v[2 * i] *= act_grad_from_saved(f.x, p.act);
+                    v[2 * i + 1] *= act_grad_from_saved(f.y, p.act);
+                  }
+                }
+              } else {
+                mask16(v, p.saved + (long long)row * p.ld_saved + col0, false, nvalid, p.act);
+              }
             }
             int ocol = col0;
             if (p.rm_C > 0) {
@@ -353,6 +398,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                         full && p.vec32, nvalid);
           }
         }
+        if (mode == MODE_F16_DACT && k + PF < NCH) prefetch(k + PF, kk);      // refill the slot just consumed
+      }
+      }
       }
       tc_fence_before();
       mbar_arrive(&tempty_bar[as]);
@@ -486,7 +534,8 @@ static void fill_splits(GemmParams& p, int split_k) {
 // C-ABI body (declared in include/b200rl.h)
 int gemm_f16_impl(const void* A, const void* B, void* C, const float* bias, const void* saved, int M, int N, int K,
                   long long lda, long long ldb, long long ldc, long long ld_saved, int mn_major, int mode, int act,
-                  float alpha, int split_k, int max_ctas, int rm_C, int rm_OW, int rm_Wg, cudaStream_t stream) {
+                  float alpha, int split_k, int max_ctas, int rm_C, int rm_OW, int rm_Wg, const void* saved_bits,
+                  cudaStream_t stream) {
   B200RL_REQUIRE(A && B && C, "gemm: null operand");
   B200RL_REQUIRE(rm_C == 0 || (rm_C % 16 == 0 && rm_OW > 0 && rm_Wg >= rm_OW && (mode == MODE_F16_ACT || mode == MODE_F16_DACT)),
                  "gemm: bad column remap");
@@ -496,7 +545,10 @@ int gemm_f16_impl(const void* A, const void* B, void* C, const float* bias, cons
   B200RL_REQUIRE((reinterpret_cast<uintptr_t>(A) & 15) == 0 && (reinterpret_cast<uintptr_t>(B) & 15) == 0,
                  "gemm: operands must be 16-byte aligned");
   B200RL_REQUIRE(mode >= 0 && mode <= 3, "gemm: bad mode %d", mode);
-  B200RL_REQUIRE(mode != MODE_F16_DACT || saved != nullptr, "gemm: MODE_F16_DACT needs the saved activation");
+  B200RL_REQUIRE(mode != MODE_F16_DACT || saved != nullptr || saved_bits != nullptr,
+                 "gemm: MODE_F16_DACT needs the saved activation (or its bit mask)");
+  B200RL_REQUIRE(saved_bits == nullptr || (mode == MODE_F16_DACT && act == ACT_RELU && (ld_saved % 16) == 0 && (N % 16) == 0),
+                 "gemm: saved_bits is a ReLU mask for MODE_F16_DACT with ld_saved and N multiples of 16");
 
   int BN;
   if (mn_major) BN = (N > 64) ? 128 : 64;
@@ -510,10 +562,12 @@ int gemm_f16_impl(const void* A, const void* B, void* C, const float* bias, cons
   B200RL_REQUIRE(split_k <= 1 || mode == MODE_F32_ATOMIC, "gemm: split_k needs the fp32 atomic epilogue");
   fill_splits(p, split_k);
   p.C = C; p.ldc = ldc; p.bias = bias; p.saved = reinterpret_cast<const __half*>(saved); p.ld_saved = ld_saved;
+  p.saved_bits = reinterpret_cast<const uint16_t*>(saved_bits);
   p.alpha = alpha; p.mode = mode; p.act = act;
   p.rm_C = rm_C; p.rm_OW = rm_OW; p.rm_Wg = rm_Wg;
   p.vec32 = ((ldc & 15) == 0) && ((reinterpret_cast<uintptr_t>(C) & 31) == 0) && (rm_C == 0 || (rm_C & 15) == 0) &&
             (!saved || (((ld_saved & 15) == 0) && ((reinterpret_cast<uintptr_t>(saved) & 31) == 0)));
+  B200RL_REQUIRE(saved_bits == nullptr || p.vec32, "gemm: saved_bits needs 32-byte aligned 16-column output chunks");
 
   CUtensorMap tmA, tmB;
   int rc;

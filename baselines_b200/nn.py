@@ -194,9 +194,12 @@ class Linear:
                      tag="wgrad." + self.name)
         ops.colsum(dz, self.gb, M, self.N, lddz, alpha=alpha)
 
-    def dgrad(self, dz, lddz, M, out, ldo, saved=None, ld_saved=0, act=ops.ACT_NONE, remap=(0, 0, 0)):
-        """out[M, K] = (dz W^T) * act'(saved)."""
-        if saved is None or act == ops.ACT_NONE:
+    def dgrad(self, dz, lddz, M, out, ldo, saved=None, ld_saved=0, act=ops.ACT_NONE, remap=(0, 0, 0), saved_bits=None):
+        """out[M, K] = (dz W^T) * act'(saved); saved_bits: the ReLU mask as 1 bit per element instead of `saved`."""
+        if saved_bits is not None and act == ops.ACT_RELU:
+            ops.gemm(dz, self.w_bwd, out, M=M, N=self.K, K=self.N, lda=lddz, ldb=self.Np, ldc=ldo, saved_bits=saved_bits,
+                     ld_saved=ld_saved, mode=ops.MODE_F16_DACT, act=act, tag="dgrad." + self.name, remap=remap)
+        elif saved is None or act == ops.ACT_NONE:
             ops.gemm(dz, self.w_bwd, out, M=M, N=self.K, K=self.N, lda=lddz, ldb=self.Np, ldc=ldo,
                      mode=ops.MODE_F16_ACT, act=ops.ACT_NONE, tag="dgrad." + self.name, remap=remap)
         else:
@@ -466,7 +469,7 @@ class Tower:
         # these instead of the fp16 activations (16x less mask traffic)
         self.hbits = [None] * len(cv)
         if os.environ.get("B200RL_NO_RELU_BITS", "0") != "1":
-            for i, c in enumerate(cv[:-1]):
+            for i, c in enumerate(cv):               # the last conv's mask serves the fc1 data gradient
                 if c.act == ops.ACT_RELU and (c.OH * c.OW * c.nf) % 16 == 0:
                     self.hbits[i] = torch.zeros(cap * (c.OH * c.OW * c.nf // 16), dtype=torch.int16,
                                                 device=self.hconv[i].device)
@@ -615,7 +618,8 @@ class Tower:
             elif self.shift_mode:
                 cL, gL = self.convs[-1], self.sg[-1]
                 out, ldo = self.dY[-1], gL["Hg"] * gL["Wg"] * cL.nf      # scatter into the zero-bordered grid
-                l.dgrad(dz, lddz, B, out, ldo, saved=xin, ld_saved=ldx, act=act_in, remap=(cL.nf, cL.OW, gL["Wg"]))
+                l.dgrad(dz, lddz, B, out, ldo, saved=xin, ld_saved=ldx, act=act_in, remap=(cL.nf, cL.OW, gL["Wg"]),
+                        saved_bits=self.hbits[-1])
             else:
                 out, ldo = self.dzconv[-1], self.flat
                 l.dgrad(dz, lddz, B, out, ldo, saved=xin, ld_saved=ldx, act=act_in)

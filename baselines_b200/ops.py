@@ -44,18 +44,19 @@ def gae_scan(rewards, values, dones, last_values, last_dones, advs, returns, gam
 
 
 def gemm(A, B, C, *, M, N, K, lda, ldb, ldc, bias=None, saved=None, ld_saved=0, mn_major=False,
-         mode=MODE_F16_ACT, act=ACT_NONE, alpha=1.0, split_k=1, max_ctas=0, tag=None, remap=(0, 0, 0)):
+         mode=MODE_F16_ACT, act=ACT_NONE, alpha=1.0, split_k=1, max_ctas=0, tag=None, remap=(0, 0, 0), saved_bits=None):
     _chk(A, torch.float16, "A")
     _chk(B, torch.float16, "B")
     _chk(bias, torch.float32, "bias")
     _chk(saved, torch.float16, "saved")
+    _chk(saved_bits, torch.int16, "saved_bits")
     _lib.call("b200rl_gemm_f16", _ptr(A), _ptr(B), _ptr(C), _ptr(bias), _ptr(saved), int(M), int(N), int(K),
               int(lda), int(ldb), int(ldc), int(ld_saved), int(bool(mn_major)), int(mode), int(act), float(alpha),
-              int(split_k), int(max_ctas), int(remap[0]), int(remap[1]), int(remap[2]), _stream(),
+              int(split_k), int(max_ctas), int(remap[0]), int(remap[1]), int(remap[2]), _ptr(saved_bits), _stream(),
               label="gemm." + (tag or ("wgrad" if mn_major else "tn")),
               flops=2.0 * M * N * K,
               nbytes=2.0 * (M * K + N * K) + M * N * (2 if mode in (MODE_F16_ACT, MODE_F16_DACT) else 4)
-              + (2.0 * M * N if mode == MODE_F16_DACT else 0))
+              + ((0.125 if saved_bits is not None else 2.0) * M * N if mode == MODE_F16_DACT else 0))
 
 
 def conv_gemm(x, B, H, W, C, R, S, stride_h, stride_w, pad_h, pad_w, OH, OW, wt_or_dz, ldb, out, ldc, N, kind,

@@ -52,7 +52,10 @@ int b200rl_gae_scan(const float* rewards, const float* values, const uint8_t* do
  * max_ctas <= 0 : one persistent CTA per SM. */
 int b200rl_gemm_f16(const void* A, const void* B, void* C, const float* bias, const void* saved, int M, int N, int K,
                     long long lda, long long ldb, long long ldc, long long ld_saved, int mn_major, int mode, int act,
-                    float alpha, int split_k, int max_ctas, int rm_C, int rm_OW, int rm_Wg, void* stream);
+                    float alpha, int split_k, int max_ctas, int rm_C, int rm_OW, int rm_Wg, const void* saved_bits,
+                    void* stream);
+/* saved_bits (MODE_F16_DACT with ReLU, optional): uint16 words, bit k of word (row*ld_saved + col)/16 set iff the saved
+ * activation element (row, col + k) > 0 -- read instead of `saved` (16x less mask traffic; conv_shift_fwd emits it). */
 /* rm_C > 0 (fp16 outputs only): output column pix*rm_C + c is stored at ((pix/rm_OW)*rm_Wg + pix%rm_OW)*rm_C + c,
  * i.e. a [.., OH, OW, C] row is scattered into a zero-bordered [.., Hg, Wg, C] grid (fc1 dgrad -> conv3's dY). */
 

@@ -894,3 +894,26 @@ def test_conv_shift_xfold_fused_uint8_source(ops, B, gather):
     assert float((G_ref - G_u8).abs().max()) <= 1e-5 * scale + 1e-3
     assert float((G_ref - G_old).abs().max()) <= 1e-5 * scale + 1e-3          # folded == un-folded wgrad
     assert torch.allclose(gb_ref, gb_u8, atol=1e-3, rtol=1e-5)
+
+
+def test_gemm_dact_bit_mask_equals_fp16_mask(ops):
+    """fc1 data gradient with the ReLU mask as 1 bit per element (as conv_shift_fwd emits it) == the same GEMM masked
+    by the fp16 activation, incl. the column remap into conv3's zero-bordered grid; M spans many tiles per CTA."""
+    torch.manual_seed(5)
+    M, N, K = 20000, 49 * 64, 512
+    A = (torch.randn(M, K, device="cuda") * 0.3).half()
+    W = (torch.randn(N, K, device="cuda") * 0.3).half()
+    saved = torch.relu(torch.randn(M, N, device="cuda")).half()
+    bits = ((saved.reshape(-1, 16) > 0).to(torch.int32) << torch.arange(16, device="cuda", dtype=torch.int32)
+            ).sum(1).to(torch.int16)
+    out_a = torch.zeros(M, 81 * 64, dtype=torch.float16, device="cuda")
+    out_b = torch.zeros_like(out_a)
+    ops.gemm(A, W, out_a, M=M, N=N, K=K, lda=K, ldb=K, ldc=81 * 64, saved=saved, ld_saved=N, mode=ops.MODE_F16_DACT,
+             act=ops.ACT_RELU, remap=(64, 7, 9))
+    ops.gemm(A, W, out_b, M=M, N=N, K=K, lda=K, ldb=K, ldc=81 * 64, saved_bits=bits, ld_saved=N, mode=ops.MODE_F16_DACT,
+             act=ops.ACT_RELU, remap=(64, 7, 9))
+    torch.cuda.synchronize()
+    assert torch.equal(out_a, out_b)
+    ref = (A[:512].float() @ W.float().t()) * (saved[:512].float() > 0)
+    grid = out_b[:512].float().view(512, 9, 9, 64)
+    assert torch.allclose(grid[:, :7, :7].reshape(512, -1), ref, atol=5e-2, rtol=5e-3)
