@@ -57,14 +57,18 @@ __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t by
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
+// try_wait suspends the warp until the phase completes or the hint expires; without a hint the default time limit is
+// short and the polling loop (YIELD / TRYWAIT / BRA) of the ~20 waiting warps took 21 % of all issued instructions in
+// the conv kernels (profiles/r2_ncu_conv_fwd.md) -- issue slots the producer and epilogue warps need.
+static constexpr uint32_t MBAR_SUSPEND_NS = 20000;
 __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
   uint32_t ok;
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
       "selp.u32 %0, 1, 0, p;\n\t}"
       : "=r"(ok)
-      : "r"(smem_u32(bar)), "r"(parity)
+      : "r"(smem_u32(bar)), "r"(parity), "r"(MBAR_SUSPEND_NS)
       : "memory");
   return ok != 0;
 }

@@ -31,10 +31,11 @@ namespace b200rl {
 
 static constexpr int SH_BM = 128;
 static constexpr int SH_THREADS = 256;             // wgrad: TMA, MMA, TMEM alloc, spare, 4 epilogue warps
-// forward: the epilogue is latency-bound per warp (a dependent chain tcgen05.ld -> math -> pack -> store of ~150
-// instructions per 16 columns at an IPC of ~0.25), so it gets SH_CG column groups of 4 warps per accumulator stage:
-// 2 stages x SH_CG groups x 4 lane quadrants
-static constexpr int SH_CG = 2;
+// forward: 2 accumulator stages x SH_CG column groups x 4 lane quadrants of epilogue warps.  Measured (ncu,
+// profiles/r2_ncu_conv_fwd.md): these kernels are bound by warp-instruction issue (epilogue + uint8 producers + barrier
+// polling = ~3400 warp instructions per 128-row tile), so a second column group only adds per-warp overhead and
+// polling warps: SH_CG = 2 was 3-6 % slower than 1 on all three layers.
+static constexpr int SH_CG = 1;
 static constexpr int SH_EPI_WARPS = 2 * SH_CG * 4;
 static constexpr int SH_FWD_THREADS = 128 + SH_EPI_WARPS * 32;
 static constexpr int SH_MAX_TAPS = 16;

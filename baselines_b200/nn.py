@@ -447,14 +447,18 @@ class Tower:
         cap, cv = self.cap, self.convs
         self.sg = []                                   # per layer: dict(Hg, Wg, Cg, k, shifts, s)
         import os
+        # the x-fold pays off in the weight-gradient kernels (-14 ms per cfg-2 update) but not in the forward ones, which
+        # are bound by warp-instruction issue and get 3 extra instructions per output element from the cross-lane sum
+        # (measured +17 ms): forward fold only on request
         xfold = os.environ.get("B200RL_NO_XFOLD", "0") != "1"
+        xfold_fwd = os.environ.get("B200RL_XFOLD_FWD", "0") == "1"
         for c in cv:
             s_, k = c.stride, c.rf // c.stride
             Hg, Wg, Cg = c.H // s_, c.W // s_, c.C * s_ * s_
             # x-fold (csrc/conv_shift.cu): the k taps of a filter row ride in the MMA's N dimension; kernels exist for
             # (k, nf, Cg) in {(2, 32, 64), (2, 64, 64), (2, 64, 128), (3, 64, 64)}
             kx = k if (xfold and (k, c.nf, Cg) in ((2, 32, 64), (2, 64, 64), (2, 64, 128), (3, 64, 64))) else 1
-            self.sg.append(dict(Hg=Hg, Wg=Wg, Cg=Cg, k=k, s=s_, kx=kx,
+            self.sg.append(dict(Hg=Hg, Wg=Wg, Cg=Cg, k=k, s=s_, kx=kx, kx_fwd=kx if xfold_fwd else 1,
                                 shifts=[a * Wg + b for a in range(k) for b in range(k)],
                                 yshifts=[a * Wg for a in range(k)]))
         c0, g0 = cv[0], self.sg[0]
@@ -478,13 +482,13 @@ class Tower:
         # data-gradient weight operands [N' = Cg, taps * nf] (tap blocks of the master weight side by side)
         self.wd = [None] + [torch.zeros(g["Cg"], g["k"] * g["k"] * c.nf, **f16) for c, g in zip(cv[1:], self.sg[1:])]
         # x-folded forward operands [kx * nf, ky * Cg]: row b*nf + n, column a*Cg + c = tap (a, b)
-        self.wfold = [torch.zeros(g["kx"] * c.nf, g["k"] * g["Cg"], **f16) if g["kx"] > 1 else None
+        self.wfold = [torch.zeros(g["kx"] * c.nf, g["k"] * g["Cg"], **f16) if g["kx_fwd"] > 1 else None
                       for c, g in zip(cv, self.sg)]
         self.flat = cv[-1].OH * cv[-1].OW * cv[-1].nf
 
     def _refresh_shift(self):
         for i, (c, g) in enumerate(zip(self.convs, self.sg)):
-            if g["kx"] > 1:
+            if g["kx_fwd"] > 1:
                 k, Cg, nf = g["k"], g["Cg"], c.nf
                 for a in range(k):
                     for b in range(k):
@@ -514,11 +518,11 @@ class Tower:
                 omap = (2, Hn * Wn * Cn, Wn * Cn, Cn, c.nf, sn)
             else:
                 omap = (0, c.OH * c.OW * c.nf, c.OW * c.nf, c.nf, 0, 0)
-            if g["kx"] > 1:
+            if g["kx_fwd"] > 1:
                 ops.conv_shift_fwd(cur, B, g["Hg"], g["Wg"], g["Cg"], self.wfold[i], g["k"] * g["Cg"], c.nf,
                                    g["yshifts"], c.OH, c.OW, self.hconv[i], omap, bias=c.b, act=c.act,
                                    tag="fwd." + c.name, u8=self._u8 if i == 0 else None, bits_out=self.hbits[i],
-                                   useful_rows=B * c.OH * c.OW, kx=g["kx"])
+                                   useful_rows=B * c.OH * c.OW, kx=g["kx_fwd"])
             else:
                 ops.conv_shift_fwd(cur, B, g["Hg"], g["Wg"], g["Cg"], c.w_fwd, c.Kp, c.nf, g["shifts"], c.OH, c.OW,
                                    self.hconv[i], omap, bias=c.b, act=c.act, tag="fwd." + c.name,

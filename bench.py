@@ -389,7 +389,7 @@ def run_ppo2(cfg, args, steps, warmup, with_profile, with_e2e, dist_ctx):
             frame_shape = tuple(cfg["ob_shape"][:-1]) + (1,)
             env_f = VecFrameStack(SyntheticVecEnv(N, frame_shape, np.uint8, seed=rank, **env_kw), 4)
             runner_f = Runner(env=env_f, model=model, nsteps=T, gamma=cfg["gamma"], lam=cfg["lam"])
-            ms_f, _ = timed(model, runner_f, max(1, steps), 1, read_back=True)
+            ms_f, _ = timed(model, runner_f, max(1, steps), 3, read_back=True)   # eager pass, capture pass, replay pass
             e2e = {"value": world * nbatch / (ms_f / 1000.0), "unit": unit, "ms_per_step": ms_f,
                    "h2d_bytes_per_step": T * N * (ob_bytes // 4 + 1) + common_h2d, "d2h_bytes_per_step": d2h,
                    "input": "VecFrameStack(host VecEnv of 84x84x1 frames, 4): new frames uploaded, stack kept in HBM"}
@@ -398,7 +398,7 @@ def run_ppo2(cfg, args, steps, warmup, with_profile, with_e2e, dist_ctx):
         # (b) a host VecEnv that hands out full observations: every one of them is uploaded
         env_h = SyntheticVecEnv(N, cfg["ob_shape"], ob_dtype, seed=rank, **env_kw)
         runner_h = Runner(env=env_h, model=model, nsteps=T, gamma=cfg["gamma"], lam=cfg["lam"])
-        ms_e2e, _ = timed(model, runner_h, max(1, steps), 1, read_back=True)
+        ms_e2e, _ = timed(model, runner_h, max(1, steps), 3, read_back=True)
         full = {"value": world * nbatch / (ms_e2e / 1000.0), "unit": unit, "ms_per_step": ms_e2e,
                 "h2d_bytes_per_step": (T + 1) * N * ob_bytes + common_h2d, "d2h_bytes_per_step": d2h,
                 "input": "host VecEnv handing out full observations: all of them uploaded"}

@@ -567,8 +567,8 @@ def test_cuda_graph_replay_equals_eager_launch_sequence():
     case = CASES["cnn_cat"]
     T, N, nmb, nep = 8, 64, 2, 2
     out = {}
-    for mode in ("eager", "graphs"):
-        if mode == "eager":
+    for mode in ("eager", "eager2", "graphs"):
+        if mode.startswith("eager"):
             os.environ["B200RL_NO_GRAPHS"] = "1"
         try:
             env, model, _ = _mk(nenv=N, nsteps=T, nminibatches=nmb, **case)
@@ -589,11 +589,18 @@ def test_cuda_graph_replay_equals_eager_launch_sequence():
             os.environ.pop("B200RL_NO_GRAPHS", None)
     assert out["eager"][3] == 0 and out["graphs"][3] >= 2 * (T + 1) + nmb * nep     # updates 2 and 3 ran from graphs
     assert out["eager"][4] == out["graphs"][4] == 3 * nmb * nep
-    for a, b in zip(out["eager"][0], out["graphs"][0]):
-        assert np.array_equal(a, b)
-    assert np.allclose(out["eager"][2], out["graphs"][2], atol=1e-6)
-    for k in out["eager"][1]:
-        assert np.allclose(out["eager"][1][k], out["graphs"][1][k], atol=2e-6), k
+    # update 1 starts from identical parameters: its rollout is bit-identical.  Later rollouts differ by what the
+    # float-atomic weight gradients (run-to-run reduction order) leave in the parameters -- Adam's first steps turn a
+    # 1e-7 difference in a near-zero gradient into a full +-lr step -- so the yardstick for "same computation" is the
+    # spread between two EAGER runs.
+    assert np.array_equal(out["eager"][0][0], out["graphs"][0][0])
+    spread = max(float(np.abs(out["eager"][1][k] - out["eager2"][1][k]).max()) for k in out["eager"][1])
+    diff = max(float(np.abs(out["eager"][1][k] - out["graphs"][1][k]).max()) for k in out["eager"][1])
+    print(f"params: eager-vs-eager spread {spread:.2e}, graphs-vs-eager {diff:.2e}")
+    assert diff <= 4 * spread + 1e-6, (diff, spread)
+    sspread = float(np.abs(out["eager"][2] - out["eager2"][2]).max())
+    sdiff = float(np.abs(out["eager"][2] - out["graphs"][2]).max())
+    assert sdiff <= 4 * sspread + 1e-5, (sdiff, sspread)
 
 
 def test_dqn_graph_replay_equals_eager():
@@ -602,8 +609,8 @@ def test_dqn_graph_replay_equals_eager():
     from baselines_b200.deepq.build_graph import DQNModel, build_act
     from baselines_b200.deepq.replay_buffer import PrioritizedReplayBuffer
     res = {}
-    for mode in ("eager", "graphs"):
-        if mode == "eager":
+    for mode in ("eager", "eager2", "graphs"):
+        if mode.startswith("eager"):
             os.environ["B200RL_NO_GRAPHS"] = "1"
         try:
             np.random.seed(0)
@@ -629,9 +636,10 @@ def test_dqn_graph_replay_equals_eager():
         finally:
             os.environ.pop("B200RL_NO_GRAPHS", None)
     assert res["eager"][3] == 0 and res["graphs"][3] >= 6
-    for a, b in zip(res["eager"][1], res["graphs"][1]):
-        assert np.array_equal(a, b)
-    for a, b in zip(res["eager"][0], res["graphs"][0]):
-        assert np.allclose(a, b, atol=1e-4)
-    for k in res["eager"][2]:
-        assert np.allclose(res["eager"][2][k], res["graphs"][2][k], atol=1e-5), k
+    assert np.array_equal(res["eager"][1][0], res["graphs"][1][0])          # first action: identical parameters
+    assert np.allclose(res["eager"][0][0], res["graphs"][0][0], atol=1e-5)  # first TD errors likewise
+    # later steps: float-atomic gradient order + Adam's early +-lr steps; compare against the eager-vs-eager spread
+    spread = max(float(np.abs(res["eager"][2][k] - res["eager2"][2][k]).max()) for k in res["eager"][2])
+    diff = max(float(np.abs(res["eager"][2][k] - res["graphs"][2][k]).max()) for k in res["eager"][2])
+    print(f"dqn params: eager-vs-eager spread {spread:.2e}, graphs-vs-eager {diff:.2e}")
+    assert diff <= 4 * spread + 1e-6, (diff, spread)
