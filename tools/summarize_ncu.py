@@ -63,5 +63,95 @@ def full(src, dst):
             f.write(f"| {n} | " + " | ".join(vals) + " |\n")
 
 
-if __name__ == "__main__":
+if __name__ == "__main__" and sys.argv[1] in ("launches", "full"):
     {"launches": launches, "full": full}[sys.argv[1]](sys.argv[2], sys.argv[3])
+
+
+# ------------------------------------------------------------------------------------------------ round 2 additions
+def _source_kernels(rep):
+    out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--print-source", "sass"],
+                         capture_output=True, text=True).stdout
+    kern, cur = [], None
+    for r in csv.reader(out.splitlines()):
+        if r and r[0] == "Kernel Name":
+            cur = {"name": r[1], "rows": []}
+            kern.append(cur)
+        elif cur is not None:
+            cur["rows"].append(r)
+    return kern
+
+
+def roles(src, dst, samples=None):
+    """Per captured launch: headline metrics (raw page) + where the issued warp instructions go (source page): static
+    instructions bucketed by execution count separate the warp roles (epilogue / producers / MMA issuer) and expose
+    barrier-polling loops; plus the stall-reason mix."""
+    raw = subprocess.run(["ncu", "-i", src, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(raw.splitlines()))
+    H = rows[0]
+    keep = [k for k in KEEP + ["sm__cycles_elapsed.max", "smsp__issue_active.avg.pct_of_peak_sustained_active",
+                               "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum.pct_of_peak_sustained_elapsed"] if k in H]
+    kern = _source_kernels(src)
+    with open(dst, "w") as f:
+        f.write(f"# ncu --set full --import-source on: {src}\n\n"
+                "Times under ncu are cold-cache and serialised; bench.py's CUDA-event numbers are the reported ones.\n")
+        for n, r in enumerate(rows[2:]):
+            name = r[H.index("Kernel Name")].split("(")[0].replace("void ", "").replace("b200rl::", "")
+            f.write(f"\n## launch {n}: `{name}`\n\n| metric | value |\n|---|---|\n")
+            for k in keep:
+                f.write(f"| {k} | {r[H.index(k)]} |\n")
+            if n < len(kern):
+                k = kern[n]
+                HH = k["rows"][0]
+                ie, ism, isrc = HH.index("Instructions Executed"), HH.index("# Samples"), HH.index("Source")
+                data = [(rr[isrc], int(rr[ie]), int(rr[ism] or 0)) for rr in k["rows"][1:] if len(rr) > ie and rr[ie].isdigit()]
+                tot, tots = sum(d[1] for d in data) or 1, sum(d[2] for d in data) or 1
+                b = collections.OrderedDict()
+                for s_, e, sm in data:
+                    if e:
+                        x = b.setdefault(float(f"{e:.2g}"), [0, 0, 0, ""])
+                        x[0] += 1; x[1] += e; x[2] += sm
+                        if "TRYWAIT" in s_ or "BAR.SYNC" in s_:
+                            x[3] = "barrier polling / sync"
+                f.write(f"\nwarp instructions executed: {tot}; pc samples: {tots}\n\n"
+                        "| executions per static instruction | static instrs | executed | share | pc samples | note |\n"
+                        "|---:|---:|---:|---:|---:|---|\n")
+                for key, (cnt, e, sm, note) in sorted(b.items(), key=lambda kv: -kv[1][1])[:8]:
+                    note = note if cnt <= 6 else "warp-role body (epilogue / producer / MMA issuer)"
+                    f.write(f"| ~{key:.0f} | {cnt} | {e} | {100 * e / tot:.1f}% | {100 * sm / tots:.1f}% | {note} |\n")
+                st = [h for h in HH if h.startswith("stall_") and "Not Issued" not in h]
+                acc = {h: 0 for h in st}
+                for rr in k["rows"][1:]:
+                    for h in st:
+                        i = HH.index(h)
+                        if len(rr) > i and rr[i].isdigit():
+                            acc[h] += int(rr[i])
+                ts = sum(acc.values()) or 1
+                f.write("\nstall reasons (pc sampling): " + ", ".join(f"{h[6:]} {100 * v / ts:.0f}%" for h, v in
+                                                                       sorted(acc.items(), key=lambda kv: -kv[1])[:7]) + "\n")
+
+
+def traffic(src, dst, samples):
+    """profiles/r2_traffic.json: DRAM bytes per sample of every captured kernel (dram__bytes_read + write of an
+    `ncu --set full` capture whose launches processed `samples` samples each); bench.py scales it to its launch size."""
+    import json
+    import os
+    raw = subprocess.run(["ncu", "-i", src, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(raw.splitlines()))
+    H, U = rows[0], rows[1]
+    ir, iw, ik = H.index("dram__bytes_read.sum"), H.index("dram__bytes_write.sum"), H.index("Kernel Name")
+    scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+    out = json.load(open(dst)) if os.path.exists(dst) else {}
+    for r in rows[2:]:
+        name = r[ik].split("(")[0].replace("void ", "").replace("b200rl::", "")
+        b = float(r[ir].replace(",", "")) * scale.get(U[ir], 1.0) + float(r[iw].replace(",", "")) * scale.get(U[iw], 1.0)
+        out[name] = {"dram_bytes_per_sample": b / float(samples), "capture_samples": int(samples),
+                     "src": f"{os.path.basename(src)} (ncu --set full --clock-control none)"}
+    json.dump(out, open(dst, "w"), indent=1, sort_keys=True)
+
+
+if __name__ == "__main__" and len(sys.argv) > 1 and sys.argv[1] in ("roles", "traffic"):
+    if sys.argv[1] == "roles":
+        roles(sys.argv[2], sys.argv[3])
+    else:
+        traffic(sys.argv[2], sys.argv[3], sys.argv[4])
+    sys.exit(0)
