@@ -29,6 +29,7 @@ SIGNATURES = {
     "b200rl_cat_step": [_p, _ll, _i, _p, _ll, _p, _ull, _ull, _p, _p, _p, _p, _ll, _p],
     "b200rl_gauss_step": [_p, _ll, _p, _i, _p, _ll, _p, _ull, _ull, _p, _p, _p, _p, _ll, _p],
     "b200rl_set_scalars": [_p, _i, _f, _f, _f, _f, _p],
+    "b200rl_shuffle_indices": [_p, _ll, _ull, _ll, _ll, _p],
     "b200rl_counter_add": [_p, _ull, _p],
     "b200rl_adv_stats": [_p, _p, _p, _ll, _p, _p],
     "b200rl_cat_loss": [_p, _ll, _i, _p, _ll, _p, _p, _p, _p, _p, _p, _f, _f, _f, _p, _ll, _p, _ll, _p, _ll, _p, _p],

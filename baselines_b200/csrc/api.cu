@@ -40,6 +40,7 @@ int gauss_step_impl(const float*, long long, const float*, int, const float*, lo
                     unsigned long long, unsigned long long, const unsigned long long*, float*, float*, float*,
                     long long, cudaStream_t);
 int set_scalars_impl(float*, int, float, float, float, float, cudaStream_t);
+int shuffle_indices_impl(long long*, long long, unsigned long long, long long, long long, cudaStream_t);
 int counter_add_impl(unsigned long long*, unsigned long long, cudaStream_t);
 int adv_stats_impl(const float*, const float*, const long long*, long long, double*, cudaStream_t);
 int cat_loss_impl(const float*, long long, int, const float*, long long, const long long*, const long long*,
@@ -150,6 +151,9 @@ int b200rl_cat_step(const float* logits, long long ld, int nA, const float* vpre
                     long long B, void* stream) {
   return cat_step_impl(logits, ld, nA, vpred, ldv, uniforms, seed, offset, offset_dev, actions, values, neglogp, B,
                        S(stream));
+}
+int b200rl_shuffle_indices(long long* out, long long n, unsigned long long key, long long T, long long N, void* stream) {
+  return shuffle_indices_impl(out, n, key, T, N, S(stream));
 }
 int b200rl_set_scalars(float* dst, int n, float a, float b, float c, float d, void* stream) {
   return set_scalars_impl(dst, n, a, b, c, d, S(stream));

@@ -463,7 +463,7 @@ conv_shift_fwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_cons
       }
     } else {
       // 16-column chunks handled together (loads in flight); the masked data gradient also holds the mask words
-      constexpr int G = DACT ? ((NCG >= 32) ? 2 : 1) : ((NCG >= 64) ? 4 : NCG / 16);
+      constexpr int G = (DACT && SH_CG > 1) ? ((NCG >= 32) ? 2 : 1) : ((NCG >= 64) ? 4 : NCG / 16);
       for (int tile = blockIdx.x + as * (int)gridDim.x; tile < p.num_tiles; tile += 2 * (int)gridDim.x) {
         const uint32_t m = (uint32_t)tile * SH_BM + ew * 32 + lane;       // M < 2^31 (checked on the host)
         const uint32_t t2 = p.fwg.div(m);

@@ -35,7 +35,7 @@ static constexpr int UMMA_K = 16;
 // TMA, MMA, TMEM alloc, spare + epilogue warps: 2 accumulator stages x GEMM_CG column groups x 4 lane quadrants.  The
 // epilogue is a latency-bound dependent chain per warp (tcgen05.ld -> math -> pack -> store), so the columns of a tile
 // are split over GEMM_CG warps per quadrant.
-static constexpr int GEMM_CG = 1;      // (2 gave no gain on the fc1 GEMMs and doubles the polling warps)
+static constexpr int GEMM_CG = 2;      // measured: fc1 data gradient 10.2 ms -> 8.3 ms per cfg-2 update, fwd / wgrad unchanged
 static constexpr int NUM_THREADS = 128 + 2 * GEMM_CG * 128;
 
 

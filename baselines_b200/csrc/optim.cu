@@ -215,6 +215,53 @@ int counter_add_impl(unsigned long long* ctr, unsigned long long inc, cudaStream
   return check_launch("counter_add_kernel");
 }
 
+// Minibatch shuffle on the device (replaces np.random.shuffle(inds) of ppo2/ppo2.py:160 + the index arithmetic of
+// sf01, ppo2/runner.py:69-74): out[i] = buffer offset of the pi(i)-th sample, pi a keyed pseudo-random BIJECTION of
+// [0, n) -- a 6-round Feistel network over the next power of four with cycle walking, the construction of
+// thrust::shuffle -- so no permutation array is generated, sorted or uploaded.  Env-major flat index j = e*T + t maps
+// to buffer offset t*N + e.  (The host MT19937 shuffle stays available for seed-for-seed parity runs.)
+__device__ __forceinline__ uint32_t feistel_round(uint32_t x, uint32_t k) {
+  x ^= k;
+  x *= 0x9E3779B1u;
+  x ^= x >> 15;
+  x *= 0x85EBCA77u;
+  x ^= x >> 13;
+  return x;
+}
+__global__ void __launch_bounds__(256)
+shuffle_indices_kernel(long long* __restrict__ out, long long n, unsigned long long key, int half_bits, long long T,
+                       long long N) {
+  const uint32_t mask = (1u << half_bits) - 1u;
+  uint32_t rk[6];
+#pragma unroll
+  for (int r = 0; r < 6; ++r) rk[r] = (uint32_t)(key >> (8 * r)) * 0x9E3779B1u + (uint32_t)(key >> 32) + 0x7F4A7C15u * (r + 1);
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    unsigned long long x = (unsigned long long)i;
+    do {                                             // cycle walking: re-encrypt until the value lands in [0, n)
+      uint32_t l = (uint32_t)(x >> half_bits) & mask, r = (uint32_t)x & mask;
+#pragma unroll
+      for (int k = 0; k < 6; ++k) {
+        const uint32_t t = l ^ (feistel_round(r, rk[k]) & mask);
+        l = r;
+        r = t;
+      }
+      x = ((unsigned long long)l << half_bits) | r;
+    } while (x >= (unsigned long long)n);
+    const long long j = (long long)x;
+    out[i] = (T > 0) ? (j % T) * N + j / T : j;
+  }
+}
+
+int shuffle_indices_impl(long long* out, long long n, unsigned long long key, long long T, long long N,
+                         cudaStream_t stream) {
+  B200RL_REQUIRE(out && n > 0 && n < (1LL << 40), "shuffle_indices: bad args");
+  B200RL_REQUIRE(T == 0 || T * N == n, "shuffle_indices: T*N must equal n");
+  int half_bits = 1;
+  while ((1LL << (2 * half_bits)) < n) ++half_bits;  // domain 4^half_bits >= n: at most 4x the range (<= 4 walks expected)
+  shuffle_indices_kernel<<<grid_for(n, 256, 8), 256, 0, stream>>>(out, n, key, half_bits, T, N);
+  return check_launch("shuffle_indices_kernel");
+}
+
 int clip_accumulate_impl(const float* g, float* acc, long long n, float clip, float weight, const double* sumsq,
                          cudaStream_t stream) {
   B200RL_REQUIRE(g && acc && n > 0, "clip_accumulate: bad args");

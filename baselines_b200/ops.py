@@ -221,6 +221,13 @@ def set_scalars(dst, *vals):
     _lib.call("b200rl_set_scalars", _ptr(dst), len(vals), v[0], v[1], v[2], v[3], _stream())
 
 
+def shuffle_indices(out, n, key, T=0, N=0):
+    """out[:n] = buffer offsets of a keyed pseudo-random permutation of the n rollout samples (ppo2.py:160)."""
+    _chk(out, torch.int64, "out")
+    _lib.call("b200rl_shuffle_indices", _ptr(out), int(n), int(key) & 0xFFFFFFFFFFFFFFFF, int(T), int(N), _stream(),
+              label="shuffle_indices", nbytes=8.0 * n)
+
+
 def counter_add(ctr, inc=1):
     _chk(ctr, torch.int64, "ctr")
     _lib.call("b200rl_counter_add", _ptr(ctr), int(inc), _stream())

@@ -42,6 +42,12 @@ class Rollout:
         a = getattr(self, name)
         return a.view((self.T * self.N,) + tuple(a.shape[2:]))
 
+    def shuffle_buffer(self):
+        """Device home of the current epoch's shuffled sample offsets (ops.shuffle_indices)."""
+        if self._arange is None:
+            self._arange = torch.empty(self.T * self.N, dtype=torch.int64, device=self.device)
+        return self._arange
+
     def src_index(self, inds):
         """env-major flat indices (device int64) -> buffer offsets."""
         return (inds % self.T) * self.N + torch.div(inds, self.T, rounding_mode="floor")

@@ -329,7 +329,8 @@ def run_ppo2(cfg, args, steps, warmup, with_profile, with_e2e, dist_ctx):
 
     def update(model, runner):
         ro, _ = runner.run_device()
-        st = run_epochs(model, ro, cfg["lr"], cfg["cliprange"], nbatch, nbatch_train, cfg["noptepochs"], dev)
+        st = run_epochs(model, ro, cfg["lr"], cfg["cliprange"], nbatch, nbatch_train, cfg["noptepochs"], dev,
+                        shuffle=args.shuffle)
         return torch.stack(st).mean(dim=0)
 
     def timed(model, runner, steps, warmup, read_back, profile=False):
@@ -517,6 +518,8 @@ def main():
     ap.add_argument("--config", default="cfg2", choices=sorted(CFGS))
     ap.add_argument("--nenvs", type=int, default=None, help="envs per GPU (default: the BASELINE config)")
     ap.add_argument("--ref-envs", type=int, default=None, help="envs in the bounded CPU-reference sample")
+    ap.add_argument("--shuffle", default="device", choices=["device", "host"],
+                    help="minibatch permutation: keyed bijection kernel (default) or the reference's host np.random.shuffle")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-profile", action="store_true", help="skip the per-kernel CUDA-event profile pass")
@@ -640,7 +643,9 @@ def main():
                   "l2": "inputs larger than L2 (rollout observations %.1f GB, every minibatch streams %.2f GB)" %
                         (N * T * np.prod(cfg["ob_shape"]) * (1 if cfg["ob_dtype"] == "uint8" else 4) / 1e9,
                          N * T * np.prod(cfg["ob_shape"]) * (1 if cfg["ob_dtype"] == "uint8" else 4) / cfg["nminibatches"] / 1e9),
-                  "train_chunk": res["chunk"]}
+                  "train_chunk": res["chunk"],
+                  "shuffle": args.shuffle + (" (keyed Feistel bijection evaluated on the device, ops.shuffle_indices)"
+                                             if args.shuffle == "device" else " (np.random.shuffle, indices uploaded)")}
         dtype = "f16 operands / f32 accumulate (GAE f64 carry)"
     else:
         tf_step = None

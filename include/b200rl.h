@@ -134,6 +134,10 @@ int b200rl_gauss_step(const float* mean, long long ld, const float* logstd, int 
  *   override the by-value argument; set_scalars writes up to 4 floats from its own kernel arguments (no host staging
  *   buffer to race with); counter_add advances the sampler's stream position after each acting pass. */
 int b200rl_set_scalars(float* dst, int n, float a, float b, float c, float d, void* stream);
+/* Device minibatch shuffle: ppo2/ppo2.py:160 (np.random.shuffle(inds)) + the env-major -> buffer index map of sf01
+ * (ppo2/runner.py:69-74).  out[i] = offset of sample pi(i), pi = keyed Feistel bijection of [0, n) with cycle walking;
+ * T > 0: flat index j = e*T + t -> t*N + e (T*N == n); T == 0: out[i] = pi(i). */
+int b200rl_shuffle_indices(long long* out, long long n, unsigned long long key, long long T, long long N, void* stream);
 int b200rl_counter_add(unsigned long long* ctr, unsigned long long inc, void* stream);
 
 /* per-minibatch advantage moments: ppo2/model.py:136-139.  out = {mean, std} (float64). */

@@ -917,3 +917,32 @@ def test_gemm_dact_bit_mask_equals_fp16_mask(ops):
     ref = (A[:512].float() @ W.float().t()) * (saved[:512].float() > 0)
     grid = out_b[:512].float().view(512, 9, 9, 64)
     assert torch.allclose(grid[:, :7, :7].reshape(512, -1), ref, atol=5e-2, rtol=5e-3)
+
+
+@pytest.mark.parametrize("n,T,N", [(1, 0, 0), (7, 0, 0), (4096, 0, 0), (524288, 128, 4096), (100003, 0, 0),
+                                   (8 * 1024 * 1024 + 5, 0, 0)])
+def test_shuffle_indices_is_a_keyed_permutation(ops, n, T, N):
+    """ops.shuffle_indices (ppo2.py:160 on the device): a bijection of [0, n) for any n, different for different keys,
+    composed with the env-major -> buffer offset map of sf01 when (T, N) are given; positions look uniform."""
+    out1 = torch.empty(n, dtype=torch.int64, device="cuda")
+    out2 = torch.empty(n, dtype=torch.int64, device="cuda")
+    ops.shuffle_indices(out1, n, 0x1234567890ABCDEF, T, N)
+    ops.shuffle_indices(out2, n, 0x0FEDCBA987654321, T, N)
+    torch.cuda.synchronize()
+    assert torch.equal(torch.sort(out1).values, torch.arange(n, device="cuda"))
+    assert torch.equal(torch.sort(out2).values, torch.arange(n, device="cuda"))
+    if n >= 4096:
+        assert float((out1 == out2).float().mean()) < 0.01
+        # a uniform permutation has E[pi(i)] = (n-1)/2 over any block of positions; |corr(i, pi(i))| small
+        x = out1.double()
+        if T:
+            e, t = x % N, torch.div(x, N, rounding_mode="floor")           # undo offset t*N + e -> flat e*T + t
+            x = e * T + t
+        i = torch.arange(n, device="cuda", dtype=torch.float64)
+        corr = float(((x - x.mean()) * (i - i.mean())).mean() / (x.std() * i.std()))
+        assert abs(corr) < 0.02, corr
+        first = x[: n // 16].mean() / ((n - 1) / 2.0)
+        assert abs(float(first) - 1.0) < 0.05
+    out3 = torch.empty(n, dtype=torch.int64, device="cuda")
+    ops.shuffle_indices(out3, n, 0x1234567890ABCDEF, T, N)
+    assert torch.equal(out1, out3)                                         # reproducible given the key
