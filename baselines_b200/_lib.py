@@ -40,6 +40,7 @@ SIGNATURES = {
     "b200rl_clip_adam": [_p, _p, _p, _p, _ll, _f, _f, _f, _f, _f, _p, _p, _i, _p, _p],
     "b200rl_clip_accumulate": [_p, _p, _ll, _f, _f, _p, _p],
     "b200rl_cast_transpose": [_p, _i, _i, _p, _ll, _p, _ll, _f, _p],
+    "b200rl_cast_transpose_batch": [_p, _i, _i, _i, _p],
     "b200rl_cast_f32_f16": [_p, _p, _ll, _i, _ll, _ll, _f, _p],
     "b200rl_obs_encode": [_p, _p, _ll, _i, _i, _i, _p, _p, _f, _f, _i, _p, _p],
     "b200rl_tree_set": [_p, _p, _ll, _p, _p, _i, _p],

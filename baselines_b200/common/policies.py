@@ -185,7 +185,23 @@ class PolicyNet:
             self.head_pi.gb.zero_()
 
     def refresh(self):
-        """Re-derive the fp16 operand copies from the fp32 master weights (after init / Adam / load)."""
+        """Re-derive the fp16 operand copies from the fp32 master weights (after init / Adam / load): one batched
+        launch (ops.CastPlan) for every cast / transpose, plus the few operand kernels that are not plain casts."""
+        if getattr(self, "_cast_plan", None) is None:
+            self._cast_plan = ops.CastPlan(self._refresh_layers, self.device)
+        else:
+            self._refresh_other()
+        self._cast_plan.run()
+
+    def _refresh_other(self):
+        """Operand refreshes that are not cast_transpose jobs (they ran eagerly while the plan was recorded)."""
+        for t in (self.tower_pi, self.tower_vf):
+            if t is not None:
+                for c in t.convs:
+                    if c.wdg is not None:
+                        ops.dgrad_weights(c.w, c.wdg, c.rf, c.rf, c.C, c.nf, c.stride, c.ld_wdg)
+
+    def _refresh_layers(self):
         self.tower_pi.refresh()
         if self.tower_vf:
             self.tower_vf.refresh()

@@ -56,6 +56,7 @@ int clip_adam_impl(float*, const float*, float*, float*, long long, float, float
 int clip_accumulate_impl(const float*, float*, long long, float, float, const double*, cudaStream_t);
 int cast_transpose_impl(const float*, int, int, void*, long long, void*, long long, float, cudaStream_t);
 int cast_f32_f16_impl(const float*, void*, long long, int, long long, long long, float, cudaStream_t);
+int cast_transpose_batch_impl(const void*, int, int, int, cudaStream_t);
 int obs_encode_impl(const float*, const long long*, long long, int, int, int, const float*, const float*, float, float,
                     int, void*, cudaStream_t);
 int tree_set_impl(double*, double*, long long, const long long*, const double*, int, cudaStream_t);
@@ -207,6 +208,9 @@ int b200rl_clip_accumulate(const float* g, float* acc, long long n, float clip, 
 int b200rl_cast_transpose(const float* src, int R, int C, void* dst, long long ld_dst, void* dstT, long long ld_t,
                           float scale, void* stream) {
   return cast_transpose_impl(src, R, C, dst, ld_dst, dstT, ld_t, scale, S(stream));
+}
+int b200rl_cast_transpose_batch(const void* jobs, int njobs, int max_rows, int max_cols, void* stream) {
+  return cast_transpose_batch_impl(jobs, njobs, max_rows, max_cols, S(stream));
 }
 int b200rl_cast_f32_f16(const float* src, void* dst, long long rows, int cols, long long ld_src, long long ld_dst,
                         float scale, void* stream) {

@@ -144,6 +144,43 @@ cast_f32_f16_kernel(const float* __restrict__ src, __half* __restrict__ dst, lon
   }
 }
 
+// All operand refreshes of a network in ONE launch: job j of the table is a cast_transpose (blockIdx.z = j; blocks
+// outside a job's tile range exit).  One PPO2 minibatch used to issue 18 of these launches (cfg-2), 8 per tower at
+// cfg-3 and 23 per deepq step -- each a 4-10 us kernel.
+struct CastJob {
+  const float* src;
+  __half* dst;
+  __half* dstT;
+  long long ld_dst, ld_t;
+  int R, C;
+  float scale;
+  int pad;
+};
+__global__ void __launch_bounds__(256)
+cast_transpose_batch_kernel(const CastJob* __restrict__ jobs) {
+  const CastJob j = jobs[blockIdx.z];
+  const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
+  if (c0 >= j.C || r0 >= j.R) return;
+  __shared__ float tile[32][33];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  for (int i = ty; i < 32; i += 8) {
+    const int r = r0 + i, c = c0 + tx;
+    float x = 0.0f;
+    if (r < j.R && c < j.C) {
+      x = j.src[(long long)r * j.C + c] * j.scale;
+      if (j.dst) j.dst[(long long)r * j.ld_dst + c] = __float2half_rn(x);
+    }
+    tile[i][tx] = x;
+  }
+  __syncthreads();
+  if (j.dstT) {
+    for (int i = ty; i < 32; i += 8) {
+      const int c = c0 + i, r = r0 + tx;
+      if (r < j.R && c < j.C) j.dstT[(long long)c * j.ld_t + r] = __float2half_rn(tile[tx][i]);
+    }
+  }
+}
+
 // Weight operand of the implicit-GEMM data gradient of a strided convolution ("pixel shuffle" form):
 //   out[(py, px, c), (a', b', co)] = W[s*(An-1-a') + py, s*(An-1-b') + px, c, co]   (0 when outside the filter)
 // with W in HWIO [R, S, Cin, Cout] fp32, An = ceil(R/s); out is fp16 [s*s*Cin, An*An*Cout] (row pitch ld).
@@ -277,6 +314,14 @@ int cast_transpose_impl(const float* src, int R, int C, void* dst, long long ld_
   cast_transpose_kernel<<<grid, 256, 0, stream>>>(src, R, C, reinterpret_cast<__half*>(dst), ld_dst,
                                                   reinterpret_cast<__half*>(dstT), ld_t, scale);
   return check_launch("cast_transpose_kernel");
+}
+
+int cast_transpose_batch_impl(const void* jobs, int njobs, int max_rows, int max_cols, cudaStream_t stream) {
+  B200RL_REQUIRE(jobs && njobs > 0 && njobs <= 65535 && max_rows > 0 && max_cols > 0, "cast_transpose_batch: bad args");
+  static_assert(sizeof(CastJob) == 56, "CastJob layout is part of the C ABI (see include/b200rl.h)");
+  dim3 grid(ceil_div(max_cols, 32), ceil_div(max_rows, 32), njobs);
+  cast_transpose_batch_kernel<<<grid, 256, 0, stream>>>(reinterpret_cast<const CastJob*>(jobs));
+  return check_launch("cast_transpose_batch_kernel");
 }
 
 int dgrad_weights_impl(const float* w, void* out, int R, int S, int Cin, int Cout, int s, long long ld,

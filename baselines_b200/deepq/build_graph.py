@@ -84,6 +84,16 @@ class QNet:
         self.dout = torch.zeros(cap, self.ld_dout, **f16)
 
     def refresh(self):
+        """fp16 operand copies of every layer in one batched launch (ops.CastPlan)."""
+        if getattr(self, "_cast_plan", None) is None:
+            self._cast_plan = ops.CastPlan(self._refresh_layers, self.device)
+        else:
+            for c in self.trunk.convs:
+                if c.wdg is not None:
+                    ops.dgrad_weights(c.w, c.wdg, c.rf, c.rf, c.C, c.nf, c.stride, c.ld_wdg)
+        self._cast_plan.run()
+
+    def _refresh_layers(self):
         self.trunk.refresh()
         for si, layers in enumerate(self.streams):
             for l in layers:

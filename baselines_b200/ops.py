@@ -284,10 +284,48 @@ def clip_accumulate(g, acc, clip, weight, sumsq_buf):
               _ptr(sumsq_buf), _stream(), label="clip_accumulate", nbytes=12.0 * g.numel())
 
 
+_cast_recording = None      # list of jobs while a CastPlan is being recorded
+
+
 def cast_transpose(src, R, C, dst, ld_dst, dstT, ld_t, scale=1.0):
     _chk(src, torch.float32, "src")
+    if _cast_recording is not None:
+        _cast_recording.append((src, int(R), int(C), dst, int(ld_dst), dstT, int(ld_t), float(scale)))
+        return
     _lib.call("b200rl_cast_transpose", _ptr(src), int(R), int(C), _ptr(dst), int(ld_dst), _ptr(dstT), int(ld_t),
               float(scale), _stream())
+
+
+class CastPlan:
+    """The fp16 operand refresh of a whole network (every cast_transpose its layers issue) as ONE launch: the calls are
+    recorded once into a device table of jobs (pointers are fixed for the life of the network)."""
+
+    def __init__(self, fn, device):
+        global _cast_recording
+        import numpy as np
+        _cast_recording = []
+        try:
+            fn()
+            jobs = _cast_recording
+        finally:
+            _cast_recording = None
+        self.n = len(jobs)
+        self.keep = jobs                                   # keeps the tensors (and their storage) alive
+        rec = np.zeros(max(self.n, 1), dtype=np.dtype([("src", "<u8"), ("dst", "<u8"), ("dstT", "<u8"), ("ld_dst", "<i8"),
+                                                        ("ld_t", "<i8"), ("R", "<i4"), ("C", "<i4"), ("scale", "<f4"),
+                                                        ("pad", "<i4")]))
+        assert rec.dtype.itemsize == 56
+        for i, (src, Rr, Cc, dst, ld_dst, dstT, ld_t, scale) in enumerate(jobs):
+            rec[i] = (src.data_ptr(), 0 if dst is None else dst.data_ptr(), 0 if dstT is None else dstT.data_ptr(),
+                      ld_dst, ld_t, Rr, Cc, scale, 0)
+        self.table = torch.from_numpy(rec.view(np.uint8).copy()).to(device)
+        self.max_r = max([j[1] for j in jobs], default=1)
+        self.max_c = max([j[2] for j in jobs], default=1)
+
+    def run(self):
+        if self.n:
+            _lib.call("b200rl_cast_transpose_batch", _ptr(self.table), self.n, self.max_r, self.max_c, _stream(),
+                      label="cast_transpose_batch")
 
 
 def cast_f32_f16(src, dst, rows, cols, ld_src, ld_dst, scale=1.0):

@@ -171,6 +171,10 @@ int b200rl_clip_accumulate(const float* g, float* acc, long long n, float clip, 
                            void* stream);
 int b200rl_cast_transpose(const float* src, int R, int C, void* dst, long long ld_dst, void* dstT, long long ld_t,
                           float scale, void* stream);
+/* njobs cast_transpose operations in one launch.  jobs: device array of 56-byte records
+ *   { const float* src; __half* dst; __half* dstT; long long ld_dst, ld_t; int R, C; float scale; int pad; }
+ * (dst / dstT may be NULL); max_rows / max_cols: the largest R / C in the table. */
+int b200rl_cast_transpose_batch(const void* jobs, int njobs, int max_rows, int max_cols, void* stream);
 int b200rl_cast_f32_f16(const float* src, void* dst, long long rows, int cols, long long ld_src, long long ld_dst,
                         float scale, void* stream);
 
