@@ -99,8 +99,9 @@ def roles(src, dst, samples=None):
             f.write(f"\n## launch {n}: `{name}`\n\n| metric | value |\n|---|---|\n")
             for k in keep:
                 f.write(f"| {k} | {r[H.index(k)]} |\n")
-            if n < len(kern):
-                k = kern[n]
+            norm = lambda z: z.replace("(int)", "").replace("(bool)", "").split("(")[0].replace("void ", "").replace("b200rl::", "")
+            k = next((kk for kk in kern if norm(kk["name"]) == norm(name) and len(kk["rows"]) > 2), None)
+            if k is not None:
                 HH = k["rows"][0]
                 ie, ism, isrc = HH.index("Instructions Executed"), HH.index("# Samples"), HH.index("Source")
                 data = [(rr[isrc], int(rr[ie]), int(rr[ism] or 0)) for rr in k["rows"][1:] if len(rr) > ie and rr[ie].isdigit()]
