@@ -213,6 +213,41 @@ colsum_kernel(const __half* __restrict__ dz, float* __restrict__ db, long long r
   }
 }
 
+// same sum with 16-byte loads: thread = (row group, 8-column slice); C and ld multiples of 8, 16-byte aligned base
+__global__ void __launch_bounds__(256)
+colsum_vec_kernel(const __half* __restrict__ dz, float* __restrict__ db, long long rows, int C, long long ld, float alpha,
+                  int rows_per_block) {
+  __shared__ float red[256][9];
+  const int slices = C >> 3;                         // 8-column slices per row (<= 32)
+  const int tid = threadIdx.x;
+  const int sl = tid % slices, grp = tid / slices;
+  const int groups = 256 / slices;
+  const long long r0 = (long long)blockIdx.x * rows_per_block;
+  const long long r1 = min(rows, r0 + rows_per_block);
+  float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  if (grp < groups) {
+    for (long long r = r0 + grp; r < r1; r += groups) {
+      const uint4 q = *reinterpret_cast<const uint4*>(dz + r * ld + 8 * sl);
+      const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&w[i]));
+        acc[2 * i] += f.x;
+        acc[2 * i + 1] += f.y;
+      }
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) red[tid][i] = acc[i];
+  __syncthreads();
+  if (tid < C) {
+    const int s2 = tid >> 3, i = tid & 7;
+    float s = 0.0f;
+    for (int gI = 0; gI < groups; ++gI) s += red[gI * slices + s2][i];
+    atomicAdd(db + tid, s * alpha);
+  }
+}
+
 static int grid_for(long long total, int threads) {
   long long blocks = (total + threads - 1) / threads;
   const long long cap = 148LL * 32;
@@ -368,6 +403,10 @@ int colsum_impl(const void* dz, float* db, long long rows, int C, long long ld, 
   long long rpb = (rows + 148LL * 8 - 1) / (148LL * 8);
   if (rpb < 64) rpb = 64;
   const int grid = (int)((rows + rpb - 1) / rpb);
+  if ((C & 7) == 0 && C <= 256 && (ld & 7) == 0 && (reinterpret_cast<uintptr_t>(dz) & 15) == 0) {
+    colsum_vec_kernel<<<grid, 256, 0, stream>>>(reinterpret_cast<const __half*>(dz), db, rows, C, ld, alpha, (int)rpb);
+    return check_launch("colsum_vec_kernel");
+  }
   colsum_kernel<<<grid, 256, 0, stream>>>(reinterpret_cast<const __half*>(dz), db, rows, C, ld, alpha, (int)rpb);
   return check_launch("colsum_kernel");
 }

@@ -483,30 +483,30 @@ conv_shift_fwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_cons
         const uint32_t taddr0 = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(as * BN);
   #pragma unroll 1
         for (int c0 = cg * NCG; c0 < (cg + 1) * NCG; c0 += 16 * G) {
-          uint32_t sv[G][8];
+          // activation-derivative mask of this lane's 16-column chunks as 1 bit per element (bit k <-> column c + k):
+          // read as such (saved_bits: 2 B instead of 32 B of HBM traffic per chunk), or derived from the fp16 activation
+          uint32_t mw[G];
           if (DACT) {
+  #pragma unroll
+            for (int j = 0; j < G; ++j) mw[j] = 0xffffu;
             if (masked && ok && p.saved_bits != nullptr) {
-              // 1 bit per element instead of the fp16 activation: 2 B instead of 32 B of HBM traffic per 16 columns;
-              // expanded to the half2 words {1.0 | 0.0} the mask code below expects
-              uint32_t bw[G];
   #pragma unroll
               for (int j = 0; j < G; ++j)
-                bw[j] = __ldg(p.saved_bits + ((sbase + map_coloff(p.smap, c0 + 16 * j)) >> 4));
-  #pragma unroll
-              for (int j = 0; j < G; ++j)
-  #pragma unroll
-                for (int i = 0; i < 8; ++i)
-                  sv[j][i] = (((bw[j] >> (2 * i)) & 1u) ? 0x3c00u : 0u) | (((bw[j] >> (2 * i + 1)) & 1u) ? 0x3c000000u : 0u);
+                mw[j] = __ldg(p.saved_bits + ((sbase + map_coloff(p.smap, c0 + 16 * j)) >> 4));
             } else if (masked && ok) {
   #pragma unroll
               for (int j = 0; j < G; ++j) {
-                ldg256(p.saved + sbase + map_coloff(p.smap, c0 + 16 * j), sv[j]);
+                uint32_t sv[8];
+                ldg256(p.saved + sbase + map_coloff(p.smap, c0 + 16 * j), sv);
+                uint32_t m = 0;
+  #pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                  const float2 h = __half22float2(*reinterpret_cast<const __half2*>(&sv[i]));
+                  m |= (h.x > lo ? 1u : 0u) << (2 * i);
+                  m |= (h.y > lo ? 2u : 0u) << (2 * i);
+                }
+                mw[j] = m;
               }
-            } else {
-  #pragma unroll
-              for (int j = 0; j < G; ++j)
-  #pragma unroll
-                for (int i = 0; i < 8; ++i) sv[j][i] = 0x3c003c00u;
             }
           }
           uint32_t r[G][16];
@@ -521,9 +521,8 @@ conv_shift_fwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_cons
               if (DACT) {
   #pragma unroll
                 for (int i = 0; i < 8; ++i) {
-                  const float2 h = __half22float2(*reinterpret_cast<const __half2*>(&sv[j][i]));
-                  const float a = (h.x > lo) ? __uint_as_float(r[j][2 * i]) * p.alpha : 0.0f;
-                  const float b = (h.y > lo) ? __uint_as_float(r[j][2 * i + 1]) * p.alpha : 0.0f;
+                  const float a = (mw[j] & (1u << (2 * i))) ? __uint_as_float(r[j][2 * i]) * p.alpha : 0.0f;
+                  const float b = (mw[j] & (2u << (2 * i))) ? __uint_as_float(r[j][2 * i + 1]) * p.alpha : 0.0f;
                   const __half2 o = __floats2half2_rn(a, b);
                   packed[i] = *reinterpret_cast<const uint32_t*>(&o);
                 }

@@ -253,13 +253,30 @@ cat_loss_kernel(const float* __restrict__ logits, long long ld, int nA, const fl
     const float clip = pc.cliprange_dev ? *pc.cliprange_dev : pc.cliprange;
     const float g_nlp = pg_loss_grad(nlp, pc.old_neglogp[s], adv, clip, pgl, kl, cf);
     const float g_v = value_loss_grad(vpred[b * ldv], oldv, R, clip, pc.vf_coef, vl);
-    for (int j = 0; j < nA; ++j) {
-      const float a0 = l[j] - m;
-      const float pj = expf(a0) / z;
-      const float logpj = a0 - logz;
-      // d nlp/dl_j = p_j - 1{j=a};  d(-ent_coef*H)/dl_j = ent_coef * p_j * (log p_j + H)
-      const float g = g_nlp * (pj - (j == a ? 1.0f : 0.0f)) + pc.ent_coef * pj * (logpj + H);
-      dlogits[b * ld_dl + j] = __float2half_rn(g);
+    // gradients leave as 16-byte stores (8 fp16 per store; one 2-byte store per column made the kernel
+    // store-instruction bound: 32 rows x 2 B per instruction).  Columns past nA inside the last group are zero.
+    __half* drow = dlogits + b * ld_dl;
+    const bool vec = ((ld_dl & 7) == 0) && ((reinterpret_cast<uintptr_t>(dlogits) & 15) == 0) && (((nA + 7) & ~7) <= ld_dl);
+    for (int j0 = 0; j0 < nA; j0 += 8) {
+      __align__(16) __half g8[8];
+#pragma unroll
+      for (int jj = 0; jj < 8; ++jj) {
+        const int j = j0 + jj;
+        float g = 0.0f;
+        if (j < nA) {
+          const float a0 = l[j] - m;
+          const float pj = expf(a0) / z;
+          const float logpj = a0 - logz;
+          // d nlp/dl_j = p_j - 1{j=a};  d(-ent_coef*H)/dl_j = ent_coef * p_j * (log p_j + H)
+          g = g_nlp * (pj - (j == a ? 1.0f : 0.0f)) + pc.ent_coef * pj * (logpj + H);
+        }
+        g8[jj] = __float2half_rn(g);
+      }
+      if (vec) {
+        *reinterpret_cast<uint4*>(drow + j0) = *reinterpret_cast<const uint4*>(g8);
+      } else {
+        for (int jj = 0; jj < 8 && j0 + jj < nA; ++jj) drow[j0 + jj] = g8[jj];
+      }
     }
     dv[b * ld_dv] = __float2half_rn(g_v);
     st[0] = pgl; st[1] = vl; st[2] = H; st[3] = kl; st[4] = cf;
@@ -278,7 +295,7 @@ gauss_loss_kernel(const float* __restrict__ mean, long long ld, const float* __r
   __syncthreads();
   const long long b = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   double st[5] = {0, 0, 0, 0, 0};
-  float g_nlp = 0.0f;
+  float g_nlp = 0.0f, g_v = 0.0f;
   long long srow = 0;
   if (b < B) {
     const long long s = pc.src_idx ? pc.src_idx[b] : b;
@@ -298,23 +315,39 @@ gauss_loss_kernel(const float* __restrict__ mean, long long ld, const float* __r
     float pgl, kl, cf, vl;
     const float clip = pc.cliprange_dev ? *pc.cliprange_dev : pc.cliprange;
     g_nlp = pg_loss_grad(nlp, pc.old_neglogp[s], adv, clip, pgl, kl, cf);
-    const float g_v = value_loss_grad(vpred[b * ldv], oldv, R, clip, pc.vf_coef, vl);
-    dv[b * ld_dv] = __float2half_rn(g_v);
+    g_v = value_loss_grad(vpred[b * ldv], oldv, R, clip, pc.vf_coef, vl);
     st[0] = pgl; st[1] = vl; st[2] = H; st[3] = kl; st[4] = cf;
   }
   // every lane takes part in the warp reductions of dL/dlogstd (inactive rows contribute 0): one shared-memory
   // atomic per warp and action dimension instead of one per sample
-  for (int j = 0; j < d; ++j) {
-    float gl = 0.0f;
-    if (b < B) {
-      const float sd = expf(logstd[j]);
-      const float t = (actions[srow * d + j] - mean[b * ld + j]) / sd;
-      dmean[b * ld_dm + j] = __float2half_rn(g_nlp * (-t / sd));      // d nlp/d mu = -(x-mu)/sigma^2
-      gl = g_nlp * (1.0f - t * t) - pc.ent_coef;   // d nlp/d logstd = 1 - t^2 ; d(-ent_coef*H)/d logstd = -ent_coef
+  const bool vec = ((ld_dm & 7) == 0) && ((reinterpret_cast<uintptr_t>(dmean) & 15) == 0) && (((d + 7) & ~7) <= ld_dm);
+  for (int j0 = 0; j0 < d; j0 += 8) {
+    __align__(16) __half g8[8];
+#pragma unroll
+    for (int jj = 0; jj < 8; ++jj) {
+      const int j = j0 + jj;
+      float gl = 0.0f, gm = 0.0f;
+      if (b < B && j < d) {
+        const float sd = expf(logstd[j]);
+        const float t = (actions[srow * d + j] - mean[b * ld + j]) / sd;
+        gm = g_nlp * (-t / sd);                      // d nlp/d mu = -(x-mu)/sigma^2
+        gl = g_nlp * (1.0f - t * t) - pc.ent_coef;   // d nlp/d logstd = 1 - t^2 ; d(-ent_coef*H)/d logstd = -ent_coef
+      }
+      g8[jj] = __float2half_rn(gm);
+      if (j < d) {                                   // uniform across the warp
+        gl = warp_sum(gl);
+        if ((threadIdx.x & 31) == 0) atomicAdd(&s_dls[j], gl);
+      }
     }
-    gl = warp_sum(gl);
-    if ((threadIdx.x & 31) == 0) atomicAdd(&s_dls[j], gl);
+    if (b < B) {
+      if (vec) {
+        *reinterpret_cast<uint4*>(dmean + b * ld_dm + j0) = *reinterpret_cast<const uint4*>(g8);
+      } else {
+        for (int jj = 0; jj < 8 && j0 + jj < d; ++jj) dmean[b * ld_dm + j0 + jj] = g8[jj];
+      }
+    }
   }
+  if (b < B) dv[b * ld_dv] = __float2half_rn(g_v);   // after dmean: with a fused [pi | vf] head dv is column d of the same row
   __syncthreads();
   for (int j = threadIdx.x; j < d; j += blockDim.x) atomicAdd(dlogstd + j, s_dls[j] * inv_M);
   block_accumulate5(st, pc.stats);
