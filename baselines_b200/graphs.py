@@ -29,7 +29,7 @@ class GraphCache:
         self.seen = set()
         self.max_graphs = max_graphs
 
-    def run(self, key, fn):
+    def run(self, key, fn, allow_fallback=False):
         if not enabled() or _lib._prof is not None:            # per-call profiling needs the eager sequence
             fn()
             return
@@ -42,8 +42,20 @@ class GraphCache:
                 return
             g = torch.cuda.CUDAGraph()
             before = _lib.LAUNCHES
-            with torch.cuda.graph(g):
+            try:
+                with torch.cuda.graph(g):
+                    fn()
+            except Exception as ex:                              # noqa: BLE001 -- e.g. a collective that cannot be captured
+                if not allow_fallback:
+                    raise
+                import warnings
+                warnings.warn(f"CUDA-graph capture of {key[0]!r} failed ({ex!r}); this sequence stays eager")
+                torch.cuda.synchronize()
+                self.seen.discard(key)
+                self.max_graphs = 0                              # stop capturing in this cache
+                _lib.LAUNCHES = before
                 fn()
+                return
             ent = self.graphs[key] = (g, _lib.LAUNCHES - before)
             _lib.LAUNCHES = before                               # nothing ran during capture
         ent[0].replay()

@@ -152,12 +152,16 @@ class Model(object):
             else:
                 key = ("train", M, obs.data_ptr(), actions.data_ptr(), returns.data_ptr(), values.data_ptr(),
                        neglogpacs.data_ptr())
-                if self.dist.active:
+                if self.dist.active and os.environ.get("B200RL_GRAPH_NCCL", "0") != "1":
                     self.graphs.run(key + ("grads",), grads)
                     self.dist.average_gradients(store)                   # mpi_adam_optimizer.py:39-40, BEFORE the clip
                     self.graphs.run(key + ("update",), update)
                 else:
-                    self.graphs.run(key, lambda: (grads(), update()))
+                    # single process: one graph per minibatch.  (B200RL_GRAPH_NCCL=1 also captures the NCCL all-reduce;
+                    # measured on 2 GPUs it is no faster than the split form -- 236.7 vs 236.6 ms -- and the process
+                    # group then hangs at teardown, so the split form is the default.)
+                    self.graphs.run(key, lambda: (grads(), self.dist.average_gradients(store), update()),
+                                    allow_fallback=self.dist.active)
             self._after_train_call()
             return self._stats_out / M
 
