@@ -372,6 +372,14 @@ def run_ppo2(cfg, args, steps, warmup, with_profile, with_e2e, dist_ctx):
         ms_prof, _ = timed(model, runner, max(1, min(steps, 2)), 0, read_back=False, profile=True)
         prof = (_lib.profile_end(), max(1, min(steps, 2)))
     value = world * nbatch / (ms_step / 1000.0)
+    # every rank's own kernel-time sum (eager profile pass): with 16 synchronising all-reduces per update the job runs at
+    # the pace of the slowest GPU, so a per-GPU spread shows up 1:1 in the N-GPU step time
+    per_rank_kernel_ms = None
+    if prof is not None and world > 1:
+        mine = torch.tensor([sum(v[0] for v in prof[0].values()) / prof[1]], device=dev)
+        allk = [torch.zeros_like(mine) for _ in range(world)]
+        dist.all_gather(allk, mine)
+        per_rank_kernel_ms = [round(float(t.item()), 2) for t in allk]
 
     # ---- e2e through the host VecEnv
     e2e = None
@@ -409,7 +417,7 @@ def run_ppo2(cfg, args, steps, warmup, with_profile, with_e2e, dist_ctx):
             e2e["stacked_upload"] = full
         del runner_h, env_h
     res = dict(value=value, ms_step=ms_step, launches=launches, clocks=clocks, e2e=e2e, prof=prof, ms_prof=ms_prof,
-               chunk=model.chunk, nbatch=nbatch)
+               chunk=model.chunk, nbatch=nbatch, per_rank_kernel_ms=per_rank_kernel_ms)
     del model
     torch.cuda.empty_cache()
     return res
@@ -661,6 +669,7 @@ def main():
            "gpu_launches": int(round(res["launches"] * args.steps)), "gpu_launches_per_step": res["launches"],
            "timing": "value: un-instrumented timed region; kernels / roofline: a second pass with per-call CUDA events"
                      + (f" ({res['ms_prof']:.1f} ms per step with the events)" if res.get("ms_prof") else ""),
+           "per_rank_kernel_ms": res.get("per_rank_kernel_ms"),
            "clocks": res["clocks"], "e2e": res["e2e"], "roofline": roofline, "roofline_all": roofline_all,
            "cpu_baseline": cpu_baseline, "other_configs": others, "targets": targets, "kernels": kernels}
     print(json.dumps(out), flush=True)
