@@ -551,7 +551,9 @@ int gemm_f16_impl(const void* A, const void* B, void* C, const float* bias, cons
                  "gemm: saved_bits is a ReLU mask for MODE_F16_DACT with ld_saved and N multiples of 16");
 
   int BN;
-  if (mn_major) BN = (N > 64) ? 128 : 64;
+  // wgrad form: a 256-wide N tile halves the shared-memory traffic per MMA column (A is staged once per 256 instead of
+  // per 128 output columns): fc1's weight gradient is bound by the 128 B/clk smem port, not by the tensor pipe
+  if (mn_major) BN = (N > 128 && N % 256 == 0) ? 256 : (N > 64) ? 128 : 64;
   else BN = (N > 128 && (N % 256 == 0)) ? 256 : (N > 64) ? 128 : (N > 32) ? 64 : 32;
 
   GemmParams p = {};
@@ -581,6 +583,7 @@ int gemm_f16_impl(const void* A, const void* B, void* C, const float* bias, cons
   if (mn_major) {
     B200RL_REQUIRE(mode == MODE_F32_ATOMIC, "gemm: the MN-major (wgrad) layout uses the fp32 atomic epilogue");
     if (BN == 64) return launch<64, 64, true, false, false, MODE_F32_ATOMIC>(tmA, tmB, p, max_ctas, stream);
+    if (BN == 256) return launch<256, 64, true, false, false, MODE_F32_ATOMIC>(tmA, tmB, p, max_ctas, stream);
     return launch<128, 64, true, false, false, MODE_F32_ATOMIC>(tmA, tmB, p, max_ctas, stream);
   }
 #define GEMM_KMAJOR(bn)                                                                                         \

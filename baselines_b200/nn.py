@@ -183,7 +183,8 @@ class Linear:
 
     def wgrad(self, x, ldx, dz, lddz, M, alpha):
         """gW += alpha * x^T dz (fp32 atomics, split-K over the batch rows); gb += alpha * colsum(dz)."""
-        tiles = -(-self.K // 128) * -(-self.N // (128 if self.N > 64 else 64))
+        bn = 256 if (self.N > 128 and self.N % 256 == 0) else (128 if self.N > 64 else 64)   # gemm_f16_impl's N tile
+        tiles = -(-self.K // 128) * -(-self.N // bn)
         kb = -(-M // 64)
         split = max(1, min(kb // 2 if kb >= 2 else 1, -(-296 // tiles)))
         ops.gemm(x, dz, self.gw, M=self.K, N=self.N, K=M, lda=ldx, ldb=lddz, ldc=self.N, mn_major=True,
