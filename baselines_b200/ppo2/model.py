@@ -26,7 +26,7 @@ class Model(object):
         self.device = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
         self.ent_coef, self.vf_coef, self.max_grad_norm = float(ent_coef), float(vf_coef), max_grad_norm
         self.nbatch_act, self.nbatch_train, self.nsteps = nbatch_act, nbatch_train, nsteps
-        chunk = int(train_chunk or os.environ.get("B200RL_TRAIN_CHUNK", 65536))
+        chunk = int(train_chunk or os.environ.get("B200RL_TRAIN_CHUNK", 131072))
         if microbatch_size is not None:                       # microbatched_model.py:5: same maths, smaller launches
             chunk = int(microbatch_size)
         self.chunk = max(1, min(chunk, max(1, nbatch_train)))

@@ -116,6 +116,14 @@ class Runner:
             self._news_pin = torch.ones(nenv, dtype=torch.uint8).pin_memory()
             self._news_dev = torch.zeros(nenv, dtype=torch.uint8, device=self.device)
             self._zero_obs = torch.zeros_like(self._cur)
+            # the upload of the new frames (PCIe-bound: 29 MB per step at cfg-2) is pipelined against the acting
+            # forward: the envs are cut into chunks, and while chunk k+1 is still in flight on the copy stream the
+            # frame-stack update and the policy forward of chunk k already run
+            import os
+            k = int(os.environ.get("B200RL_ACT_CHUNKS", 4 if (nenv % 4 == 0 and nenv >= 2048) else 1))
+            self.act_chunks = k if (k > 1 and nenv % k == 0) else 1
+            self._copy_stream = torch.cuda.Stream(device=self.device)
+            self._chunk_ev = [torch.cuda.Event() for _ in range(self.act_chunks)]
             # reset(): stack = 0, newest slot = first frame  (vec_frame_stack.py:27-31)
             self._stack_frames(env.reset_frames(), np.ones(nenv, dtype=np.bool_), self._zero_obs, self._cur)
         else:
@@ -150,6 +158,31 @@ class Runner:
         self._news_dev.copy_(self._news_pin, non_blocking=True)
         ops.frame_stack(prev, self._frame_dev, self._news_dev, out, self.env.nstack, self.env.frame_channels)
 
+    def _stack_and_act_chunked(self, frames, news, prev, t1):
+        """Frames of step t1 arrive: per env chunk, upload (copy stream) -> frame-stack update into rollout.obs[t1] ->
+        policy step into the rollout slots of t1, so the forward of chunk k overlaps the upload of chunk k+1."""
+        ro, model, K = self.rollout, self.model, self.act_chunks
+        tsrc = torch.from_numpy(frames) if isinstance(frames, np.ndarray) and frames.flags.c_contiguous else None
+        if tsrc is not None and tsrc.dtype == torch.uint8 and tsrc.shape == self._frame_pin.shape and tsrc.is_pinned():
+            src = tsrc
+        else:
+            self._frame_pin.numpy()[...] = frames
+            src = self._frame_pin
+        self._news_pin.numpy()[...] = np.asarray(news, dtype=np.uint8)
+        step = self.nenv // K
+        cur = torch.cuda.current_stream()
+        out = ro.obs[t1]
+        for k in range(K):
+            sl = slice(k * step, (k + 1) * step)
+            with torch.cuda.stream(self._copy_stream):
+                self._frame_dev[sl].copy_(src[sl], non_blocking=True)
+                self._news_dev[sl].copy_(self._news_pin[sl], non_blocking=True)
+                self._chunk_ev[k].record(self._copy_stream)
+            cur.wait_event(self._chunk_ev[k])
+            ops.frame_stack(prev[sl], self._frame_dev[sl], self._news_dev[sl], out[sl], self.env.nstack,
+                            self.env.frame_channels)
+            model.step_device(out[sl], ro.actions[t1][sl], ro.values[t1][sl], ro.neglogpacs[t1][sl], persistent=True)
+
     # -- stage the current observation into `dst` (rollout.obs[t] or a temp) in the network's input format
     def _upload_obs(self, dst):
         if self.device_env:
@@ -180,11 +213,15 @@ class Runner:
             self._ro_copied.synchronize()
             if self.fs:
                 ro.obs[0].copy_(self._cur)
+            chunked = self.fs and self.act_chunks > 1 and nz is None
+            acted = False                      # step t's policy pass already issued (chunk-wise, with the upload)
             for t in range(T):
                 if not self.fs:
                     self._upload_obs(ro.obs[t])
-                model.step_device(ro.obs[t], ro.actions[t], ro.values[t], ro.neglogpacs[t],
-                                  noise=None if nz is None else nz[t], persistent=True)
+                if not acted:
+                    model.step_device(ro.obs[t], ro.actions[t], ro.values[t], ro.neglogpacs[t],
+                                      noise=None if nz is None else nz[t], persistent=True)
+                acted = False
                 if self.device_env:
                     ro.dones[t].copy_(self._dev_dones)
                     self._dev_obs, rew, self._dev_dones = self.env.step_device(ro.actions[t])
@@ -197,7 +234,11 @@ class Runner:
                 if self.fs:
                     frames, rewards, self.dones, infos = self.env.step_frames(actions)
                     self.dones = np.asarray(self.dones, dtype=np.bool_)
-                    self._stack_frames(frames, self.dones, ro.obs[t], ro.obs[t + 1] if t + 1 < T else self._cur)
+                    if chunked and t + 1 < T:
+                        self._stack_and_act_chunked(frames, self.dones, ro.obs[t], t + 1)
+                        acted = True
+                    else:
+                        self._stack_frames(frames, self.dones, ro.obs[t], ro.obs[t + 1] if t + 1 < T else self._cur)
                 else:
                     obs, rewards, self.dones, infos = self.env.step(actions)             # runner.py:38
                     self._take_obs(obs)

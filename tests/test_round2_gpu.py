@@ -643,3 +643,54 @@ def test_dqn_graph_replay_equals_eager():
     diff = max(float(np.abs(res["eager"][2][k] - res["graphs"][2][k]).max()) for k in res["eager"][2])
     print(f"dqn params: eager-vs-eager spread {spread:.2e}, graphs-vs-eager {diff:.2e}")
     assert diff <= 4 * spread + 1e-6, (diff, spread)
+
+
+def test_chunked_upload_pipeline_equals_unchunked_rollout():
+    """Runner (VecFrameStack path): the env chunks' frame upload / frame-stack update / policy pass pipeline must produce
+    the same stacked observations and the same values as the one-shot path (the frames of a scripted env do not depend
+    on the actions; the sampled actions differ only through the sampler's stream position)."""
+    from baselines_b200.common import spaces
+    from baselines_b200.common.vec_env import VecEnv, VecFrameStack
+    from baselines_b200.ppo2.runner import Runner
+    case = CASES["cnn_cat"]
+    T, N = 3, 2048
+    env0, model, _ = _mk(nenv=N, nsteps=T, nminibatches=1, **case)
+    rng = np.random.RandomState(4)
+    frames = rng.randint(0, 256, (2 * T + 1, N, 84, 84, 1)).astype(np.uint8)
+    rew = rng.randn(2 * T, N).astype(np.float32)
+    done = rng.rand(2 * T, N) < 0.3
+
+    class Scripted(VecEnv):
+        def __init__(self):
+            super().__init__(N, spaces.Box(0, 255, (84, 84, 1), np.uint8), env0.action_space)
+            self.t = 0
+
+        def reset(self):
+            self.t = 0
+            return frames[0]
+
+        def step_async(self, actions):
+            pass
+
+        def step_wait(self):
+            r, d = rew[self.t], done[self.t]
+            self.t += 1
+            return frames[self.t], r, d, [{} for _ in range(N)]
+
+    outs = {}
+    for chunks in (1, 4):
+        os.environ["B200RL_ACT_CHUNKS"] = str(chunks)
+        try:
+            runner = Runner(env=VecFrameStack(Scripted(), 4), model=model, nsteps=T, gamma=0.99, lam=0.95)
+        finally:
+            del os.environ["B200RL_ACT_CHUNKS"]
+        assert runner.fs and runner.act_chunks == chunks
+        res = []
+        for k in range(2):
+            ro, _ = runner.run_device()
+            torch.cuda.synchronize()
+            res.append((ro.obs.clone(), ro.values.clone(), ro.dones.clone(), ro.rewards.clone(), ro.last_values.clone()))
+        outs[chunks] = res
+    for a, b in zip(outs[1], outs[4]):
+        assert torch.equal(a[0], b[0]) and torch.equal(a[2], b[2]) and torch.equal(a[3], b[3])
+        assert torch.equal(a[1], b[1]) and torch.equal(a[4], b[4])          # forward is batch-partition invariant
