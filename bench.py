@@ -269,9 +269,21 @@ def summarize_profile(prof, steps):
     return out
 
 
+# bench label -> kernel template instance (conv_shift.cu dispatch for the NatureCNN layers): <BN,KH,DACT,U8,KX> for the
+# forward / dgrad kernel, <BN,KH,U8,KX> for the wgrad kernel
+TRAFFIC_KERNEL = {
+    "convs.fwd.pi/c1": "conv_shift_fwd_kernel<32, 1, 0, 1, 1>", "convs.fwd.pi/c2": "conv_shift_fwd_kernel<64, 2, 0, 0, 1>",
+    "convs.fwd.pi/c3": "conv_shift_fwd_kernel<64, 1, 0, 0, 1>", "convs.dgrad.pi/c3": "conv_shift_fwd_kernel<64, 1, 1, 0, 1>",
+    "convs.dgrad.pi/c2": "conv_shift_fwd_kernel<128, 1, 1, 0, 1>", "convs.wgrad.pi/c1": "conv_shift_wgrad_kernel<32, 1, 1, 2>",
+    "convs.wgrad.pi/c2": "conv_shift_wgrad_kernel<64, 2, 0, 2>", "convs.wgrad.pi/c3": "conv_shift_wgrad_kernel<64, 1, 0, 3>",
+}
+
+
 def load_traffic():
-    """DRAM bytes per launch of named kernels from committed ncu `--set full` captures (profiles/r2_traffic.json is
-    written by tools/summarize_ncu.py from the .ncu-rep raw page -- never by hand)."""
+    """DRAM bytes per SAMPLE of each conv kernel instance from the committed `ncu --set full` capture
+    (profiles/r2_traffic.json, written by `tools/summarize_ncu.py traffic <rep> ... <samples>` from the .ncu-rep raw
+    page: dram__bytes_read.sum + dram__bytes_write.sum of one launch / the samples that launch processed).  bench
+    multiplies by the samples one of ITS launches processes; every launch here and in the capture is >> L2."""
     tj = os.path.join(ROOT, "profiles", "r2_traffic.json")
     return json.load(open(tj)) if os.path.exists(tj) else {}
 
@@ -290,9 +302,10 @@ def kernel_roofline(name, k, peaks, traffic=None):
     else:
         r = {"kernel": name, "bound": "hbm", "achieved": f_hbm * peaks["hbm_gbs"], "peak": peaks["hbm_gbs"],
              "unit": "GB/s", "frac": f_hbm, "peak_src": peaks["src"] + " (copy bandwidth)"}
-    t = (traffic or {}).get(name)
-    r.update({"traffic": t["dram_bytes_per_launch"] if t else None,
-              "traffic_src": t.get("src") if t else None,
+    t = (traffic or {}).get(TRAFFIC_KERNEL.get(name.split("@")[0], ""))
+    samples = k.get("samples_per_launch")
+    r.update({"traffic": t["dram_bytes_per_sample"] * samples if t and samples else None,
+              "traffic_src": (t.get("src") + f", {t['capture_samples']} samples/launch, scaled per sample") if t else None,
               "algorithmic_bytes_per_launch": k.get("bytes_per_step", 0.0) / n_launch,
               "algorithmic_flops_per_launch": k.get("flops_per_step", 0.0) / n_launch,
               "flops_are": "useful (valid conv outputs only)", "frac_tensor": f_tensor, "frac_hbm": f_hbm,
@@ -588,6 +601,11 @@ def main():
     traffic = load_traffic()
     kernels = _kernels_of(res)
     roofline, roofline_all = None, []
+    if kernels and cfg["kind"] == "ppo2":
+        per = {"train": min(res.get("chunk") or 1 << 62, cfg["nenvs"] * cfg["nsteps"] // cfg["nminibatches"]),
+               "act": cfg["nenvs"]}
+        for name, k in kernels.items():
+            k["samples_per_launch"] = per.get(name.split("@")[-1])
     if kernels:
         for name, k in sorted(kernels.items(), key=lambda kv: -kv[1]["ms_per_step"]):
             if k.get("flops_per_step") or k.get("bytes_per_step"):

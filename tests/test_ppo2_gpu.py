@@ -374,3 +374,37 @@ def test_command_line_trains_and_saves(tmp_path):
     assert "ppo2_model/pi/mlp_fc0/w:0" in ck and ck["ppo2_model/pi/mlp_fc0/w:0"].shape == (4, 64)
     a, v, s, nlp = model.step(np.zeros((2, 4), np.float32))
     assert a.shape == (2,) and s is None
+
+
+def test_command_line_play_loop(tmp_path, monkeypatch, capsys):
+    """--play (run.py:222-247): after training the trained model is stepped on the env forever, rendering each step
+    and printing `episode_rew=<return>` when an env finishes.  The loop has no exit in the reference either; the test
+    bounds it by making the (otherwise unused) render hook raise after a fixed number of steps."""
+    from baselines_b200 import logger, run
+    from baselines_b200.common import vec_env
+
+    class _Stop(Exception):
+        pass
+
+    calls = {"n": 0}
+
+    def render(self, *a, **k):
+        calls["n"] += 1
+        if calls["n"] >= 400:
+            raise _Stop
+
+    for cls in (vec_env.VecEnv, vec_env.DummyVecEnv, vec_env.SubprocVecEnv, vec_env.VecEnvWrapper):
+        monkeypatch.setattr(cls, "render", render, raising=False)
+    try:
+        with pytest.raises(_Stop):
+            run.main(["--alg=ppo2", "--env=CartPole-v0", "--num_timesteps=512", "--num_env=1", "--seed=0",
+                      "--network=mlp", "--nsteps=128", "--nminibatches=4", "--noptepochs=1", "--log_interval=100",
+                      f"--log_path={tmp_path / 'log'}", "--play"])
+    finally:
+        logger.configure(None)
+    out = capsys.readouterr().out
+    rets = [float(l.split("=")[1]) for l in out.splitlines() if l.startswith("episode_rew=")]
+    # CartPole-v0 pays +1 per step and ends within 200 steps: 400 play steps finish at least one episode and every
+    # printed return is that episode's step count
+    assert calls["n"] == 400 and len(rets) >= 1
+    assert all(r == int(r) and 1 <= r <= 200 for r in rets) and sum(rets) <= 400
