@@ -123,110 +123,131 @@ __device__ __forceinline__ void u8x16_to_f16(const uint4& q, uint4& lo, uint4& h
   hi = make_uint4(o[4], o[5], o[6], o[7]);
 }
 
-// cp.async (LDGSTS) with zero fill: src_bytes = 0 writes 16 zero bytes
-__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc, int src_bytes) {
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_u32(smem_dst)), "l"(gsrc), "r"(src_bytes)
-               : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+// Rolling A ring of the uint8-fed kernels.  A CTA's tiles are CONSECUTIVE in grid rows, so the rows tile i reads
+// through its shifted descriptors past its own TR rows are simply the first rows of tile i+1: the producer warps cast
+// every input row exactly once into a circular buffer of STAGES tiles (TR rows of 128 B each, 128B-swizzled by
+// absolute shared-memory address) instead of re-building a halo per tile.  The buffer ends with one extra 32-row
+// unit that mirrors the first unit of stage 0, so the tile in the last stage can read past the end.
+//
+// Shared memory bandwidth (128 B/clk, shared by the tensor core's operand fetch and the LSU) is what bounds these
+// kernels (profiles/r2_ncu_convs.md: wavefronts + SS operand fetch add up to the tile time), so the raw bytes go
+// global -> registers -> cast -> one swizzled store: no staging copy in shared memory.
+//
+// Work unit = 32 consecutive grid rows (one warp, lane = row); unit u of the CTA covers rows row_start + 32u ...,
+// belongs to tile u / UPT, and the units are dealt round-robin to the U8_WARPS producer warps.  Each warp keeps
+// U8_DEPTH units of loads in flight in registers (the sample index of the gather is looked up one round earlier).
+// Barriers per stage: full (UPT unit arrivals [+ the TMA of the other operand]), head (the first unit alone: the
+// tile in the PREVIOUS stage waits for it), empty (tcgen05.commit of the tile's MMAs).
+static constexpr int U8_DEPTH = 3;
 
-// Producer work unit = 32 consecutive grid rows of one tile (one warp, lane = row): the raw 4 x 16 uint8 segments of
-// a row are staged with cp.async into a per-warp ring (U8_DEPTH units in flight, no registers held; the lane that
-// staged bytes reads them back, so the ring needs no cross-thread synchronisation), then cast and written into the
-// 128B-swizzled fp16 tile.  Units are dealt round-robin to the U8_WARPS producer warps across tiles.
-static constexpr int U8_DEPTH = 4;
-static constexpr int U8_UNIT_BYTES = 32 * 64;
-static constexpr int U8_RING_BYTES = U8_WARPS * U8_DEPTH * U8_UNIT_BYTES;     // 64 KB
-
-__device__ __forceinline__ uint4 ld_shared_v4(uint32_t addr) {
+__device__ __forceinline__ uint4 ldg_stream_v4(const void* p) {
   uint4 v;
-  asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
+  asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+               : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
+               : "l"(p));
   return v;
 }
 __device__ __forceinline__ void st_shared_v4(uint32_t addr, const uint4& v) {
   asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }
 
-struct U8Unit {
-  long long sb;            // sample index of this lane's row in the NEXT unit to issue (-1: out of range -> zeros)
-  __device__ __forceinline__ void lookup(const U8Src& u, long long m, long long M) {
-    sb = -1;
-    if (m >= 0 && m < M) {
-      const uint32_t n = u.per.div((uint32_t)m);
-      sb = u.idx ? __ldg(u.idx + n) : (long long)n;
-    }
-  }
-  __device__ __forceinline__ void issue(const U8Src& u, long long m, uint32_t slot_lane) const {
-    const uint8_t* src = u.x;
-    int sz = 0, rowstride = 0;
-    if (sb >= 0) {
-      const uint32_t mm = (uint32_t)m;
-      const uint32_t rem = mm - u.per.div(mm) * u.per.d;
-      const uint32_t Y = u.wg.div(rem), X = rem - Y * u.wg.d;
-      rowstride = u.row_bytes;
-      src += sb * u.sample_bytes + (long long)(Y * (uint32_t)u.y_bytes + X * (uint32_t)u.x_bytes);
-      sz = 16;
-    }
-#pragma unroll
-    for (int dy = 0; dy < 4; ++dy)
-      asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(slot_lane + dy * 512), "l"(src + dy * rowstride),
-                   "r"(sz)
-                   : "memory");
-  }
-  // row_sw = smem address of this lane's tile row + ((lane & 7) << 4): chunk c of the row lives at row_sw ^ (c << 4)
-  __device__ __forceinline__ void convert(uint32_t slot_lane, uint32_t row_sw) const {
-#pragma unroll
-    for (int dy = 0; dy < 4; ++dy) {
-      uint4 lo, hi;
-      u8x16_to_f16(ld_shared_v4(slot_lane + dy * 512), lo, hi);
-      st_shared_v4(row_sw ^ (uint32_t)((2 * dy) << 4), lo);
-      st_shared_v4(row_sw ^ (uint32_t)((2 * dy + 1) << 4), hi);
-    }
-  }
+template <int TR, int STAGES>
+struct U8Ring {
+  static constexpr int UPT = TR / 32;                    // units per tile
+  static constexpr int ROWS = STAGES * TR + 32;          // + the mirror unit
+  static constexpr int BYTES = ROWS * 128;
+  static_assert(TR % 32 == 0 && BYTES % 1024 == 0, "ring keeps the 1024 B swizzle atoms aligned");
 };
 
-// The producer-warp loop shared by forward and wgrad.  Tile `seq` (0-based, local to this CTA) starts at grid row
-// row0(seq) and occupies pipeline stage seq % STAGES; it has RB = NROWS/32 units.
-template <int NROWS, int STAGES, typename Row0>
-__device__ __forceinline__ void u8_producer_loop(const U8Src& u, long long M, int ntiles, Row0 row0, uint8_t* stages,
-                                                 int stage_bytes, uint64_t* full_bar, uint64_t* empty_bar,
-                                                 uint8_t* ring_base, int pw, int lane) {
-  constexpr int RB = NROWS / 32;
-  static_assert(NROWS % 32 == 0, "unit = 32 rows");
-  const uint32_t ring = smem_u32(ring_base) + pw * (U8_DEPTH * U8_UNIT_BYTES) + lane * 16;
-  const uint32_t tile0 = smem_u32(stages) + lane * 128 + ((lane & 7) << 4);
-  const int total = ntiles * RB;
-  U8Unit t;
-  auto row_of = [&](int unit) { return row0(unit / RB) + (unit % RB) * 32 + lane; };
-  int ui = pw;
-  t.lookup(u, row_of(ui), ui < total ? M : 0);
+// sample slot of this lane's row of `unit` (-1: outside the matrix -> zeros)
+__device__ __forceinline__ long long u8_lookup(const U8Src& u, long long row_start, int unit, int total, long long M,
+                                               int lane) {
+  const long long m = row_start + (long long)unit * 32 + lane;
+  if (unit >= total || m < 0 || m >= M) return -1;
+  const uint32_t n = u.per.div((uint32_t)m);
+  return u.idx ? __ldg(u.idx + n) : (long long)n;
+}
+// the s segments (dy) of s*C = 16 bytes of this lane's grid row
+__device__ __forceinline__ void u8_load(const U8Src& u, long long row_start, int unit, long long sb, int lane,
+                                        uint4 (&q)[4]) {
+  if (sb >= 0) {
+    const uint32_t mm = (uint32_t)(row_start + (long long)unit * 32 + lane);
+    const uint32_t rem = mm - u.per.div(mm) * u.per.d;
+    const uint32_t Y = u.wg.div(rem), X = rem - Y * u.wg.d;
+    const uint8_t* src = u.x + sb * u.sample_bytes + (long long)(Y * (uint32_t)u.y_bytes + X * (uint32_t)u.x_bytes);
 #pragma unroll
-  for (int d = 0; d < U8_DEPTH; ++d) {
-    if (ui < total) t.issue(u, row_of(ui), ring + d * U8_UNIT_BYTES);
-    cp_async_commit();
-    ui += U8_WARPS;
-    t.lookup(u, row_of(ui), ui < total ? M : 0);
+    for (int dy = 0; dy < 4; ++dy) q[dy] = ldg_stream_v4(src + (long long)dy * u.row_bytes);
+  } else {
+#pragma unroll
+    for (int dy = 0; dy < 4; ++dy) q[dy] = make_uint4(0u, 0u, 0u, 0u);
   }
-  int d = 0;
-  for (int uc = pw; uc < total; uc += U8_WARPS) {
-    const int seq = uc / RB, rb = uc - seq * RB;
-    const int s = seq % STAGES;
-    const uint32_t ph = (uint32_t)(seq / STAGES) & 1u;
-    cp_async_wait<U8_DEPTH - 1>();
-    mbar_wait(&empty_bar[s], ph ^ 1);
-    t.convert(ring + d * U8_UNIT_BYTES, tile0 + s * stage_bytes + rb * (32 * 128));
-    fence_proxy_async_smem();                           // generic-proxy writes -> visible to the tensor core
-    __syncwarp();
-    if (lane == 0) mbar_arrive(&full_bar[s]);
-    if (ui < total) t.issue(u, row_of(ui), ring + d * U8_UNIT_BYTES);
-    cp_async_commit();
-    ui += U8_WARPS;
-    t.lookup(u, row_of(ui), ui < total ? M : 0);
-    if (++d == U8_DEPTH) d = 0;
+}
+
+template <int TR, int STAGES>
+__device__ __forceinline__ void u8_ring_producer(const U8Src& u, long long M, long long row_start, int ntiles,
+                                                 uint8_t* ring, uint64_t* full_bar, uint64_t* head_bar,
+                                                 uint64_t* empty_bar, int pw, int lane) {
+  using R = U8Ring<TR, STAGES>;
+  constexpr int UPT = R::UPT, D = U8_DEPTH, RND = U8_WARPS * D;
+  if (ntiles <= 0) return;
+  const int total = ntiles * UPT + 1;                    // + the head unit the last tile reads into
+  // row_sw = address of this lane's row of unit 0 of stage 0, + ((lane & 7) << 4): chunk c of a row lives at row_sw ^ (c << 4)
+  const uint32_t ring0 = smem_u32(ring) + lane * 128 + ((lane & 7) << 4);
+  uint4 q[D][4];
+  long long sb[D];
+#pragma unroll
+  for (int d = 0; d < D; ++d) sb[d] = u8_lookup(u, row_start, pw + U8_WARPS * d, total, M, lane);
+#pragma unroll
+  for (int d = 0; d < D; ++d) {
+    u8_load(u, row_start, pw + U8_WARPS * d, sb[d], lane, q[d]);
+    sb[d] = u8_lookup(u, row_start, pw + U8_WARPS * d + RND, total, M, lane);
   }
-  cp_async_wait<0>();
+  for (int base = pw; base < total; base += RND) {
+#pragma unroll
+    for (int d = 0; d < D; ++d) {
+      const int uc = base + U8_WARPS * d;
+      if (uc < total) {                                  // warp-uniform
+        const int tile = uc / UPT, ub = uc - tile * UPT;
+        const int s = tile % STAGES;
+        const uint32_t fill = (uint32_t)(tile / STAGES);
+        mbar_wait(&empty_bar[s], (fill & 1u) ^ 1u);
+        const uint32_t dst = ring0 + (uint32_t)(s * TR + ub * 32) * 128u;
+        const bool mirror = (s == 0) && (ub == 0);
+#pragma unroll
+        for (int dy = 0; dy < 4; ++dy) {
+          uint4 lo, hi;
+          u8x16_to_f16(q[d][dy], lo, hi);
+          st_shared_v4(dst ^ (uint32_t)((2 * dy) << 4), lo);
+          st_shared_v4(dst ^ (uint32_t)((2 * dy + 1) << 4), hi);
+          if (mirror) {
+            st_shared_v4((dst + (uint32_t)(STAGES * TR) * 128u) ^ (uint32_t)((2 * dy) << 4), lo);
+            st_shared_v4((dst + (uint32_t)(STAGES * TR) * 128u) ^ (uint32_t)((2 * dy + 1) << 4), hi);
+          }
+        }
+        fence_proxy_async_smem();                        // generic-proxy writes -> visible to the tensor core
+        __syncwarp();
+        if (lane == 0) {
+          if (tile < ntiles) mbar_arrive(&full_bar[s]);
+          if (ub == 0) mbar_arrive(&head_bar[s]);
+        }
+        u8_load(u, row_start, uc + RND, sb[d], lane, q[d]);
+        sb[d] = u8_lookup(u, row_start, uc + 2 * RND, total, M, lane);
+      }
+    }
+  }
+}
+
+// bit k of the result = (fp16 element k of the 16 packed values > 0): one packed compare (0xffff per true half) and
+// one LOP3 per pair instead of two compares, two selects and two ORs
+__device__ __forceinline__ uint16_t relu_bits16(const uint32_t (&packed)[8]) {
+  const __half2 z = __floats2half2_rn(0.0f, 0.0f);
+  uint32_t acc = 0;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const uint32_t m = __hgt2_mask(*reinterpret_cast<const __half2*>(&packed[i]), z);
+    acc |= m & ((1u << (2 * i)) | (0x20000u << (2 * i)));
+  }
+  return (uint16_t)((acc & 0xffffu) | (acc >> 16));
 }
 
 struct ShiftParams {
@@ -264,15 +285,19 @@ __global__ void __launch_bounds__(SH_FWD_THREADS + (U8 ? U8_THREADS : 0), 1)
 conv_shift_fwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW,
                       const __grid_constant__ ShiftParams p) {
   static_assert(KX == 1 || !DACT, "the data gradient keeps one MMA group per tap");
+  static_assert(!(U8 && KX > 1), "the rolling A ring needs tiles that start a whole tile apart");
   constexpr int NO = BN / KX;                        // output channels
   constexpr int TSTEP = SH_BM - (KX - 1);
   constexpr int STAGE_BYTES = KH * SH_ABYTES;
   constexpr int STAGES = (KH == 1) ? 6 : 3;
+  using Ring = U8Ring<SH_BM, STAGES>;                // uint8-fed first layer: rolling ring instead of per-tile stages
+  constexpr int A_PITCH = U8 ? SH_BM * 128 : STAGE_BYTES;
+  constexpr int A_TOTAL = U8 ? Ring::BYTES : STAGES * STAGE_BYTES;
   constexpr int W_SUB = BN * 128;                    // one (tap, half) weight sub-tile
   constexpr int TMEM_COLS = (2 * BN <= 64) ? 64 : (2 * BN <= 128) ? 128 : (2 * BN <= 256) ? 256 : 512;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* wres = smem + STAGES * STAGE_BYTES;       // resident weights: taps*KH sub-tiles
+  uint8_t* wres = smem + A_TOTAL;                    // resident weights: taps*KH sub-tiles
   uint64_t* bars = reinterpret_cast<uint64_t*>(wres + 80 * 1024);
   uint64_t* full_bar = bars;
   uint64_t* empty_bar = bars + STAGES;
@@ -280,6 +305,7 @@ conv_shift_fwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_cons
   uint64_t* tempty_bar = bars + 2 * STAGES + 2;
   uint64_t* w_bar = bars + 2 * STAGES + 4;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 5);
+  uint64_t* head_bar = bars + 2 * STAGES + 6;        // U8: first unit of the stage's tile is in place
 
   __shared__ float s_bias[NO];
   // x-fold halo exchange: [accumulator stage][parity][warp][halo row slot][column of the current chunk]
@@ -295,7 +321,11 @@ conv_shift_fwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_cons
     tma_prefetch_desc(&tmW);
   }
   if (warp == 1 && lane == 0) {
-    for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], U8 ? SH_AROWS / 32 : 1); mbar_init(&empty_bar[s], 1); }
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full_bar[s], U8 ? Ring::UPT : 1);
+      mbar_init(&empty_bar[s], 1);
+      if (U8) mbar_init(&head_bar[s], 1);
+    }
     for (int s = 0; s < 2; ++s) { mbar_init(&tfull_bar[s], 1); mbar_init(&tempty_bar[s], 128 * SH_CG); }
     mbar_init(w_bar, 1);
     fence_barrier_init();
@@ -305,6 +335,20 @@ conv_shift_fwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_cons
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+
+  // Tiles of this CTA: tile(i) = tile_first + i * tile_stride, i < tile_count.  TMA-fed layers interleave the CTAs
+  // (neighbouring CTAs share L2 lines of the halo rows); the uint8-fed layer gives every CTA one consecutive run.
+  int tile_first, tile_stride, tile_count;
+  if (U8) {
+    const int q = p.num_tiles / (int)gridDim.x, r = p.num_tiles % (int)gridDim.x, b = (int)blockIdx.x;
+    tile_first = b * q + min(b, r);
+    tile_stride = 1;
+    tile_count = q + (b < r ? 1 : 0);
+  } else {
+    tile_first = (int)blockIdx.x;
+    tile_stride = (int)gridDim.x;
+    tile_count = tile_first < p.num_tiles ? (p.num_tiles - tile_first + tile_stride - 1) / tile_stride : 0;
+  }
 
   // Role loops are warp-uniform; only the issue of the uniform-datapath instructions (TMA, tcgen05.mma,
   // tcgen05.commit) is gated by elect.sync -- a data-dependent `if (lane == 0)` makes the compiler wrap every
@@ -318,7 +362,8 @@ conv_shift_fwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_cons
     int s = 0;
     uint32_t ph = 0;
     if (!U8) {
-      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+      for (int i = 0; i < tile_count; ++i) {
+        const int tile = tile_first + i * tile_stride;
         mbar_wait(&empty_bar[s], ph ^ 1);
         if (elect_one()) {
           uint8_t* sa = smem + s * STAGE_BYTES;
@@ -332,13 +377,9 @@ conv_shift_fwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_cons
       }
     }
   } else if (U8 && warp >= 4 + SH_EPI_WARPS) {
-    // uint8 producer warps (the cp.async ring lives in the unused 64 KB of the weight area)
-    const int step = gridDim.x, first = blockIdx.x;
-    const int ntiles = first < p.num_tiles ? (p.num_tiles - first + step - 1) / step : 0;
-    const int min_shift = p.min_shift;
-    u8_producer_loop<SH_AROWS, STAGES>(
-        p.u8, p.M, ntiles, [=](int seq) { return (long long)(first + seq * step) * TSTEP + min_shift; }, smem,
-        STAGE_BYTES, full_bar, empty_bar, wres + 16384, warp - (4 + SH_EPI_WARPS), lane);
+    // uint8 producer warps
+    u8_ring_producer<SH_BM, STAGES>(p.u8, p.M, (long long)tile_first * SH_BM + p.min_shift, tile_count, smem, full_bar,
+                                    head_bar, empty_bar, warp - (4 + SH_EPI_WARPS), lane);
   } else if (warp == 1) {
     constexpr uint32_t IDESC = (1u << 4) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(SH_BM >> 4) << 24);
     int s = 0, as = 0;
@@ -348,12 +389,16 @@ conv_shift_fwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_cons
     // (byte offset >> 4) per MMA
     const uint64_t desc_hi = make_sdesc(0, 16, 1024, 2u);
     const uint32_t w_lo = (smem_u32(wres) & 0x3FFFFu) >> 4;
-    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+    for (int i = 0; i < tile_count; ++i) {
       mbar_wait(&tempty_bar[as], aph ^ 1);
       mbar_wait(&full_bar[s], ph);
+      if (U8) {                                          // the shifted taps read into the first unit of the next tile
+        const int s1 = (s + 1 == STAGES) ? 0 : s + 1;
+        mbar_wait(&head_bar[s1], s1 == 0 ? ph ^ 1 : ph);
+      }
       tc_fence_after();
       if (elect_one()) {
-        const uint32_t a_lo = (smem_u32(smem + s * STAGE_BYTES) & 0x3FFFFu) >> 4;
+        const uint32_t a_lo = (smem_u32(smem + s * A_PITCH) & 0x3FFFFu) >> 4;
         const uint32_t tmem_d = tmem_base + (uint32_t)(as * BN);
         uint32_t acc = 0;
         for (int t = 0; t < p.taps; ++t) {
@@ -385,7 +430,8 @@ conv_shift_fwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_cons
     uint32_t aph = 0;
     if constexpr (KX > 1) {
       uint32_t par = 0;
-      for (int tile = blockIdx.x + as * (int)gridDim.x; tile < p.num_tiles; tile += 2 * (int)gridDim.x) {
+      for (int i = as; i < tile_count; i += 2) {
+        const int tile = tile_first + i * tile_stride;
         const int ml = ew * 32 + lane;
         const uint32_t m = (uint32_t)tile * TSTEP + ml;
         const uint32_t t2 = p.fwg.div(m);
@@ -447,12 +493,7 @@ conv_shift_fwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_cons
               const long long eo = obase + map_coloff(p.omap, c);
               stg256(p.out + eo, packed);
               if (p.bits_out != nullptr) {
-                uint32_t bits = 0;
-#pragma unroll
-                for (int i = 0; i < 8; ++i)
-                  bits |= (((packed[i] & 0x7fffu) != 0u) ? (1u << (2 * i)) : 0u) |
-                          (((packed[i] & 0x7fff0000u) != 0u) ? (2u << (2 * i)) : 0u);
-                p.bits_out[eo >> 4] = (uint16_t)bits;
+                p.bits_out[eo >> 4] = relu_bits16(packed);
               }
             }
           }
@@ -464,7 +505,8 @@ conv_shift_fwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_cons
     } else {
       // 16-column chunks handled together (loads in flight); the masked data gradient also holds the mask words
       constexpr int G = (DACT && SH_CG > 1) ? ((NCG >= 32) ? 2 : 1) : ((NCG >= 64) ? 4 : NCG / 16);
-      for (int tile = blockIdx.x + as * (int)gridDim.x; tile < p.num_tiles; tile += 2 * (int)gridDim.x) {
+      for (int i = as; i < tile_count; i += 2) {
+        const int tile = tile_first + i * tile_stride;
         const uint32_t m = (uint32_t)tile * SH_BM + ew * 32 + lane;       // M < 2^31 (checked on the host)
         const uint32_t t2 = p.fwg.div(m);
         const int x = (int)(m - t2 * (uint32_t)p.Wg);
@@ -478,6 +520,7 @@ conv_shift_fwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_cons
         // (The epilogue is instruction-FETCH bound when its unrolled body outgrows the L0 / L1.5 I-caches, so it is
         // kept small: no tanh here, no per-element mode switches.)
         const float lo = (p.act == ACT_RELU) ? 0.0f : -INFINITY;
+        const __half2 lo2 = __floats2half2_rn(lo, lo);
         mbar_wait(&tfull_bar[as], aph);
         tc_fence_after();
         const uint32_t taddr0 = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(as * BN);
@@ -528,22 +571,17 @@ conv_shift_fwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_cons
                 }
               } else {
   #pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                  const float a = fmaxf(fmaf(__uint_as_float(r[j][2 * i]), p.alpha, s_bias[c + 2 * i]), lo);
-                  const float b = fmaxf(fmaf(__uint_as_float(r[j][2 * i + 1]), p.alpha, s_bias[c + 2 * i + 1]), lo);
-                  const __half2 o = __floats2half2_rn(a, b);
+                for (int i = 0; i < 8; ++i) {               // relu after the rounding: same result, one packed max
+                  const float a = fmaf(__uint_as_float(r[j][2 * i]), p.alpha, s_bias[c + 2 * i]);
+                  const float b = fmaf(__uint_as_float(r[j][2 * i + 1]), p.alpha, s_bias[c + 2 * i + 1]);
+                  const __half2 o = __hmax2(__floats2half2_rn(a, b), lo2);
                   packed[i] = *reinterpret_cast<const uint32_t*>(&o);
                 }
               }
               const long long eo = obase + map_coloff(p.omap, c);
               stg256(p.out + eo, packed);
               if (!DACT && p.bits_out != nullptr) {
-                uint32_t bits = 0;
-  #pragma unroll
-                for (int i = 0; i < 8; ++i)
-                  bits |= (((packed[i] & 0x7fffu) != 0u) ? (1u << (2 * i)) : 0u) |
-                          (((packed[i] & 0x7fff0000u) != 0u) ? (2u << (2 * i)) : 0u);
-                p.bits_out[eo >> 4] = (uint16_t)bits;
+                p.bits_out[eo >> 4] = relu_bits16(packed);
               }
             }
           }
@@ -590,16 +628,23 @@ conv_shift_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_co
   constexpr int BROWS = 64 + (KX - 1);                        // dY rows per stage (halo of KX - 1 rows in front)
   constexpr int B_BYTES = BROWS * BROWB;
   constexpr int B_REGION = (B_BYTES + 1023) & ~1023;
-  constexpr int STAGE_BYTES = KH * SH_WABYTES + B_REGION;     // A halves + B, keeps 1024 B alignment
   constexpr int STAGES = (KH == 1) ? 8 : (KX == 1 ? 6 : 5);
+  static_assert(!U8 || KH == 1, "the uint8-fed layer has 64 space-to-depth channels");
+  // TMA-fed: stage = [A halves | B], 1024 B aligned.  uint8-fed: [rolling A ring (64-row tiles) | B stages]
+  using Ring = U8Ring<64, STAGES>;
+  constexpr int A_PITCH = U8 ? 64 * 128 : KH * SH_WABYTES + B_REGION;
+  constexpr int B_PITCH = U8 ? B_REGION : KH * SH_WABYTES + B_REGION;
+  constexpr int B_BASE = U8 ? Ring::BYTES : KH * SH_WABYTES;
+  constexpr int SMEM_TILES = U8 ? Ring::BYTES + STAGES * B_REGION : STAGES * (KH * SH_WABYTES + B_REGION);
   constexpr int NW = KX * BN;                                 // MMA N
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + SMEM_TILES);
   uint64_t* full_bar = bars;
   uint64_t* empty_bar = bars + STAGES;
   uint64_t* done_bar = bars + 2 * STAGES;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 1);
+  uint64_t* head_bar = bars + 2 * STAGES + 2;                 // U8: first unit of the stage's k-block is in place
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int kb0 = blockIdx.x * p.kb_per_cta;
@@ -613,8 +658,9 @@ conv_shift_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_co
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < STAGES; ++s) {
-      mbar_init(&full_bar[s], U8 ? 1 + SH_WROWS_K / 32 : 1);
+      mbar_init(&full_bar[s], U8 ? 1 + Ring::UPT : 1);
       mbar_init(&empty_bar[s], p.gbias ? 2 : 1);
+      if (U8) mbar_init(&head_bar[s], 1);
     }
     mbar_init(done_bar, 1);
     fence_barrier_init();
@@ -631,21 +677,20 @@ conv_shift_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_co
     for (int kb = kb0; kb < kb1; ++kb) {
       mbar_wait(&empty_bar[s], ph ^ 1);
       if (elect_one()) {
-        uint8_t* sa = smem + s * STAGE_BYTES;
+        uint8_t* sa = smem + s * A_PITCH;
         mbar_arrive_expect_tx(&full_bar[s], (uint32_t)((U8 ? 0 : KH * SH_WABYTES) + B_BYTES));
         if (!U8) {
 #pragma unroll
           for (int h = 0; h < KH; ++h) tma_load_2d(sa + h * SH_WABYTES, &tmX, &full_bar[s], h * 64, kb * 64);
         }
-        tma_load_2d(sa + KH * SH_WABYTES, &tmD, &full_bar[s], 0, kb * 64 - (KX - 1));   // negative rows: zero fill
+        tma_load_2d(smem + B_BASE + s * B_PITCH, &tmD, &full_bar[s], 0, kb * 64 - (KX - 1));   // negative rows: zero fill
       }
       __syncwarp();
       if (++s == STAGES) { s = 0; ph ^= 1; }
     }
   } else if (U8 && warp >= 8) {
-    u8_producer_loop<SH_WROWS_K, STAGES>(
-        p.u8, p.M, kb1 - kb0, [=](int seq) { return (long long)(kb0 + seq) * 64; }, smem, STAGE_BYTES, full_bar,
-        empty_bar, smem + STAGES * STAGE_BYTES + 256, warp - 8, lane);
+    u8_ring_producer<64, STAGES>(p.u8, p.M, (long long)kb0 * 64, kb1 - kb0, smem, full_bar, head_bar, empty_bar,
+                                 warp - 8, lane);
   } else if (warp == 1) {
     constexpr uint32_t IDESC = (1u << 4) | (1u << 15) | (1u << 16) | ((uint32_t)(NW >> 3) << 17) |
                                ((uint32_t)(SH_BM >> 4) << 24);
@@ -654,10 +699,14 @@ conv_shift_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_co
       uint32_t ph = 0;
       for (int kb = kb0; kb < kb1; ++kb) {
         mbar_wait(&full_bar[s], ph);
+        if (U8) {                                          // the shifted taps read into the first unit of the next block
+          const int s1 = (s + 1 == STAGES) ? 0 : s + 1;
+          mbar_wait(&head_bar[s1], s1 == 0 ? ph ^ 1 : ph);
+        }
         tc_fence_after();
         if (elect_one()) {
-        const uint32_t a_addr = smem_u32(smem + s * STAGE_BYTES);
-        const uint32_t b_addr = a_addr + KH * SH_WABYTES;
+        const uint32_t a_addr = smem_u32(smem + s * A_PITCH);
+        const uint32_t b_addr = smem_u32(smem + B_BASE + s * B_PITCH);
         // KX == 1: one chunk (LBO unused).  KX > 1: N-chunk j of the dY operand starts j rows further into the tile
         const uint64_t bdesc0 = make_sdesc(b_addr, KX == 1 ? 64 * BROWB : BROWB, 8 * BROWB, LAYOUT_B);
         for (int j = 0; j < n_mt; ++j) {
@@ -696,7 +745,7 @@ conv_shift_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_co
       for (int kb = kb0; kb < kb1; ++kb, s = (s + 1 == STAGES) ? 0 : s + 1, ph ^= (s == 0)) {
         if ((s & 3) != ew) continue;
         mbar_wait(&full_bar[s], ph);
-        const uint8_t* sb = smem + s * STAGE_BYTES + KH * SH_WABYTES;
+        const uint8_t* sb = smem + B_BASE + s * B_PITCH;
 #pragma unroll 8
         for (int r = rg + (KX - 1); r < 64 + (KX - 1); r += RG) {           // the halo rows belong to the previous block
           const int sw = (BROWB == 128) ? (r & 7) : ((r >> 1) & 3);
@@ -771,7 +820,7 @@ static U8Src make_u8src(const void* x, const long long* idx, int H, int W, int C
 template <int BN, int KH, bool DACT, bool U8 = false, int KX = 1>
 static int launch_fwd(const CUtensorMap& tmX, const CUtensorMap& tmW, const ShiftParams& p, cudaStream_t st) {
   constexpr int STAGES = (KH == 1) ? 6 : 3;
-  constexpr int SMEM = STAGES * KH * SH_ABYTES + 80 * 1024 + 1024 + 256;
+  constexpr int SMEM = (U8 ? U8Ring<SH_BM, STAGES>::BYTES : STAGES * KH * SH_ABYTES) + 80 * 1024 + 1024 + 256;
   static bool attr = false;
   auto kern = conv_shift_fwd_kernel<BN, KH, DACT, U8, KX>;
   if (!attr) {
@@ -793,7 +842,8 @@ static int launch_wgrad(const CUtensorMap& tmX, const CUtensorMap& tmD, const Sh
   constexpr int STAGES = (KH == 1) ? 8 : (KX == 1 ? 6 : 5);
   constexpr int BROWB = (BN >= 64) ? 128 : BN * 2;
   constexpr int B_REGION = ((64 + KX - 1) * BROWB + 1023) & ~1023;
-  constexpr int SMEM = STAGES * (KH * SH_WABYTES + B_REGION) + 1024 + 256 + (U8 ? U8_RING_BYTES : 0);
+  constexpr int SMEM =
+      (U8 ? U8Ring<64, STAGES>::BYTES + STAGES * B_REGION : STAGES * (KH * SH_WABYTES + B_REGION)) + 1024 + 256;
   static_assert(SMEM <= 227 * 1024, "conv_shift_wgrad: shared memory budget");
   static bool attr = false;
   auto kern = conv_shift_wgrad_kernel<BN, KH, U8, KX>;
@@ -872,8 +922,8 @@ int conv_shift_fwd_impl(const void* X, long long B, int Hg, int Wg, int C, const
   B200RL_REQUIRE(act == ACT_NONE || act == ACT_RELU, "conv_shift_fwd: activation must be none or relu");
   if ((rc = make_tmap_2d_f16(&tmW, W, (long long)kx * N, (long long)taps * C, ldw, 64, kx * N)) != 0) return rc;
   if (u8_x) {                                                          // tmX unused: A tiles come from the producers
-    if (kx == 2) return launch_fwd<64, 1, false, true, 2>(tmW, tmW, p, stream);
-    B200RL_REQUIRE(kx == 1, "conv_shift_fwd: the uint8-fed first layer supports kx = 1 or 2");
+    B200RL_REQUIRE(kx == 1, "conv_shift_fwd: the uint8-fed first layer has no x-folded forward (rolling A ring)");
+    B200RL_REQUIRE(hi - lo <= 32, "conv_shift_fwd: uint8-fed shift span %d exceeds one 32-row unit", hi - lo);
     return launch_fwd<32, 1, false, true>(tmW, tmW, p, stream);
   }
   if ((rc = make_tmap_2d_f16(&tmX, X, p.M, C, C, 64, SH_AROWS)) != 0) return rc;

@@ -36,7 +36,12 @@ def _rank():
 class _Human:
     def __init__(self, target):
         self.own = isinstance(target, str)
-        self.f = open(target, "wt") if self.own else target
+        self._stdout = target is sys.stdout          # follow later redirections of sys.stdout (test capture, tee)
+        self._f = open(target, "wt") if self.own else target
+
+    @property
+    def f(self):
+        return sys.stdout if self._stdout else self._f
 
     @staticmethod
     def _cut(s):
@@ -60,7 +65,7 @@ class _Human:
 
     def close(self):
         if self.own:
-            self.f.close()
+            self._f.close()
 
 
 class _Json:

@@ -468,6 +468,8 @@ class Tower:
         self.fused_u8 = (os.environ.get("B200RL_NO_FUSED_U8", "0") != "1" and c0.stride == 4 and c0.C == 4 and
                          c0.nf == 32 and g0["Cg"] == 64)
         self.x16 = None if self.fused_u8 else torch.empty(cap, g0["Hg"] * g0["Wg"] * g0["Cg"], **f16)
+        if self.fused_u8:
+            g0["kx_fwd"] = 1                           # the uint8-fed forward kernel (rolling A ring) has no folded variant
         # activations: layer i's output is stored space-to-depth'ed for layer i+1 (compact after the last conv)
         self.hconv = [torch.empty(cap, c.OH * c.OW * c.nf, **f16) for c in cv]
         # 1 bit per element "activation > 0" of every conv output a later dgrad masks with: the backward kernels read
