@@ -12,9 +12,10 @@
 //   conv_shift_wgrad_kernel (MN-major): G[t, c, n] += alpha * sum_m X[m + sh_t, c] * dY[m, n]         wgrad
 //                                       (all taps' accumulators live in TMEM at once; X and dY are read once)
 //
-// Warp roles (forward, 384 threads [+256]): 0 TMA loads (weights once, A tile per tile) | 1 MMA issue (elect.sync) |
-// 2 TMEM alloc | 3 spare | 4-7 / 8-11 epilogue sets for accumulator stage 0 / 1 | 12-19 (first layer only) uint8
-// producer warps that build the A tile from raw frames instead of the TMA.  wgrad (256 threads [+256]): 0 TMA | 1 MMA |
+// Warp roles (forward, 384 threads [+256]): 0 TMA loads (weights once, A tile per tile) | 1 and 3 MMA issue (elect.sync)
+// for the even / odd tiles | 2 TMEM alloc | 4-7 / 8-11 epilogue sets for the even / odd tiles (4 TMEM accumulator
+// stages) | 12-19 (first layer only) uint8 producer warps that cast raw frames into a rolling A ring instead of the
+// TMA.  wgrad (256 threads [+256]): 0 TMA | 1 MMA |
 // 2 TMEM | 3 spare | 4-7 fused bias-gradient sums during the main loop, then the epilogue | 8-15 uint8 producers.
 // The forward epilogue can also write 1 bit per output element (act > 0); the dgrad of the next layer reads that
 // instead of the fp16 activation.
@@ -39,8 +40,14 @@ static constexpr int SH_CG = 1;
 static constexpr int SH_EPI_WARPS = 2 * SH_CG * 4;
 static constexpr int SH_FWD_THREADS = 128 + SH_EPI_WARPS * 32;
 static constexpr int SH_MAX_TAPS = 16;
-static constexpr int SH_AROWS = 160;                 // 128 + max shift span (<= 32)
-static constexpr int SH_ABYTES = SH_AROWS * 128;     // one 64-channel half of an A stage
+// rows of one TMA-fed A stage: 128 + the largest shift span.  64-channel inputs: span <= 32.  128-channel inputs (two
+// halves per stage): span <= 16, so that FOUR stages fit beside the weights -- the stage count must be even, because
+// the two MMA-issuing warps alternate over the tiles and each must own its stages' barriers (a warp that met only
+// every other phase of an mbarrier could mistake an old phase of that parity for the one it waits for).
+__host__ __device__ constexpr int sh_arows(int KH) { return KH == 1 ? 160 : 144; }
+__host__ __device__ constexpr int sh_stages(int KH) { return KH == 1 ? 6 : 4; }
+// resident-weight region of the forward kernel (all taps): 80 KB beside 64-channel stages, 64 KB beside 128-channel ones
+__host__ __device__ constexpr int sh_wres_bytes(int KH) { return KH == 1 ? 80 * 1024 : 64 * 1024; }
 static constexpr int SH_WROWS_K = 96;                // wgrad: 64 + max shift span (<= 32)
 static constexpr int SH_WABYTES = SH_WROWS_K * 128;
 
@@ -186,10 +193,11 @@ __device__ __forceinline__ void u8_load(const U8Src& u, long long row_start, int
 template <int TR, int STAGES>
 __device__ __forceinline__ void u8_ring_producer(const U8Src& u, long long M, long long row_start, int ntiles,
                                                  uint8_t* ring, uint64_t* full_bar, uint64_t* head_bar,
-                                                 uint64_t* empty_bar, int pw, int lane) {
+                                                 uint64_t* empty_bar, int pw, int lane, bool dry = false) {
   using R = U8Ring<TR, STAGES>;
   constexpr int UPT = R::UPT, D = U8_DEPTH, RND = U8_WARPS * D;
   if (ntiles <= 0) return;
+  if (dry) M = 0;                                        // diagnostics: every row "outside the matrix": no loads
   const int total = ntiles * UPT + 1;                    // + the head unit the last tile reads into
   // row_sw = address of this lane's row of unit 0 of stage 0, + ((lane & 7) << 4): chunk c of a row lives at row_sw ^ (c << 4)
   const uint32_t ring0 = smem_u32(ring) + lane * 128 + ((lane & 7) << 4);
@@ -214,7 +222,7 @@ __device__ __forceinline__ void u8_ring_producer(const U8Src& u, long long M, lo
         const uint32_t dst = ring0 + (uint32_t)(s * TR + ub * 32) * 128u;
         const bool mirror = (s == 0) && (ub == 0);
 #pragma unroll
-        for (int dy = 0; dy < 4; ++dy) {
+        for (int dy = 0; dy < 4 && !dry; ++dy) {
           uint4 lo, hi;
           u8x16_to_f16(q[d][dy], lo, hi);
           st_shared_v4(dst ^ (uint32_t)((2 * dy) << 4), lo);
@@ -271,6 +279,7 @@ struct ShiftParams {
   int act, dact;           // dact = 1: multiply by act'(saved) instead of applying act
   float alpha;
   int num_tiles;
+  int debug;               // diagnostics (B200RL_CONV_DEBUG): 1 producers / TMA move no data, 2 no MMAs, 4 no epilogue work
 };
 
 // ------------------------------------------------------------------------------------------------ forward / dgrad
@@ -288,24 +297,33 @@ conv_shift_fwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_cons
   static_assert(!(U8 && KX > 1), "the rolling A ring needs tiles that start a whole tile apart");
   constexpr int NO = BN / KX;                        // output channels
   constexpr int TSTEP = SH_BM - (KX - 1);
+  constexpr int SH_ABYTES = sh_arows(KH) * 128;      // one 64-channel half of an A stage
   constexpr int STAGE_BYTES = KH * SH_ABYTES;
-  constexpr int STAGES = (KH == 1) ? 6 : 3;
+  constexpr int STAGES = sh_stages(KH);
+  static_assert(STAGES % 2 == 0, "each MMA-issuing warp owns alternate stages");
   using Ring = U8Ring<SH_BM, STAGES>;                // uint8-fed first layer: rolling ring instead of per-tile stages
   constexpr int A_PITCH = U8 ? SH_BM * 128 : STAGE_BYTES;
   constexpr int A_TOTAL = U8 ? Ring::BYTES : STAGES * STAGE_BYTES;
   constexpr int W_SUB = BN * 128;                    // one (tap, half) weight sub-tile
-  constexpr int TMEM_COLS = (2 * BN <= 64) ? 64 : (2 * BN <= 128) ? 128 : (2 * BN <= 256) ? 256 : 512;
+  // Accumulator stages.  The hand-off of a TMEM stage (tcgen05.commit -> mbarrier -> epilogue warps wake, read, arrive
+  // -> MMA warp wakes) costs on the order of a whole tile of these small MMAs (tools/conv_roles.py: a tile loop with all
+  // data movement and math removed still runs at ~40 % of the full kernel's time), so two stages leave the tensor core
+  // idle; four hide it.  Two epilogue warp sets still alternate over the tiles.
+  constexpr int NACC = (BN <= 128) ? 4 : 2;
+  constexpr int TMEM_COLS = (NACC * BN <= 64) ? 64 : (NACC * BN <= 128) ? 128 : (NACC * BN <= 256) ? 256 : 512;
+  static_assert(NACC * BN <= 512, "accumulator stages exceed TMEM");
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* wres = smem + A_TOTAL;                    // resident weights: taps*KH sub-tiles
-  uint64_t* bars = reinterpret_cast<uint64_t*>(wres + 80 * 1024);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(wres + sh_wres_bytes(KH));
   uint64_t* full_bar = bars;
   uint64_t* empty_bar = bars + STAGES;
   uint64_t* tfull_bar = bars + 2 * STAGES;
-  uint64_t* tempty_bar = bars + 2 * STAGES + 2;
-  uint64_t* w_bar = bars + 2 * STAGES + 4;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 5);
-  uint64_t* head_bar = bars + 2 * STAGES + 6;        // U8: first unit of the stage's tile is in place
+  uint64_t* tempty_bar = bars + 2 * STAGES + NACC;
+  uint64_t* w_bar = bars + 2 * STAGES + 2 * NACC;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 2 * NACC + 1);
+  uint64_t* head_bar = bars + 2 * STAGES + 2 * NACC + 2;   // U8: first unit of the stage's tile is in place
+  static_assert((3 * STAGES + 2 * NACC + 2) * 8 <= 256, "barrier block");
 
   __shared__ float s_bias[NO];
   // x-fold halo exchange: [accumulator stage][parity][warp][halo row slot][column of the current chunk]
@@ -323,12 +341,13 @@ conv_shift_fwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_cons
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(&full_bar[s], U8 ? Ring::UPT : 1);
-      mbar_init(&empty_bar[s], 1);
+      mbar_init(&empty_bar[s], U8 ? 2 : 1);                // ring: the stage's own tile and the tile before it (see the MMA warps)
       if (U8) mbar_init(&head_bar[s], 1);
     }
-    for (int s = 0; s < 2; ++s) { mbar_init(&tfull_bar[s], 1); mbar_init(&tempty_bar[s], 128 * SH_CG); }
+    for (int s = 0; s < NACC; ++s) { mbar_init(&tfull_bar[s], 1); mbar_init(&tempty_bar[s], 128 * SH_CG); }
     mbar_init(w_bar, 1);
     fence_barrier_init();
+    if (U8) mbar_arrive(&empty_bar[0]);                    // stands in for "the tile before" the CTA's first tile
   }
   if (warp == 2) tmem_alloc<TMEM_COLS>(tmem_slot);
   tc_fence_before();
@@ -379,59 +398,91 @@ conv_shift_fwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_cons
   } else if (U8 && warp >= 4 + SH_EPI_WARPS) {
     // uint8 producer warps
     u8_ring_producer<SH_BM, STAGES>(p.u8, p.M, (long long)tile_first * SH_BM + p.min_shift, tile_count, smem, full_bar,
-                                    head_bar, empty_bar, warp - (4 + SH_EPI_WARPS), lane);
-  } else if (warp == 1) {
+                                    head_bar, empty_bar, warp - (4 + SH_EPI_WARPS), lane, (p.debug & 1) != 0);
+  } else if (warp == 1 || warp == 3) {
+    // TWO MMA-issuing warps, even / odd tiles.  tcgen05.mma issue is not fire-and-forget at this size: the issuing thread
+    // stalls on the (shallow) MMA queue, so with one issuer the per-tile barrier waits + commits (~430 clocks, measured
+    // with tools/conv_roles.py) ADD to the 16..36 small MMAs instead of hiding under them.  With two issuers one warp
+    // does its waits while the other feeds the tensor core; the two tiles use different TMEM stages (NACC even).
+    static_assert(NACC % 2 == 0, "issuers own alternate accumulator stages");
     constexpr uint32_t IDESC = (1u << 4) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(SH_BM >> 4) << 24);
-    int s = 0, as = 0;
+    const int iss = warp >> 1;
+    int s = iss % STAGES, as = iss;
     uint32_t ph = 0, aph = 0;
     mbar_wait(w_bar, 0);
-    // descriptors differ only in their 14-bit start-address field: build the constant part once and add
-    // (byte offset >> 4) per MMA
-    const uint64_t desc_hi = make_sdesc(0, 16, 1024, 2u);
-    const uint32_t w_lo = (smem_u32(wres) & 0x3FFFFu) >> 4;
-    for (int i = 0; i < tile_count; ++i) {
+    // descriptors differ only in the 14-bit start-address field of their low word: the rest is built once, and
+    // every MMA adds (byte offset >> 4) to a low word (shared memory ends below 256 KB, so the field never carries)
+    constexpr uint64_t DESC0 = (1ull << 46) | (2ull << 61) | ((uint64_t)(1024 >> 4) << 32) | ((uint64_t)(16 >> 4) << 16);
+    constexpr uint32_t D_HI = (uint32_t)(DESC0 >> 32), D_LO = (uint32_t)DESC0;
+    const uint32_t w_lo = D_LO + ((smem_u32(wres) & 0x3FFFFu) >> 4);
+    for (int i = iss; i < tile_count; i += 2) {
+      const int s1 = (s + 1 == STAGES) ? 0 : s + 1;
       mbar_wait(&tempty_bar[as], aph ^ 1);
       mbar_wait(&full_bar[s], ph);
-      if (U8) {                                          // the shifted taps read into the first unit of the next tile
-        const int s1 = (s + 1 == STAGES) ? 0 : s + 1;
-        mbar_wait(&head_bar[s1], s1 == 0 ? ph ^ 1 : ph);
-      }
+      if (U8) mbar_wait(&head_bar[s1], s1 == 0 ? ph ^ 1 : ph);   // the shifted taps read into the next tile's first unit
       tc_fence_after();
       if (elect_one()) {
-        const uint32_t a_lo = (smem_u32(smem + s * A_PITCH) & 0x3FFFFu) >> 4;
+        const uint32_t a_lo = D_LO + ((smem_u32(smem + s * A_PITCH) & 0x3FFFFu) >> 4);
         const uint32_t tmem_d = tmem_base + (uint32_t)(as * BN);
-        uint32_t acc = 0;
-        for (int t = 0; t < p.taps; ++t) {
-          const uint32_t at = a_lo + (uint32_t)p.shift[t] * 8u;          // 128 B per row = 8 x 16 B
-          const uint32_t wt = w_lo + (uint32_t)(t * KH) * (W_SUB >> 4);
+        if (!(p.debug & 2)) {
+          // tap 0 overwrites the accumulator with its first MMA; the others accumulate
+          {
+            const uint32_t at = a_lo + (uint32_t)p.shift[0] * 8u;        // 128 B per row = 8 x 16 B
 #pragma unroll
-          for (int h = 0; h < KH; ++h) {
+            for (int h = 0; h < KH; ++h) {
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
-              umma_f16(tmem_d, desc_hi | (uint64_t)(at + h * (SH_ABYTES >> 4) + 2 * k),
-                       desc_hi | (uint64_t)(wt + h * (W_SUB >> 4) + 2 * k), IDESC, acc);
-              acc = 1;
+              for (int k = 0; k < 4; ++k) {
+                if (h == 0 && k == 0)
+                  umma_f16_lh<false>(tmem_d, at, D_HI, w_lo, D_HI, IDESC);
+                else
+                  umma_f16_lh<true>(tmem_d, at + h * (SH_ABYTES >> 4) + 2 * k, D_HI, w_lo + h * (W_SUB >> 4) + 2 * k,
+                                    D_HI, IDESC);
+              }
+            }
+          }
+          // not unrolled: an unrolled tap loop keeps dozens of descriptor pairs live and spills the uniform registers;
+          // the next tap's shift is fetched (constant bank) while this tap's MMAs are issued
+          uint32_t wt = w_lo;
+          uint32_t sh_next = (uint32_t)p.shift[1];
+#pragma unroll 1
+          for (int t = 1; t < p.taps; ++t) {
+            const uint32_t at = a_lo + sh_next * 8u;
+            sh_next = (uint32_t)p.shift[(t + 1) & (SH_MAX_TAPS - 1)];
+            wt += (uint32_t)KH * (W_SUB >> 4);
+#pragma unroll
+            for (int h = 0; h < KH; ++h) {
+#pragma unroll
+              for (int k = 0; k < 4; ++k)
+                umma_f16_lh<true>(tmem_d, at + h * (SH_ABYTES >> 4) + 2 * k, D_HI, wt + h * (W_SUB >> 4) + 2 * k, D_HI,
+                                  IDESC);
             }
           }
         }
         umma_commit(&empty_bar[s]);
+        // ring: this tile also read the head of the next stage, whose own tile belongs to the OTHER issuer -- that
+        // stage is free only when both tiles are done (barrier count 2)
+        if (U8) umma_commit(&empty_bar[s1]);
         umma_commit(&tfull_bar[as]);
       }
       __syncwarp();
-      if (++s == STAGES) { s = 0; ph ^= 1; }
-      if (++as == 2) { as = 0; aph ^= 1; }
+      s += 2;
+      if (s >= STAGES) { s -= STAGES; ph ^= 1; }
+      as += 2;
+      if (as >= NACC) { as -= NACC; aph ^= 1; }
     }
   } else if (warp >= 4 && warp < 4 + SH_EPI_WARPS) {
-    // epilogue warp e = warp - 4: accumulator stage as = e / (4*SH_CG) (even / odd tiles), column group
+    // epilogue warp e = warp - 4: warp set eset = e / (4*SH_CG) (even / odd tiles; tile i sits in accumulator stage
+    // i % NACC, use number i / NACC), column group
     // cg = (e / 4) % SH_CG, TMEM lane quadrant ew = warp % 4 (a warp reaches only that quadrant)
     const int ew = warp & 3;
-    const int as = (warp - 4) / (4 * SH_CG);
+    const int eset = (warp - 4) / (4 * SH_CG);
     const int cg = ((warp - 4) >> 2) % SH_CG;
-    uint32_t aph = 0;
     if constexpr (KX > 1) {
       uint32_t par = 0;
-      for (int i = as; i < tile_count; i += 2) {
+      for (int i = eset; i < tile_count; i += 2) {
         const int tile = tile_first + i * tile_stride;
+        const int as = i % NACC;
+        const uint32_t aph = (uint32_t)(i / NACC) & 1u;
         const int ml = ew * 32 + lane;
         const uint32_t m = (uint32_t)tile * TSTEP + ml;
         const uint32_t t2 = p.fwg.div(m);
@@ -456,18 +507,18 @@ conv_shift_fwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_cons
 #pragma unroll
           for (int b = 1; b < KX; ++b) {
             if (lane < b) {
-              float* dst = s_xch[as * SH_CG + cg][par][ew][(b * (b - 1)) / 2 + lane];
+              float* dst = s_xch[eset * SH_CG + cg][par][ew][(b * (b - 1)) / 2 + lane];
 #pragma unroll
               for (int j = 0; j < XG; ++j)
 #pragma unroll
                 for (int i = 0; i < 16; ++i) dst[16 * j + i] = __uint_as_float(r[b][j][i]);
             }
           }
-          asm volatile("bar.sync %0, 128;" ::"r"(1 + as * SH_CG + cg) : "memory");
+          asm volatile("bar.sync %0, 128;" ::"r"(1 + eset * SH_CG + cg) : "memory");
 #pragma unroll
           for (int b = 1; b < KX; ++b) {
             const bool halo = lane >= 32 - b;
-            const float* src = s_xch[as * SH_CG + cg][par][(ew + 1) & 3][(b * (b - 1)) / 2 + (halo ? lane - (32 - b) : 0)];
+            const float* src = s_xch[eset * SH_CG + cg][par][(ew + 1) & 3][(b * (b - 1)) / 2 + (halo ? lane - (32 - b) : 0)];
 #pragma unroll
             for (int j = 0; j < XG; ++j)
 #pragma unroll
@@ -500,13 +551,14 @@ conv_shift_fwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_cons
         }
         tc_fence_before();
         mbar_arrive(&tempty_bar[as]);
-        aph ^= 1;
       }
     } else {
       // 16-column chunks handled together (loads in flight); the masked data gradient also holds the mask words
       constexpr int G = (DACT && SH_CG > 1) ? ((NCG >= 32) ? 2 : 1) : ((NCG >= 64) ? 4 : NCG / 16);
-      for (int i = as; i < tile_count; i += 2) {
+      for (int i = eset; i < tile_count; i += 2) {
         const int tile = tile_first + i * tile_stride;
+        const int as = i % NACC;
+        const uint32_t aph = (uint32_t)(i / NACC) & 1u;
         const uint32_t m = (uint32_t)tile * SH_BM + ew * 32 + lane;       // M < 2^31 (checked on the host)
         const uint32_t t2 = p.fwg.div(m);
         const int x = (int)(m - t2 * (uint32_t)p.Wg);
@@ -525,7 +577,7 @@ conv_shift_fwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_cons
         tc_fence_after();
         const uint32_t taddr0 = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(as * BN);
   #pragma unroll 1
-        for (int c0 = cg * NCG; c0 < (cg + 1) * NCG; c0 += 16 * G) {
+        for (int c0 = cg * NCG; c0 < ((p.debug & 4) ? 0 : (cg + 1) * NCG); c0 += 16 * G) {
           // activation-derivative mask of this lane's 16-column chunks as 1 bit per element (bit k <-> column c + k):
           // read as such (saved_bits: 2 B instead of 32 B of HBM traffic per chunk), or derived from the fp16 activation
           uint32_t mw[G];
@@ -588,7 +640,6 @@ conv_shift_fwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_cons
         }
         tc_fence_before();
         mbar_arrive(&tempty_bar[as]);
-        aph ^= 1;
       }
     }
   }
@@ -613,6 +664,7 @@ struct ShiftWgradParams {
   long long ldg;
   float alpha;
   int kb_total, kb_per_cta;
+  int debug;               // diagnostics (B200RL_CONV_DEBUG): 1 producers move no data, 2 no MMAs, 4 no bias sums
 };
 
 // KX > 1 ("x-fold", see the forward kernel): the accumulator holds G for one filter row a and all KX taps b of it,
@@ -628,7 +680,9 @@ conv_shift_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_co
   constexpr int BROWS = 64 + (KX - 1);                        // dY rows per stage (halo of KX - 1 rows in front)
   constexpr int B_BYTES = BROWS * BROWB;
   constexpr int B_REGION = (B_BYTES + 1023) & ~1023;
-  constexpr int STAGES = (KH == 1) ? 8 : (KX == 1 ? 6 : 5);
+  // uint8-fed: 16 stages of 64 rows -- a stage's round trip (tcgen05.commit -> producers / TMA wake -> HBM latency of
+  // the dY tile -> MMA) is ~2800 clocks, far more than its 4 MMAs; 8 stages left the kernel waiting on it
+  constexpr int STAGES = U8 ? 16 : (KH == 1) ? 8 : (KX == 1 ? 6 : 5);
   static_assert(!U8 || KH == 1, "the uint8-fed layer has 64 space-to-depth channels");
   // TMA-fed: stage = [A halves | B], 1024 B aligned.  uint8-fed: [rolling A ring (64-row tiles) | B stages]
   using Ring = U8Ring<64, STAGES>;
@@ -690,11 +744,25 @@ conv_shift_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_co
     }
   } else if (U8 && warp >= 8) {
     u8_ring_producer<64, STAGES>(p.u8, p.M, (long long)kb0 * 64, kb1 - kb0, smem, full_bar, head_bar, empty_bar,
-                                 warp - 8, lane);
+                                 warp - 8, lane, (p.debug & 1) != 0);
   } else if (warp == 1) {
     constexpr uint32_t IDESC = (1u << 4) | (1u << 15) | (1u << 16) | ((uint32_t)(NW >> 3) << 17) |
                                ((uint32_t)(SH_BM >> 4) << 24);
     {
+      // Descriptor words relative to the stage base, built once (see the forward kernel): A chunk pair j = accumulator
+      // rows of taps/halves (2j, 2j+1): start = shift of the first, LBO = distance to the second.  B (dY): KX == 1 one
+      // chunk (LBO unused); KX > 1: N-chunk j of the dY operand starts j rows further into the tile.
+      constexpr uint32_t HI_A = (uint32_t)(((1ull << 46) | (2ull << 61) | ((uint64_t)(1024 >> 4) << 32)) >> 32);
+      constexpr uint32_t HI_B = (uint32_t)(((1ull << 46) | ((uint64_t)LAYOUT_B << 61) | ((uint64_t)((8 * BROWB) >> 4) << 32)) >> 32);
+      constexpr uint32_t B_REL = (uint32_t)(((KX == 1 ? 64 * BROWB : BROWB) >> 4) & 0x3FFF) << 16;
+      auto a_rel_of = [&](int j) {
+        const int q0 = 2 * j, q1 = 2 * j + 1;
+        const uint32_t st0 = (uint32_t)((q0 % KH) * SH_WABYTES + p.shift[q0 / KH] * 128);
+        uint32_t lbo = 128;
+        if (q1 < nchunks) lbo = (uint32_t)((q1 % KH) * SH_WABYTES + p.shift[q1 / KH] * 128) - st0;
+        return (st0 >> 4) + (((lbo >> 4) & 0x3FFFu) << 16);
+      };
+      const uint32_t a_rel0 = a_rel_of(0), a_rel1 = n_mt > 1 ? a_rel_of(1) : 0u;   // the x-folded layers have n_mt <= 2
       int s = 0;
       uint32_t ph = 0;
       for (int kb = kb0; kb < kb1; ++kb) {
@@ -705,21 +773,19 @@ conv_shift_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_co
         }
         tc_fence_after();
         if (elect_one()) {
-        const uint32_t a_addr = smem_u32(smem + s * A_PITCH);
-        const uint32_t b_addr = smem_u32(smem + B_BASE + s * B_PITCH);
-        // KX == 1: one chunk (LBO unused).  KX > 1: N-chunk j of the dY operand starts j rows further into the tile
-        const uint64_t bdesc0 = make_sdesc(b_addr, KX == 1 ? 64 * BROWB : BROWB, 8 * BROWB, LAYOUT_B);
-        for (int j = 0; j < n_mt; ++j) {
-          const int q0 = 2 * j, q1 = 2 * j + 1;
-          const uint32_t st0 = a_addr + (q0 % KH) * SH_WABYTES + p.shift[q0 / KH] * 128;
-          uint32_t lbo = 128;
-          if (q1 < nchunks) lbo = (a_addr + (q1 % KH) * SH_WABYTES + p.shift[q1 / KH] * 128) - st0;
-          const uint64_t adesc0 = make_sdesc(st0, lbo, 1024, 2u);
-          const uint32_t td = tmem_base + (uint32_t)(j * NW);
+        const uint32_t a_base = (smem_u32(smem + s * A_PITCH) & 0x3FFFFu) >> 4;
+        const uint32_t b_lo = B_REL + ((smem_u32(smem + B_BASE + s * B_PITCH) & 0x3FFFFu) >> 4);
+        if (!(p.debug & 2)) {
+          const uint32_t accum = (kb > kb0) ? 1u : 0u;      // the CTA's first k-block overwrites the accumulators
+#pragma unroll 1
+          for (int j = 0; j < n_mt; ++j) {
+            const uint32_t a_lo = a_base + (j == 0 ? a_rel0 : (j == 1 ? a_rel1 : a_rel_of(j)));
+            const uint32_t td = tmem_base + (uint32_t)(j * NW);
+            umma_f16_lhp(td, a_lo, HI_A, b_lo, HI_B, IDESC, accum);
 #pragma unroll
-          for (int k = 0; k < 4; ++k)
-            umma_f16(td, adesc0 + (uint64_t)(k * (16 * 128 / 16)), bdesc0 + (uint64_t)(k * (16 * BROWB / 16)), IDESC,
-                     (kb > kb0 || k > 0) ? 1u : 0u);
+            for (int k = 1; k < 4; ++k)
+              umma_f16_lh<true>(td, a_lo + k * (16 * 128 / 16), HI_A, b_lo + k * (16 * BROWB / 16), HI_B, IDESC);
+          }
         }
         umma_commit(&empty_bar[s]);
         if (kb == kb1 - 1) umma_commit(done_bar);
@@ -747,7 +813,7 @@ conv_shift_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_co
         mbar_wait(&full_bar[s], ph);
         const uint8_t* sb = smem + B_BASE + s * B_PITCH;
 #pragma unroll 8
-        for (int r = rg + (KX - 1); r < 64 + (KX - 1); r += RG) {           // the halo rows belong to the previous block
+        for (int r = rg + (KX - 1); r < ((p.debug & 4) ? 0 : 64 + (KX - 1)); r += RG) {   // the halo rows belong to the previous block
           const int sw = (BROWB == 128) ? (r & 7) : ((r >> 1) & 3);
           const uint2 w = *reinterpret_cast<const uint2*>(sb + r * BROWB + ((chunk ^ sw) << 4) + within);
           a[0] += __half2float(__ushort_as_half((unsigned short)(w.x & 0xffffu)));
@@ -803,6 +869,13 @@ conv_shift_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_co
 }
 
 // ------------------------------------------------------------------------------------------------ host
+// Role-isolation diagnostics for tools/conv_roles.py: results are garbage when the mask is non-zero.  Read per call
+// (getenv is ~100 ns) so one process can time every mask.
+static int conv_debug_mask() {
+  const char* e = getenv("B200RL_CONV_DEBUG");
+  return e ? atoi(e) : 0;
+}
+
 static U8Src make_u8src(const void* x, const long long* idx, int H, int W, int C, int s) {
   U8Src u{};
   u.x = reinterpret_cast<const uint8_t*>(x);
@@ -819,8 +892,9 @@ static U8Src make_u8src(const void* x, const long long* idx, int H, int W, int C
 
 template <int BN, int KH, bool DACT, bool U8 = false, int KX = 1>
 static int launch_fwd(const CUtensorMap& tmX, const CUtensorMap& tmW, const ShiftParams& p, cudaStream_t st) {
-  constexpr int STAGES = (KH == 1) ? 6 : 3;
-  constexpr int SMEM = (U8 ? U8Ring<SH_BM, STAGES>::BYTES : STAGES * KH * SH_ABYTES) + 80 * 1024 + 1024 + 256;
+  constexpr int STAGES = sh_stages(KH);
+  constexpr int SMEM = (U8 ? U8Ring<SH_BM, STAGES>::BYTES : STAGES * KH * sh_arows(KH) * 128) + sh_wres_bytes(KH) + 1024 + 256;
+  static_assert(SMEM + 4096 <= 227 * 1024, "conv_shift_fwd: shared memory budget (+ static bias / exchange arrays)");
   static bool attr = false;
   auto kern = conv_shift_fwd_kernel<BN, KH, DACT, U8, KX>;
   if (!attr) {
@@ -839,11 +913,11 @@ static int launch_fwd(const CUtensorMap& tmX, const CUtensorMap& tmW, const Shif
 template <int BN, int KH, bool U8 = false, int KX = 1>
 static int launch_wgrad(const CUtensorMap& tmX, const CUtensorMap& tmD, const ShiftWgradParams& p, int grid,
                         cudaStream_t st) {
-  constexpr int STAGES = (KH == 1) ? 8 : (KX == 1 ? 6 : 5);
+  constexpr int STAGES = U8 ? 16 : (KH == 1) ? 8 : (KX == 1 ? 6 : 5);
   constexpr int BROWB = (BN >= 64) ? 128 : BN * 2;
   constexpr int B_REGION = ((64 + KX - 1) * BROWB + 1023) & ~1023;
   constexpr int SMEM =
-      (U8 ? U8Ring<64, STAGES>::BYTES + STAGES * B_REGION : STAGES * (KH * SH_WABYTES + B_REGION)) + 1024 + 256;
+      (U8 ? U8Ring<64, STAGES>::BYTES + STAGES * B_REGION : STAGES * (KH * SH_WABYTES + B_REGION)) + 1024 + 512;
   static_assert(SMEM <= 227 * 1024, "conv_shift_wgrad: shared memory budget");
   static bool attr = false;
   auto kern = conv_shift_wgrad_kernel<BN, KH, U8, KX>;
@@ -888,11 +962,12 @@ int conv_shift_fwd_impl(const void* X, long long B, int Hg, int Wg, int C, const
   B200RL_REQUIRE(C == 64 || C == 128, "conv_shift_fwd: C must be 64 or 128 (got %d)", C);
   B200RL_REQUIRE(N == 32 || N == 64 || N == 128, "conv_shift_fwd: N must be 32, 64 or 128 (got %d)", N);
   B200RL_REQUIRE(taps >= 1 && taps <= SH_MAX_TAPS, "conv_shift_fwd: 1..%d taps", SH_MAX_TAPS);
-  B200RL_REQUIRE((long long)taps * (C / 64) * kx * N * 128 <= 80 * 1024, "conv_shift_fwd: weights do not fit in smem");
+  B200RL_REQUIRE((C == 64 || C == 128) && (long long)taps * (C / 64) * kx * N * 128 <= sh_wres_bytes(C / 64),
+                 "conv_shift_fwd: weights do not fit in smem");
   ShiftParams p = {};
   int lo = shifts[0], hi = shifts[0];
   for (int t = 1; t < taps; ++t) { lo = shifts[t] < lo ? shifts[t] : lo; hi = shifts[t] > hi ? shifts[t] : hi; }
-  B200RL_REQUIRE(hi - lo <= SH_AROWS - SH_BM, "conv_shift_fwd: shift span %d too large", hi - lo);
+  B200RL_REQUIRE(hi - lo <= sh_arows(C / 64) - SH_BM, "conv_shift_fwd: shift span %d too large for C = %d", hi - lo, C);
   B200RL_REQUIRE(B * Hg * Wg < (1LL << 31) - 4096, "conv_shift_fwd: too many rows");
   p.M = B * Hg * Wg; p.Hg = Hg; p.Wg = Wg; p.N = N; p.taps = taps; p.min_shift = lo;
   for (int t = 0; t < taps; ++t) p.shift[t] = shifts[t] - lo;
@@ -914,6 +989,7 @@ int conv_shift_fwd_impl(const void* X, long long B, int Hg, int Wg, int C, const
   p.tstep = SH_BM - (kx - 1);
   p.num_tiles = (int)((p.M + p.tstep - 1) / p.tstep);
   p.u8 = make_u8src(u8_x, u8_idx, u8_H, u8_W, u8_C, u8_s);
+  p.debug = conv_debug_mask();
   B200RL_REQUIRE(Hg >= 2 && Wg >= 2, "conv_shift_fwd: grid must be at least 2x2");
   p.fwg = make_fastdiv((uint32_t)Wg);
   p.fhg = make_fastdiv((uint32_t)Hg);
@@ -926,7 +1002,7 @@ int conv_shift_fwd_impl(const void* X, long long B, int Hg, int Wg, int C, const
     B200RL_REQUIRE(hi - lo <= 32, "conv_shift_fwd: uint8-fed shift span %d exceeds one 32-row unit", hi - lo);
     return launch_fwd<32, 1, false, true>(tmW, tmW, p, stream);
   }
-  if ((rc = make_tmap_2d_f16(&tmX, X, p.M, C, C, 64, SH_AROWS)) != 0) return rc;
+  if ((rc = make_tmap_2d_f16(&tmX, X, p.M, C, C, 64, sh_arows(C / 64))) != 0) return rc;
   const int KH = C / 64;
   if (kx > 1) {
     if (kx == 2 && N == 32 && KH == 1) return launch_fwd<64, 1, false, false, 2>(tmX, tmW, p, stream);
@@ -981,6 +1057,7 @@ int conv_shift_wgrad_impl(const void* X, long long rows, int C, const void* dY, 
   p.kb_per_cta = (p.kb_total + ctas - 1) / ctas;
   const int grid = (p.kb_total + p.kb_per_cta - 1) / p.kb_per_cta;
   p.u8 = make_u8src(u8_x, u8_idx, u8_H, u8_W, u8_C, u8_s);
+  p.debug = conv_debug_mask();
   CUtensorMap tmX, tmD;
   int rc;
   if ((rc = make_tmap_2d_f16(&tmD, dY, rows, N, N, N < 64 ? N : 64, 64 + kx - 1)) != 0) return rc;

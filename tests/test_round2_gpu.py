@@ -596,8 +596,13 @@ def test_cuda_graph_replay_equals_eager_launch_sequence():
     assert np.array_equal(out["eager"][0][0], out["graphs"][0][0])
     spread = max(float(np.abs(out["eager"][1][k] - out["eager2"][1][k]).max()) for k in out["eager"][1])
     diff = max(float(np.abs(out["eager"][1][k] - out["graphs"][1][k]).max()) for k in out["eager"][1])
-    print(f"params: eager-vs-eager spread {spread:.2e}, graphs-vs-eager {diff:.2e}")
-    assert diff <= 4 * spread + 1e-6, (diff, spread)
+    # the maximum over 1.7 M parameters is a heavy-tailed statistic of two samples; the mean difference is the stable one
+    n = sum(v.size for v in out["eager"][1].values())
+    mspread = sum(float(np.abs(out["eager"][1][k] - out["eager2"][1][k]).sum()) for k in out["eager"][1]) / n
+    mdiff = sum(float(np.abs(out["eager"][1][k] - out["graphs"][1][k]).sum()) for k in out["eager"][1]) / n
+    print(f"params: eager-vs-eager spread {spread:.2e} (mean {mspread:.2e}), graphs-vs-eager {diff:.2e} (mean {mdiff:.2e})")
+    assert mdiff <= 2 * mspread + 1e-8, (mdiff, mspread)
+    assert diff <= 10 * spread + 1e-6, (diff, spread)
     sspread = float(np.abs(out["eager"][2] - out["eager2"][2]).max())
     sdiff = float(np.abs(out["eager"][2] - out["graphs"][2]).max())
     assert sdiff <= 4 * sspread + 1e-5, (sdiff, sspread)
@@ -641,8 +646,12 @@ def test_dqn_graph_replay_equals_eager():
     # later steps: float-atomic gradient order + Adam's early +-lr steps; compare against the eager-vs-eager spread
     spread = max(float(np.abs(res["eager"][2][k] - res["eager2"][2][k]).max()) for k in res["eager"][2])
     diff = max(float(np.abs(res["eager"][2][k] - res["graphs"][2][k]).max()) for k in res["eager"][2])
-    print(f"dqn params: eager-vs-eager spread {spread:.2e}, graphs-vs-eager {diff:.2e}")
-    assert diff <= 4 * spread + 1e-6, (diff, spread)
+    n = sum(v.size for v in res["eager"][2].values())
+    mspread = sum(float(np.abs(res["eager"][2][k] - res["eager2"][2][k]).sum()) for k in res["eager"][2]) / n
+    mdiff = sum(float(np.abs(res["eager"][2][k] - res["graphs"][2][k]).sum()) for k in res["eager"][2]) / n
+    print(f"dqn params: eager-vs-eager spread {spread:.2e} (mean {mspread:.2e}), graphs-vs-eager {diff:.2e} (mean {mdiff:.2e})")
+    assert mdiff <= 2 * mspread + 1e-8, (mdiff, mspread)
+    assert diff <= 10 * spread + 1e-6, (diff, spread)
 
 
 def test_chunked_upload_pipeline_equals_unchunked_rollout():
