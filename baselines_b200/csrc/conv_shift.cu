@@ -37,8 +37,12 @@ static constexpr int SH_THREADS = 256;             // wgrad: TMA, MMA, TMEM allo
 // polling = ~3400 warp instructions per 128-row tile), so a second column group only adds per-warp overhead and
 // polling warps: SH_CG = 2 was 3-6 % slower than 1 on all three layers.
 static constexpr int SH_CG = 1;
-static constexpr int SH_EPI_WARPS = 2 * SH_CG * 4;
-static constexpr int SH_FWD_THREADS = 128 + SH_EPI_WARPS * 32;
+// Epilogue warp sets of the forward kernel (4 warps x SH_CG each; set e takes the tiles i = e mod sets).  The uint8-fed
+// layer has four: its epilogue's tcgen05.ld queues behind the other tile's MMAs, and with two sets that wait was on
+// the critical path (tools/conv_roles.py: MMA + epilogue alone took the sum of their times).
+__host__ __device__ constexpr int sh_epi_sets(bool u8) { return u8 ? 4 : 2; }
+__host__ __device__ constexpr int sh_epi_warps(bool u8) { return sh_epi_sets(u8) * SH_CG * 4; }
+__host__ __device__ constexpr int sh_fwd_threads(bool u8) { return 128 + sh_epi_warps(u8) * 32 + (u8 ? 256 : 0); }
 static constexpr int SH_MAX_TAPS = 16;
 // rows of one TMA-fed A stage: 128 + the largest shift span.  64-channel inputs: span <= 32.  128-channel inputs (two
 // halves per stage): span <= 16, so that FOUR stages fit beside the weights -- the stage count must be even, because
@@ -46,6 +50,7 @@ static constexpr int SH_MAX_TAPS = 16;
 // every other phase of an mbarrier could mistake an old phase of that parity for the one it waits for).
 __host__ __device__ constexpr int sh_arows(int KH) { return KH == 1 ? 160 : 144; }
 __host__ __device__ constexpr int sh_stages(int KH) { return KH == 1 ? 6 : 4; }
+__host__ __device__ constexpr int sh_wgrad_krows(bool u8) { return u8 ? 128 : 64; }   // wgrad: reduction rows per stage
 // resident-weight region of the forward kernel (all taps): 80 KB beside 64-channel stages, 64 KB beside 128-channel ones
 __host__ __device__ constexpr int sh_wres_bytes(int KH) { return KH == 1 ? 80 * 1024 : 64 * 1024; }
 static constexpr int SH_WROWS_K = 96;                // wgrad: 64 + max shift span (<= 32)
@@ -142,10 +147,9 @@ __device__ __forceinline__ void u8x16_to_f16(const uint4& q, uint4& lo, uint4& h
 //
 // Work unit = 32 consecutive grid rows (one warp, lane = row); unit u of the CTA covers rows row_start + 32u ...,
 // belongs to tile u / UPT, and the units are dealt round-robin to the U8_WARPS producer warps.  Each warp keeps
-// U8_DEPTH units of loads in flight in registers (the sample index of the gather is looked up one round earlier).
+// D units of loads in flight in registers (the sample index of the gather is looked up one round earlier).
 // Barriers per stage: full (UPT unit arrivals [+ the TMA of the other operand]), head (the first unit alone: the
 // tile in the PREVIOUS stage waits for it), empty (tcgen05.commit of the tile's MMAs).
-static constexpr int U8_DEPTH = 3;
 
 __device__ __forceinline__ uint4 ldg_stream_v4(const void* p) {
   uint4 v;
@@ -190,12 +194,12 @@ __device__ __forceinline__ void u8_load(const U8Src& u, long long row_start, int
   }
 }
 
-template <int TR, int STAGES>
+template <int TR, int STAGES, int D>
 __device__ __forceinline__ void u8_ring_producer(const U8Src& u, long long M, long long row_start, int ntiles,
                                                  uint8_t* ring, uint64_t* full_bar, uint64_t* head_bar,
                                                  uint64_t* empty_bar, int pw, int lane, bool dry = false) {
   using R = U8Ring<TR, STAGES>;
-  constexpr int UPT = R::UPT, D = U8_DEPTH, RND = U8_WARPS * D;
+  constexpr int UPT = R::UPT, RND = U8_WARPS * D;
   if (ntiles <= 0) return;
   if (dry) M = 0;                                        // diagnostics: every row "outside the matrix": no loads
   const int total = ntiles * UPT + 1;                    // + the head unit the last tile reads into
@@ -290,7 +294,7 @@ struct ShiftParams {
 // out[m, n] = sum_b D[m + b, b*N + n] (warp shuffle by b lanes; the last b lanes of a warp take the rows from the next
 // warp through a tiny smem exchange; tiles overlap by KX - 1 rows so nothing crosses a tile).
 template <int BN, int KH, bool DACT, bool U8, int KX>
-__global__ void __launch_bounds__(SH_FWD_THREADS + (U8 ? U8_THREADS : 0), 1)
+__global__ void __launch_bounds__(sh_fwd_threads(U8), 1)
 conv_shift_fwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW,
                       const __grid_constant__ ShiftParams p) {
   static_assert(KX == 1 || !DACT, "the data gradient keeps one MMA group per tap");
@@ -310,6 +314,8 @@ conv_shift_fwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_cons
   // data movement and math removed still runs at ~40 % of the full kernel's time), so two stages leave the tensor core
   // idle; four hide it.  Two epilogue warp sets still alternate over the tiles.
   constexpr int NACC = (BN <= 128) ? 4 : 2;
+  constexpr int NSETS = sh_epi_sets(U8), EPI_WARPS = sh_epi_warps(U8);
+  static_assert(NACC % NSETS == 0, "each epilogue set owns its accumulator stages' barriers");
   constexpr int TMEM_COLS = (NACC * BN <= 64) ? 64 : (NACC * BN <= 128) ? 128 : (NACC * BN <= 256) ? 256 : 512;
   static_assert(NACC * BN <= 512, "accumulator stages exceed TMEM");
   extern __shared__ uint8_t smem_raw[];
@@ -331,7 +337,7 @@ conv_shift_fwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_cons
   static_assert(NCG % 16 == 0, "column groups are whole 16-column chunks");
   constexpr int XG = (KX == 2 && NCG >= 32) ? 2 : 1;                  // 16-column chunks combined per exchange round
   constexpr int XROWS = (KX * (KX - 1)) / 2;                          // sum_b b halo rows per warp
-  __shared__ float s_xch[(KX > 1) ? 2 * SH_CG : 1][2][4][(KX > 1) ? XROWS : 1][16 * XG];
+  __shared__ float s_xch[(KX > 1) ? NSETS * SH_CG : 1][2][4][(KX > 1) ? XROWS : 1][16 * XG];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x < NO) s_bias[threadIdx.x] = (p.bias && (int)threadIdx.x < p.N) ? p.bias[threadIdx.x] : 0.0f;
   if (warp == 0 && lane == 0) {
@@ -395,10 +401,10 @@ conv_shift_fwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_cons
         if (++s == STAGES) { s = 0; ph ^= 1; }
       }
     }
-  } else if (U8 && warp >= 4 + SH_EPI_WARPS) {
-    // uint8 producer warps
-    u8_ring_producer<SH_BM, STAGES>(p.u8, p.M, (long long)tile_first * SH_BM + p.min_shift, tile_count, smem, full_bar,
-                                    head_bar, empty_bar, warp - (4 + SH_EPI_WARPS), lane, (p.debug & 1) != 0);
+  } else if (U8 && warp >= 4 + EPI_WARPS) {
+    // uint8 producer warps (2 units of loads in flight each: 896 threads leave 72 registers)
+    u8_ring_producer<SH_BM, STAGES, 2>(p.u8, p.M, (long long)tile_first * SH_BM + p.min_shift, tile_count, smem,
+                                       full_bar, head_bar, empty_bar, warp - (4 + EPI_WARPS), lane, (p.debug & 1) != 0);
   } else if (warp == 1 || warp == 3) {
     // TWO MMA-issuing warps, even / odd tiles.  tcgen05.mma issue is not fire-and-forget at this size: the issuing thread
     // stalls on the (shallow) MMA queue, so with one issuer the per-tile barrier waits + commits (~430 clocks, measured
@@ -470,7 +476,7 @@ conv_shift_fwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_cons
       as += 2;
       if (as >= NACC) { as -= NACC; aph ^= 1; }
     }
-  } else if (warp >= 4 && warp < 4 + SH_EPI_WARPS) {
+  } else if (warp >= 4 && warp < 4 + EPI_WARPS) {
     // epilogue warp e = warp - 4: warp set eset = e / (4*SH_CG) (even / odd tiles; tile i sits in accumulator stage
     // i % NACC, use number i / NACC), column group
     // cg = (e / 4) % SH_CG, TMEM lane quadrant ew = warp % 4 (a warp reaches only that quadrant)
@@ -479,7 +485,7 @@ conv_shift_fwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_cons
     const int cg = ((warp - 4) >> 2) % SH_CG;
     if constexpr (KX > 1) {
       uint32_t par = 0;
-      for (int i = eset; i < tile_count; i += 2) {
+      for (int i = eset; i < tile_count; i += NSETS) {
         const int tile = tile_first + i * tile_stride;
         const int as = i % NACC;
         const uint32_t aph = (uint32_t)(i / NACC) & 1u;
@@ -555,7 +561,7 @@ conv_shift_fwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_cons
     } else {
       // 16-column chunks handled together (loads in flight); the masked data gradient also holds the mask words
       constexpr int G = (DACT && SH_CG > 1) ? ((NCG >= 32) ? 2 : 1) : ((NCG >= 64) ? 4 : NCG / 16);
-      for (int i = eset; i < tile_count; i += 2) {
+      for (int i = eset; i < tile_count; i += NSETS) {
         const int tile = tile_first + i * tile_stride;
         const int as = i % NACC;
         const uint32_t aph = (uint32_t)(i / NACC) & 1u;
@@ -677,16 +683,18 @@ conv_shift_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_co
                         const __grid_constant__ ShiftWgradParams p) {
   constexpr int BROWB = (BN >= 64) ? 128 : BN * 2;            // dY row bytes in smem
   constexpr uint32_t LAYOUT_B = (BROWB == 64) ? 4u : 2u;
-  constexpr int BROWS = 64 + (KX - 1);                        // dY rows per stage (halo of KX - 1 rows in front)
+  // reduction rows per pipeline stage ("k-block").  uint8-fed: 128 -- with 64 the single TMA-issuing thread's
+  // wait / expect_tx / issue sequence per stage (~300 clocks, tools/conv_roles.py) was the kernel's floor
+  constexpr int KR = sh_wgrad_krows(U8);
+  constexpr int BROWS = KR + (KX - 1);                        // dY rows per stage (halo of KX - 1 rows in front)
   constexpr int B_BYTES = BROWS * BROWB;
   constexpr int B_REGION = (B_BYTES + 1023) & ~1023;
-  // uint8-fed: 16 stages of 64 rows -- a stage's round trip (tcgen05.commit -> producers / TMA wake -> HBM latency of
-  // the dY tile -> MMA) is ~2800 clocks, far more than its 4 MMAs; 8 stages left the kernel waiting on it
-  constexpr int STAGES = U8 ? 16 : (KH == 1) ? 8 : (KX == 1 ? 6 : 5);
+  constexpr int STAGES = (KH == 1) ? 8 : 6;
   static_assert(!U8 || KH == 1, "the uint8-fed layer has 64 space-to-depth channels");
+  static_assert(STAGES % 2 == 0, "each MMA-issuing warp owns alternate stages");
   // TMA-fed: stage = [A halves | B], 1024 B aligned.  uint8-fed: [rolling A ring (64-row tiles) | B stages]
-  using Ring = U8Ring<64, STAGES>;
-  constexpr int A_PITCH = U8 ? 64 * 128 : KH * SH_WABYTES + B_REGION;
+  using Ring = U8Ring<KR, STAGES>;
+  constexpr int A_PITCH = U8 ? KR * 128 : KH * SH_WABYTES + B_REGION;
   constexpr int B_PITCH = U8 ? B_REGION : KH * SH_WABYTES + B_REGION;
   constexpr int B_BASE = U8 ? Ring::BYTES : KH * SH_WABYTES;
   constexpr int SMEM_TILES = U8 ? Ring::BYTES + STAGES * B_REGION : STAGES * (KH * SH_WABYTES + B_REGION);
@@ -705,6 +713,12 @@ conv_shift_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_co
   const int kb1 = min(kb0 + p.kb_per_cta, p.kb_total);
   const int nchunks = p.taps * KH;                  // 64-row chunks of the accumulator rows
   const int n_mt = (nchunks + 1) / 2;               // 128-row accumulator tiles
+  // Two MMA-issuing warps (1 and 3) take the even / odd k-blocks when a second set of accumulators fits in TMEM (see the
+  // forward kernel: the issuing thread stalls on the MMA queue, so one issuer's barrier waits add to its MMAs).  Each
+  // accumulates into its own TMEM columns; the epilogue adds the two.
+  const int acc_cols = n_mt * NW;
+  const bool two = (2 * acc_cols <= 512) && (kb1 - kb0 >= 2);
+  const int nissue = two ? 2 : 1;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmX);
@@ -713,11 +727,14 @@ conv_shift_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_co
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(&full_bar[s], U8 ? 1 + Ring::UPT : 1);
-      mbar_init(&empty_bar[s], p.gbias ? 2 : 1);
+      // ring with two issuers: a stage is free when its own k-block AND the one before it (which read this stage's head
+      // rows and belongs to the other issuer) are done
+      mbar_init(&empty_bar[s], (p.gbias ? 2 : 1) + ((U8 && two) ? 1 : 0));
       if (U8) mbar_init(&head_bar[s], 1);
     }
-    mbar_init(done_bar, 1);
+    mbar_init(done_bar, nissue);
     fence_barrier_init();
+    if (U8 && two) mbar_arrive(&empty_bar[0]);               // stands in for "the k-block before" the CTA's first one
   }
   if (warp == 2) tmem_alloc<512>(tmem_slot);
   tc_fence_before();
@@ -735,26 +752,27 @@ conv_shift_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_co
         mbar_arrive_expect_tx(&full_bar[s], (uint32_t)((U8 ? 0 : KH * SH_WABYTES) + B_BYTES));
         if (!U8) {
 #pragma unroll
-          for (int h = 0; h < KH; ++h) tma_load_2d(sa + h * SH_WABYTES, &tmX, &full_bar[s], h * 64, kb * 64);
+          for (int h = 0; h < KH; ++h) tma_load_2d(sa + h * SH_WABYTES, &tmX, &full_bar[s], h * 64, kb * KR);
         }
-        tma_load_2d(smem + B_BASE + s * B_PITCH, &tmD, &full_bar[s], 0, kb * 64 - (KX - 1));   // negative rows: zero fill
+        tma_load_2d(smem + B_BASE + s * B_PITCH, &tmD, &full_bar[s], 0, kb * KR - (KX - 1));   // negative rows: zero fill
       }
       __syncwarp();
       if (++s == STAGES) { s = 0; ph ^= 1; }
     }
   } else if (U8 && warp >= 8) {
-    u8_ring_producer<64, STAGES>(p.u8, p.M, (long long)kb0 * 64, kb1 - kb0, smem, full_bar, head_bar, empty_bar,
+    u8_ring_producer<KR, STAGES, 3>(p.u8, p.M, (long long)kb0 * KR, kb1 - kb0, smem, full_bar, head_bar, empty_bar,
                                  warp - 8, lane, (p.debug & 1) != 0);
-  } else if (warp == 1) {
+  } else if (warp == 1 || warp == 3) {
     constexpr uint32_t IDESC = (1u << 4) | (1u << 15) | (1u << 16) | ((uint32_t)(NW >> 3) << 17) |
                                ((uint32_t)(SH_BM >> 4) << 24);
-    {
+    const int iss = warp >> 1;
+    if (iss < nissue) {
       // Descriptor words relative to the stage base, built once (see the forward kernel): A chunk pair j = accumulator
       // rows of taps/halves (2j, 2j+1): start = shift of the first, LBO = distance to the second.  B (dY): KX == 1 one
       // chunk (LBO unused); KX > 1: N-chunk j of the dY operand starts j rows further into the tile.
       constexpr uint32_t HI_A = (uint32_t)(((1ull << 46) | (2ull << 61) | ((uint64_t)(1024 >> 4) << 32)) >> 32);
       constexpr uint32_t HI_B = (uint32_t)(((1ull << 46) | ((uint64_t)LAYOUT_B << 61) | ((uint64_t)((8 * BROWB) >> 4) << 32)) >> 32);
-      constexpr uint32_t B_REL = (uint32_t)(((KX == 1 ? 64 * BROWB : BROWB) >> 4) & 0x3FFF) << 16;
+      constexpr uint32_t B_REL = (uint32_t)(((KX == 1 ? KR * BROWB : BROWB) >> 4) & 0x3FFF) << 16;
       auto a_rel_of = [&](int j) {
         const int q0 = 2 * j, q1 = 2 * j + 1;
         const uint32_t st0 = (uint32_t)((q0 % KH) * SH_WABYTES + p.shift[q0 / KH] * 128);
@@ -763,35 +781,36 @@ conv_shift_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_co
         return (st0 >> 4) + (((lbo >> 4) & 0x3FFFu) << 16);
       };
       const uint32_t a_rel0 = a_rel_of(0), a_rel1 = n_mt > 1 ? a_rel_of(1) : 0u;   // the x-folded layers have n_mt <= 2
-      int s = 0;
+      int s = iss;
       uint32_t ph = 0;
-      for (int kb = kb0; kb < kb1; ++kb) {
+      const uint32_t tmem_acc = tmem_base + (uint32_t)(iss * acc_cols);
+      for (int kb = kb0 + iss; kb < kb1; kb += nissue) {
+        const int s1 = (s + 1 == STAGES) ? 0 : s + 1;
         mbar_wait(&full_bar[s], ph);
-        if (U8) {                                          // the shifted taps read into the first unit of the next block
-          const int s1 = (s + 1 == STAGES) ? 0 : s + 1;
-          mbar_wait(&head_bar[s1], s1 == 0 ? ph ^ 1 : ph);
-        }
+        if (U8) mbar_wait(&head_bar[s1], s1 == 0 ? ph ^ 1 : ph);   // the shifted taps read into the next block's first unit
         tc_fence_after();
         if (elect_one()) {
         const uint32_t a_base = (smem_u32(smem + s * A_PITCH) & 0x3FFFFu) >> 4;
         const uint32_t b_lo = B_REL + ((smem_u32(smem + B_BASE + s * B_PITCH) & 0x3FFFFu) >> 4);
         if (!(p.debug & 2)) {
-          const uint32_t accum = (kb > kb0) ? 1u : 0u;      // the CTA's first k-block overwrites the accumulators
+          const uint32_t accum = (kb > kb0 + iss) ? 1u : 0u;   // the issuer's first k-block overwrites its accumulators
 #pragma unroll 1
           for (int j = 0; j < n_mt; ++j) {
             const uint32_t a_lo = a_base + (j == 0 ? a_rel0 : (j == 1 ? a_rel1 : a_rel_of(j)));
-            const uint32_t td = tmem_base + (uint32_t)(j * NW);
+            const uint32_t td = tmem_acc + (uint32_t)(j * NW);
             umma_f16_lhp(td, a_lo, HI_A, b_lo, HI_B, IDESC, accum);
 #pragma unroll
-            for (int k = 1; k < 4; ++k)
+            for (int k = 1; k < KR / 16; ++k)
               umma_f16_lh<true>(td, a_lo + k * (16 * 128 / 16), HI_A, b_lo + k * (16 * BROWB / 16), HI_B, IDESC);
           }
         }
         umma_commit(&empty_bar[s]);
-        if (kb == kb1 - 1) umma_commit(done_bar);
+        if (U8 && two) umma_commit(&empty_bar[s1]);
+        if (kb + nissue >= kb1) umma_commit(done_bar);
         }
         __syncwarp();
-        if (++s == STAGES) { s = 0; ph ^= 1; }
+        s += nissue;
+        if (s >= STAGES) { s -= STAGES; ph ^= 1; }
       }
     }
   } else if (warp >= 4 && warp < 8) {
@@ -813,7 +832,7 @@ conv_shift_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_co
         mbar_wait(&full_bar[s], ph);
         const uint8_t* sb = smem + B_BASE + s * B_PITCH;
 #pragma unroll 8
-        for (int r = rg + (KX - 1); r < ((p.debug & 4) ? 0 : 64 + (KX - 1)); r += RG) {   // the halo rows belong to the previous block
+        for (int r = rg + (KX - 1); r < ((p.debug & 4) ? 0 : KR + (KX - 1)); r += RG) {   // the halo rows belong to the previous block
           const int sw = (BROWB == 128) ? (r & 7) : ((r >> 1) & 3);
           const uint2 w = *reinterpret_cast<const uint2*>(sb + r * BROWB + ((chunk ^ sw) << 4) + within);
           a[0] += __half2float(__ushort_as_half((unsigned short)(w.x & 0xffffu)));
@@ -847,6 +866,13 @@ conv_shift_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_co
         for (int c = 0; c < NW; c += 16) {
           uint32_t r[16];
           tmem_ld16(tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(j * NW + c), r);
+          if (two) {
+            uint32_t r2[16];
+            tmem_ld16(tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(acc_cols + j * NW + c), r2);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 16; ++i) r[i] = __float_as_uint(__uint_as_float(r[i]) + __uint_as_float(r2[i]));
+          }
           tmem_ld_wait();
           const int jb = c / BN, cn = c - jb * BN;
           if (row < mrows && cn < p.N) {
@@ -906,18 +932,19 @@ static int launch_fwd(const CUtensorMap& tmX, const CUtensorMap& tmW, const Shif
     attr = true;
   }
   const int grid = p.num_tiles < device_num_sms() ? p.num_tiles : device_num_sms();
-  kern<<<grid, SH_FWD_THREADS + (U8 ? U8_THREADS : 0), SMEM, st>>>(tmX, tmW, p);
+  kern<<<grid, sh_fwd_threads(U8), SMEM, st>>>(tmX, tmW, p);
   return check_launch("conv_shift_fwd_kernel");
 }
 
 template <int BN, int KH, bool U8 = false, int KX = 1>
 static int launch_wgrad(const CUtensorMap& tmX, const CUtensorMap& tmD, const ShiftWgradParams& p, int grid,
                         cudaStream_t st) {
-  constexpr int STAGES = U8 ? 16 : (KH == 1) ? 8 : (KX == 1 ? 6 : 5);
+  constexpr int STAGES = (KH == 1) ? 8 : 6;
+  constexpr int KR = sh_wgrad_krows(U8);
   constexpr int BROWB = (BN >= 64) ? 128 : BN * 2;
-  constexpr int B_REGION = ((64 + KX - 1) * BROWB + 1023) & ~1023;
+  constexpr int B_REGION = ((KR + KX - 1) * BROWB + 1023) & ~1023;
   constexpr int SMEM =
-      (U8 ? U8Ring<64, STAGES>::BYTES + STAGES * B_REGION : STAGES * (KH * SH_WABYTES + B_REGION)) + 1024 + 512;
+      (U8 ? U8Ring<KR, STAGES>::BYTES + STAGES * B_REGION : STAGES * (KH * SH_WABYTES + B_REGION)) + 1024 + 512;
   static_assert(SMEM <= 227 * 1024, "conv_shift_wgrad: shared memory budget");
   static bool attr = false;
   auto kern = conv_shift_wgrad_kernel<BN, KH, U8, KX>;
@@ -1050,7 +1077,8 @@ int conv_shift_wgrad_impl(const void* X, long long rows, int C, const void* dY, 
   }
   p.M = rows; p.N = N; p.taps = taps; p.G = G; p.ldg = ldg; p.alpha = alpha;
   p.gbias = gbias; p.alpha_b = alpha_b;
-  p.kb_total = (int)((rows + 63) / 64);
+  const int KR = sh_wgrad_krows(u8_x != nullptr);
+  p.kb_total = (int)((rows + KR - 1) / KR);
   int ctas = device_num_sms();
   if (max_ctas > 0 && max_ctas < ctas) ctas = max_ctas;
   if (ctas > p.kb_total) ctas = p.kb_total;
@@ -1060,7 +1088,7 @@ int conv_shift_wgrad_impl(const void* X, long long rows, int C, const void* dY, 
   p.debug = conv_debug_mask();
   CUtensorMap tmX, tmD;
   int rc;
-  if ((rc = make_tmap_2d_f16(&tmD, dY, rows, N, N, N < 64 ? N : 64, 64 + kx - 1)) != 0) return rc;
+  if ((rc = make_tmap_2d_f16(&tmD, dY, rows, N, N, N < 64 ? N : 64, KR + kx - 1)) != 0) return rc;
   if (u8_x) {
     if (kx == 2) return launch_wgrad<32, 1, true, 2>(tmD, tmD, p, grid, stream);
     B200RL_REQUIRE(kx == 1, "conv_shift_wgrad: the uint8-fed first layer supports kx = 1 or 2");
