@@ -12,11 +12,11 @@
 //   conv_shift_wgrad_kernel (MN-major): G[t, c, n] += alpha * sum_m X[m + sh_t, c] * dY[m, n]         wgrad
 //                                       (all taps' accumulators live in TMEM at once; X and dY are read once)
 //
-// Warp roles (forward, 384 threads [+256]): 0 TMA loads (weights once, A tile per tile) | 1 and 3 MMA issue (elect.sync)
-// for the even / odd tiles | 2 TMEM alloc | 4-7 / 8-11 epilogue sets for the even / odd tiles (4 TMEM accumulator
-// stages) | 12-19 (first layer only) uint8 producer warps that cast raw frames into a rolling A ring instead of the
-// TMA.  wgrad (256 threads [+256]): 0 TMA | 1 MMA |
-// 2 TMEM | 3 spare | 4-7 fused bias-gradient sums during the main loop, then the epilogue | 8-15 uint8 producers.
+// Warp roles (forward, 384 threads; uint8-fed first layer 896): 0 TMA loads (weights once, A tile per tile) | 1 and 3
+// MMA issue (elect.sync) for the even / odd tiles | 2 TMEM alloc | 4-7 / 8-11 epilogue sets for the even / odd tiles
+// (4 TMEM accumulator stages; first layer: four sets, warps 4-19) | first layer only: the last 8 warps are uint8
+// producers that cast raw frames into a rolling A ring instead of the TMA.  wgrad (256 threads [+256]): 0 TMA | 1 and 3 MMA issue for the even / odd k-blocks (own accumulators each, when two
+// sets fit in TMEM) | 2 TMEM | 4-7 fused bias-gradient sums during the main loop, then the epilogue | 8-15 uint8 producers.
 // The forward epilogue can also write 1 bit per output element (act > 0); the dgrad of the next layer reads that
 // instead of the fp16 activation.
 //
