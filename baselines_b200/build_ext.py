@@ -19,12 +19,27 @@ def _nvcc():
     raise RuntimeError("nvcc not found; libb200rl needs the CUDA toolkit to build")
 
 
+STAMP = LIB + ".srchash"
+
+
+def _source_hash():
+    """Content hash of everything the library is built from.  (File times do not survive the copy to a GPU box in
+    order, so an mtime comparison rebuilt the library there at random -- a minute of nvcc inside a measurement run.)"""
+    import hashlib
+    h = hashlib.sha256(" ".join(NVCC_FLAGS + SOURCES).encode())
+    deps = sorted(os.path.join(CSRC, f) for f in os.listdir(CSRC)) + [os.path.join(HERE, "..", "include", "b200rl.h")]
+    for d in deps:
+        h.update(os.path.basename(d).encode())
+        with open(d, "rb") as f:
+            h.update(f.read())
+    return h.hexdigest()
+
+
 def needs_build():
-    if not os.path.exists(LIB):
+    if not os.path.exists(LIB) or not os.path.exists(STAMP):
         return True
-    t = os.path.getmtime(LIB)
-    deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC)] + [os.path.join(HERE, "..", "include", "b200rl.h")]
-    return any(os.path.getmtime(d) > t for d in deps)
+    with open(STAMP) as f:
+        return f.read().strip() != _source_hash()
 
 
 def build(force=False, verbose=False):
@@ -50,6 +65,8 @@ def build(force=False, verbose=False):
         raise RuntimeError("nvcc failed building libb200rl")
     cmd = [nvcc, "-shared", "-o", LIB] + objs + ["-lcudart"]
     subprocess.check_call(cmd)
+    with open(STAMP, "w") as f:
+        f.write(_source_hash() + "\n")
     return LIB
 
 
