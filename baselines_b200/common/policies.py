@@ -224,16 +224,16 @@ class PolicyNet:
         B = t.shape[0]
         return t.reshape(B, -1).to(torch.float32).to(self.device, non_blocking=True).contiguous()
 
-    def forward(self, x, B, src_idx=None):
-        """Towers + heads for B samples of x (optionally gathered through src_idx)."""
-        lat, ldl = self.tower_pi.forward(x, B, src_idx)
+    def forward(self, x, B, src_idx=None, masks=True):
+        """Towers + heads for B samples of x (optionally gathered through src_idx); masks=False: no backward follows."""
+        lat, ldl = self.tower_pi.forward(x, B, src_idx, masks=masks)
         self._lat_pi, self._ld_lat_pi = lat, ldl
         if self.head is not None:
             self.head.forward(lat, ldl, B, self.headout, self.ld_ho, mode=ops.MODE_F32_STORE)
         else:
             # the value tower of value_network='copy' reads the same observations: encode them once
             enc = self.tower_pi.x0 if self.tower_pi.kind == "mlp" else None
-            latv, ldlv = self.tower_vf.forward(x, B, src_idx, encoded=enc)
+            latv, ldlv = self.tower_vf.forward(x, B, src_idx, encoded=enc, masks=masks)
             self._lat_vf, self._ld_lat_vf = latv, ldlv
             self.head_pi.forward(lat, ldl, B, self.pi_out, self.ld_pi, mode=ops.MODE_F32_STORE)
             self.head_vf.forward(latv, ldlv, B, self.v_out, self.ld_v, mode=ops.MODE_F32_STORE)
@@ -242,7 +242,7 @@ class PolicyNet:
         """PolicyWithValue.step (policies.py:77-96) into caller-provided device tensors.  The sampler's stream position
         is a device counter advanced after every pass, so the sequence can be replayed from a CUDA graph."""
         _lib.phase = "@act"
-        self.forward(x, B)
+        self.forward(x, B, masks=False)
         if self.discrete:
             ops.cat_step(self.pi_out, self.ld_pi, self.nout, self.v_out, self.ld_v, actions, values, neglogp, B,
                          uniforms=noise, seed=seed, offset_dev=self.rng_ctr)

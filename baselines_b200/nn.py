@@ -504,7 +504,7 @@ class Tower:
             for t in range(taps):                      # wd[:, t*nf:(t+1)*nf] = fp16(W[t*Cg:(t+1)*Cg, :])
                 ops.cast_transpose(c.w[t * Cg:(t + 1) * Cg], Cg, nf, self.wd[i][:, t * nf:], taps * nf, None, 0)
 
-    def _forward_shift(self, x, B, src_idx):
+    def _forward_shift(self, x, B, src_idx, masks=True):
         cv, sg = self.convs, self.sg
         c0 = cv[0]
         if self.fused_u8:
@@ -524,12 +524,12 @@ class Tower:
             if g["kx_fwd"] > 1:
                 ops.conv_shift_fwd(cur, B, g["Hg"], g["Wg"], g["Cg"], self.wfold[i], g["k"] * g["Cg"], c.nf,
                                    g["yshifts"], c.OH, c.OW, self.hconv[i], omap, bias=c.b, act=c.act,
-                                   tag="fwd." + c.name, u8=self._u8 if i == 0 else None, bits_out=self.hbits[i],
+                                   tag="fwd." + c.name, u8=self._u8 if i == 0 else None, bits_out=self.hbits[i] if masks else None,
                                    useful_rows=B * c.OH * c.OW, kx=g["kx_fwd"])
             else:
                 ops.conv_shift_fwd(cur, B, g["Hg"], g["Wg"], g["Cg"], c.w_fwd, c.Kp, c.nf, g["shifts"], c.OH, c.OW,
                                    self.hconv[i], omap, bias=c.b, act=c.act, tag="fwd." + c.name,
-                                   u8=self._u8 if i == 0 else None, bits_out=self.hbits[i],
+                                   u8=self._u8 if i == 0 else None, bits_out=self.hbits[i] if masks else None,
                                    useful_rows=B * c.OH * c.OW)
             cur = self.hconv[i]
         return cur, self.flat
@@ -563,11 +563,12 @@ class Tower:
             self._refresh_shift()
 
     # x: uint8 [*,H,W,C] images (cnn) or fp16 [*, in_pad] rows (mlp); src_idx gathers samples from it
-    def forward(self, x, B, src_idx=None, encoded=None):
-        """encoded (mlp only): operand rows another tower already produced from the same observations."""
+    def forward(self, x, B, src_idx=None, encoded=None, masks=True):
+        """encoded (mlp only): operand rows another tower already produced from the same observations.
+        masks=False (acting passes: no backward follows): the convs skip their 1-bit ReLU mask output."""
         assert B <= self.cap
         if self.convs and self.shift_mode:
-            h, ldh = self._forward_shift(x, B, src_idx)
+            h, ldh = self._forward_shift(x, B, src_idx, masks)
         elif self.convs:
             cur = x
             for i, c in enumerate(self.convs):

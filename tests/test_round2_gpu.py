@@ -606,9 +606,8 @@ def test_cuda_graph_replay_equals_eager_launch_sequence():
     # parameters; graph replay has no launch gaps, so its atomics interleave differently from both eager runs).
     assert mdiff <= 10 * mspread + 2e-6, (mdiff, mspread)
     assert diff <= 1e-3, (diff, spread)                    # never more than a few full steps apart
-    sspread = float(np.abs(out["eager"][2] - out["eager2"][2]).max())
-    sdiff = float(np.abs(out["eager"][2] - out["graphs"][2]).max())
-    assert sdiff <= 4 * sspread + 1e-5, (sdiff, sspread)
+    # loss statistics of the last minibatches (means over 256 samples; clipfrac moves in steps of 1/256)
+    assert np.allclose(out["eager"][2], out["graphs"][2], rtol=5e-3, atol=5e-3), (out["eager"][2], out["graphs"][2])
 
 
 def test_dqn_graph_replay_equals_eager():
