@@ -31,11 +31,9 @@
 namespace b200rl {
 
 static constexpr int SH_BM = 128;
-static constexpr int SH_THREADS = 256;             // wgrad: TMA, MMA, TMEM alloc, spare, 4 epilogue warps
-// forward: 2 accumulator stages x SH_CG column groups x 4 lane quadrants of epilogue warps.  Measured (ncu,
-// profiles/r2_ncu_conv_fwd.md): these kernels are bound by warp-instruction issue (epilogue + uint8 producers + barrier
-// polling = ~3400 warp instructions per 128-row tile), so a second column group only adds per-warp overhead and
-// polling warps: SH_CG = 2 was 3-6 % slower than 1 on all three layers.
+static constexpr int SH_THREADS = 256;             // wgrad: TMA, MMA, TMEM alloc, MMA, 4 bias-sum / epilogue warps
+// forward: epilogue sets x SH_CG column groups x 4 lane quadrants of epilogue warps.  A second column group was
+// measured 3-6 % slower on all three layers (profiles/r2_ncu_conv_fwd_xfold_cg2.md: per-warp overhead, more waiting warps).
 static constexpr int SH_CG = 1;
 // Epilogue warp sets of the forward kernel (4 warps x SH_CG each; set e takes the tiles i = e mod sets).  The uint8-fed
 // layer has four: its epilogue's tcgen05.ld queues behind the other tile's MMAs, and with two sets that wait was on
@@ -141,9 +139,9 @@ __device__ __forceinline__ void u8x16_to_f16(const uint4& q, uint4& lo, uint4& h
 // absolute shared-memory address) instead of re-building a halo per tile.  The buffer ends with one extra 32-row
 // unit that mirrors the first unit of stage 0, so the tile in the last stage can read past the end.
 //
-// Shared memory bandwidth (128 B/clk, shared by the tensor core's operand fetch and the LSU) is what bounds these
-// kernels (profiles/r2_ncu_convs.md: wavefronts + SS operand fetch add up to the tile time), so the raw bytes go
-// global -> registers -> cast -> one swizzled store: no staging copy in shared memory.
+// The raw bytes go global -> registers -> cast -> one swizzled store: no staging copy in shared memory (the port is
+// shared with the tensor core's SS operand fetch, which wins the arbitration), and no 25-50 % of halo rows cast twice.
+// What bounds the producers is measured in profiles/r2_conv_roles.md (not load latency: depth 2, 3, 4 time the same).
 //
 // Work unit = 32 consecutive grid rows (one warp, lane = row); unit u of the CTA covers rows row_start + 32u ...,
 // belongs to tile u / UPT, and the units are dealt round-robin to the U8_WARPS producer warps.  Each warp keeps
