@@ -126,6 +126,29 @@ class PolicyNet:
             self.tower_vf.materialize()
         f32 = dict(dtype=torch.float32, device=dev)
         f16 = dict(dtype=torch.float16, device=dev)
+        # value_network='copy' with mlp towers: both first layers read the same encoded observations, by far the largest
+        # operand of the network (cfg-3: 403 MB per chunk against 34 MB of hidden activations).  They run as ONE GEMM
+        # with N = 2 * hidden (forward) and ONE weight-gradient GEMM: the two Linear objects keep their own fp32
+        # parameters (checkpoint names / layouts unchanged); their fp16 forward operands, outputs and output gradients
+        # are the two halves of shared buffers.
+        tp, tv = self.tower_pi, self.tower_vf
+        import os
+        self.fuse0 = bool(tv is not None and tp.kind == "mlp" and os.environ.get("B200RL_NO_FUSE_FC0", "0") != "1" and
+                          tp.fcs[0].N == tv.fcs[0].N and tp.fcs[0].K == tv.fcs[0].K and
+                          tp.fcs[0].act == tv.fcs[0].act and 2 * tp.fcs[0].N in (64, 128, 256))
+        if self.fuse0:
+            a, b = tp.fcs[0], tv.fcs[0]
+            N = a.N
+            self.w0cat = torch.zeros(2 * N, a.Kf, **f16)
+            a.w_fwd, b.w_fwd = self.w0cat[:N], self.w0cat[N:]
+            self.h0cat = torch.empty(cap, 2 * N, **f16)
+            self.dz0cat = torch.empty(cap, 2 * N, **f16)
+            for t, c0 in ((tp, 0), (tv, N)):
+                t.hfc[0], t.dzfc[0], t.ld_hfc[0] = self.h0cat[:, c0:c0 + N], self.dz0cat[:, c0:c0 + N], 2 * N
+                if len(t.fcs) == 1:
+                    t.dlatent, t.ld_dlatent = t.dzfc[0], 2 * N
+            self.b0cat = torch.zeros(2 * N, **f32)
+            self.g0cat = torch.zeros(a.K, 2 * N, **f32)
         if self.head is not None:
             self.head.materialize()
             self.ld_ho = _pad(self.nout + 1, 16)
@@ -192,6 +215,10 @@ class PolicyNet:
         else:
             self._refresh_other()
         self._cast_plan.run()
+        if self.fuse0:                                     # the fused first layer's bias operand [b_pi | b_vf]
+            N = self.tower_pi.fcs[0].N
+            self.b0cat[:N].copy_(self.tower_pi.fcs[0].b)
+            self.b0cat[N:].copy_(self.tower_vf.fcs[0].b)
 
     def _refresh_other(self):
         """Operand refreshes that are not cast_transpose jobs (they ran eagerly while the plan was recorded)."""
@@ -226,6 +253,18 @@ class PolicyNet:
 
     def forward(self, x, B, src_idx=None, masks=True):
         """Towers + heads for B samples of x (optionally gathered through src_idx); masks=False: no backward follows."""
+        if self.fuse0:
+            tp, tv = self.tower_pi, self.tower_vf
+            a = tp.fcs[0]
+            enc = tp.encode(x, B, src_idx)
+            ops.gemm(enc, self.w0cat, self.h0cat, M=B, N=2 * a.N, K=a.Kp + a.K, lda=2 * tp.in_pad, ldb=a.Kf,
+                     ldc=2 * a.N, bias=self.b0cat, mode=ops.MODE_F16_ACT, act=a.act, tag="fwd.pi+vf/mlp_fc0")
+            lat, ldl = tp.forward(x, B, src_idx, encoded=enc, skip_first=True)
+            latv, ldlv = tv.forward(x, B, src_idx, encoded=enc, skip_first=True)
+            self._lat_pi, self._ld_lat_pi, self._lat_vf, self._ld_lat_vf = lat, ldl, latv, ldlv
+            self.head_pi.forward(lat, ldl, B, self.pi_out, self.ld_pi, mode=ops.MODE_F32_STORE)
+            self.head_vf.forward(latv, ldlv, B, self.v_out, self.ld_v, mode=ops.MODE_F32_STORE)
+            return
         lat, ldl = self.tower_pi.forward(x, B, src_idx, masks=masks)
         self._lat_pi, self._ld_lat_pi = lat, ldl
         if self.head is not None:
@@ -250,6 +289,25 @@ class PolicyNet:
             ops.gauss_step(self.pi_out, self.ld_pi, self.logstd, self.nout, self.v_out, self.ld_v, actions, values,
                            neglogp, B, normals=noise, seed=seed, offset_dev=self.rng_ctr)
         ops.counter_add(self.rng_ctr, 1)
+
+    def _fused_first_wgrad(self, B, alpha):
+        """[gW_pi | gW_vf] += alpha * x^T [dz_pi | dz_vf]: the encoded observations are read once (twice with the lo half)
+        instead of once per tower; the result is split into the two parameters' gradient views."""
+        tp, tv = self.tower_pi, self.tower_vf
+        a, b = tp.fcs[0], tv.fcs[0]
+        N2, x, ldx = 2 * a.N, tp._mlp_in, 2 * tp.in_pad
+        bn = 256 if N2 == 256 else (128 if N2 > 64 else 64)
+        tiles = -(-a.K // 128) * -(-N2 // bn)
+        kb = -(-B // 64)
+        split = max(1, min(kb // 2 if kb >= 2 else 1, -(-296 // tiles)))
+        self.g0cat.zero_()
+        for xs in ((x, x[:, a.Kp:]) if a.split_in else (x,)):
+            ops.gemm(xs, self.dz0cat, self.g0cat, M=a.K, N=N2, K=B, lda=ldx, ldb=N2, ldc=N2, mn_major=True,
+                     mode=ops.MODE_F32_ATOMIC, alpha=alpha * a.in_scale, split_k=split, tag="wgrad.pi+vf/mlp_fc0")
+        a.gw.add_(self.g0cat[:, :a.N])
+        b.gw.add_(self.g0cat[:, a.N:])
+        ops.colsum(tp.dzfc[0], a.gb, B, a.N, N2, alpha=alpha)
+        ops.colsum(tv.dzfc[0], b.gb, B, b.N, N2, alpha=alpha)
 
     def loss_backward(self, x, B, src_idx, actions, returns, old_values, old_neglogp, cliprange, ent_coef, vf_coef,
                       inv_M):
@@ -280,8 +338,10 @@ class PolicyNet:
             self.head_pi.wgrad(self._lat_pi, self._ld_lat_pi, self.dpi, self.ld_dpi, B, inv_M)
             self.head_pi.dgrad(self.dpi, self.ld_dpi, B, tp.dlatent, tp.ld_dlatent, saved=self._lat_pi,
                                ld_saved=self._ld_lat_pi, act=tp.latent_act)
-            tp.backward(B, inv_M)
+            tp.backward(B, inv_M, skip_first_wgrad=self.fuse0)
             self.head_vf.wgrad(self._lat_vf, self._ld_lat_vf, self.dv, self.ld_dv, B, inv_M)
             self.head_vf.dgrad(self.dv, self.ld_dv, B, tv.dlatent, tv.ld_dlatent, saved=self._lat_vf,
                                ld_saved=self._ld_lat_vf, act=tv.latent_act)
-            tv.backward(B, inv_M)
+            tv.backward(B, inv_M, skip_first_wgrad=self.fuse0)
+            if self.fuse0:
+                self._fused_first_wgrad(B, inv_M)

@@ -412,6 +412,7 @@ class Tower:
             self._materialize_shift(f16)
             self.hfc = [torch.empty(cap, l.Np, **f16) for l in self.fcs]
             self.dzfc = [torch.empty(cap, l.Np, **f16) for l in self.fcs]
+            self.ld_hfc = [l.Np for l in self.fcs]     # row pitch of hfc[i] / dzfc[i]
             if self.fcs:
                 self.dlatent, self.ld_dlatent = self.dzfc[-1], self.fcs[-1].Np
             else:
@@ -435,6 +436,7 @@ class Tower:
             self.x16 = torch.empty(cap, c0.H * c0.W * c0.C, **f16)     # gathered uint8 -> fp16 observations
         self.hfc = [torch.empty(cap, l.Np, **f16) for l in self.fcs]
         self.dzfc = [torch.empty(cap, l.Np, **f16) for l in self.fcs]
+        self.ld_hfc = [l.Np for l in self.fcs]         # row pitch of hfc[i] / dzfc[i] (a fused first layer widens [0])
         if self.kind == "mlp":
             self.x0 = torch.zeros(cap, 2 * self.in_pad, **f16)      # [hi | lo] operand rows of the float32 observations
         # where the heads write d(loss)/d(latent pre-activation)
@@ -563,9 +565,18 @@ class Tower:
             self._refresh_shift()
 
     # x: uint8 [*,H,W,C] images (cnn) or fp16 [*, in_pad] rows (mlp); src_idx gathers samples from it
-    def forward(self, x, B, src_idx=None, encoded=None, masks=True):
+    def encode(self, x, B, src_idx=None):
+        """mlp: float32 rows (optionally gathered through src_idx) -> encoded fp16 [hi | lo] operand rows in x0."""
+        nm = self.obs_norm
+        ops.obs_encode(x, self.x0, B, self.raw_dim, self.in_dim, self.in_pad, src_idx=src_idx,
+                       mean=nm[0] if nm else None, inv_std=nm[1] if nm else None,
+                       clip=(nm[2], nm[3]) if nm else (0.0, 0.0), onehot_n=self.onehot_n)
+        return self.x0
+
+    def forward(self, x, B, src_idx=None, encoded=None, masks=True, skip_first=False):
         """encoded (mlp only): operand rows another tower already produced from the same observations.
-        masks=False (acting passes: no backward follows): the convs skip their 1-bit ReLU mask output."""
+        masks=False (acting passes: no backward follows): the convs skip their 1-bit ReLU mask output.
+        skip_first (mlp only): hfc[0] was already produced by a fused first layer (common/policies.py)."""
         assert B <= self.cap
         if self.convs and self.shift_mode:
             h, ldh = self._forward_shift(x, B, src_idx, masks)
@@ -592,27 +603,27 @@ class Tower:
             h, ldh = cur, self.flat                      # [B, OH*OW*C] view of the NHWC activation (H,W,C order)
         else:
             # float32 rows (optionally gathered through src_idx) -> encoded fp16 [hi | lo] operand rows
-            nm = self.obs_norm
             if encoded is None:
-                ops.obs_encode(x, self.x0, B, self.raw_dim, self.in_dim, self.in_pad, src_idx=src_idx,
-                               mean=nm[0] if nm else None, inv_std=nm[1] if nm else None,
-                               clip=(nm[2], nm[3]) if nm else (0.0, 0.0), onehot_n=self.onehot_n)
-                encoded = self.x0
+                encoded = self.encode(x, B, src_idx)
             h, ldh = encoded, 2 * self.in_pad
             self._mlp_in = h
         for i, l in enumerate(self.fcs):
-            l.forward(h, ldh, B, self.hfc[i], l.Np)
-            h, ldh = self.hfc[i], l.Np
+            if not (skip_first and i == 0):
+                l.forward(h, ldh, B, self.hfc[i], self.ld_hfc[i])
+            h, ldh = self.hfc[i], self.ld_hfc[i]
         return h, ldh                                    # latent [B, latent_dim] fp16, row pitch ldh
 
     # consumes self.dlatent: fp16 [B, ld_dlatent] gradient w.r.t. the latent PRE-activation
-    def backward(self, B, alpha):
+    def backward(self, B, alpha, skip_first_wgrad=False):
+        """skip_first_wgrad (mlp): the caller computes the first layer's weight gradient (fused over two towers)."""
         nfc = len(self.fcs)
         dz, lddz = self.dlatent, self.ld_dlatent
         for i in reversed(range(nfc)):
             l = self.fcs[i]
+            if i == 0 and skip_first_wgrad and not self.convs:
+                return
             if i > 0:
-                xin, ldx, act_in = self.hfc[i - 1], self.fcs[i - 1].Np, self.fcs[i - 1].act
+                xin, ldx, act_in = self.hfc[i - 1], self.ld_hfc[i - 1], self.fcs[i - 1].act
             elif self.convs:
                 xin, ldx, act_in = self.hconv[-1], self.flat, ops.ACT_RELU
             else:
@@ -621,7 +632,7 @@ class Tower:
             if act_in is None:
                 return
             if i > 0:
-                out, ldo = self.dzfc[i - 1], self.fcs[i - 1].Np
+                out, ldo = self.dzfc[i - 1], self.ld_hfc[i - 1]
                 l.dgrad(dz, lddz, B, out, ldo, saved=xin, ld_saved=ldx, act=act_in)
             elif self.shift_mode:
                 cL, gL = self.convs[-1], self.sg[-1]
