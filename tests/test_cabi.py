@@ -55,3 +55,22 @@ def test_ops_refuse_cpu_tensors():
     a = torch.zeros(8, 8, dtype=torch.float16)
     with pytest.raises(RuntimeError):
         ops.gemm(a, a, a, M=8, N=8, K=8, lda=8, ldb=8, ldc=8)
+
+
+def test_rebuild_decision_follows_source_content_not_file_times(tmp_path):
+    """build_ext.needs_build(): a GPU box receives the tree with arbitrary file times, so the decision is a content hash
+    of csrc/ + include/b200rl.h + the nvcc flags, stamped beside the library."""
+    from baselines_b200 import build_ext
+    _lib_path()
+    assert not build_ext.needs_build()
+    src = os.path.join(build_ext.CSRC, "gae.cu")
+    st = os.stat(build_ext.LIB)
+    os.utime(src, (st.st_atime + 1000, st.st_mtime + 1000))            # "newer" source, same content
+    assert not build_ext.needs_build()
+    stamp = open(build_ext.STAMP).read()
+    try:
+        open(build_ext.STAMP, "w").write("0" * 64 + "\n")              # stale stamp = sources changed since the build
+        assert build_ext.needs_build()
+    finally:
+        open(build_ext.STAMP, "w").write(stamp)
+    assert not build_ext.needs_build()
